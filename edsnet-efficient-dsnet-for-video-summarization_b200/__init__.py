@@ -1,0 +1,13 @@
+"""edsnet_b200 -- B200 (sm_100a) implementation of EDSNet's anchor-based scoring path.
+
+Public surface:
+  DSNet            drop-in for the reference's `anchor_based.dsnet.DSNet` (nystromformer + roi pooling)
+  BatchPlan        packed variable-length batch tables
+  shard_videos     video-wise partition across ranks (no collective on the data path)
+  ScoringPipeline  host-buffer -> proposals throughput path (pinned H2D / compute / D2H overlapped)
+"""
+from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
+from .dsnet import DSNet, NystromAttention                      # noqa: F401
+from .pipeline import ScoringPipeline                            # noqa: F401
+
+__all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

@@ -1,0 +1,376 @@
+// C ABI of libedsnet_b200.so -- see include/edsnet_b200.h for the contract of every entry point.
+#include "../../include/edsnet_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
+#include "nystrom.cuh"
+#include "tail.cuh"
+#include "decode_nms.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return EDSNET_E_CUDA;
+}
+#define CU_CHECK(expr, where)                                   \
+    do {                                                        \
+        cudaError_t e__ = (expr);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where);   \
+    } while (0)
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int check_cfg(const edsnet_config* cfg) {
+    if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
+    if (cfg->n_scales < 1 || cfg->n_scales > EDSNET_MAX_SCALES)
+        return fail(EDSNET_E_ARG, "n_scales must be in 1..8");
+    for (int i = 0; i < cfg->n_scales; ++i) {
+        const int s = cfg->scales[i];
+        if (s < 2 || s > 128) return fail(EDSNET_E_ARG, "anchor scale out of range 2..128");
+        // anchor_based/dsnet.py:113-115: with an odd scale AvgPool1d yields T outputs, [:-1] leaves T-1 and the
+        // reference's .view(seq_len, num_scales) raises.  Same failure surface here.
+        if (s & 1) return fail(EDSNET_E_ARG, "odd anchor scale: the reference's view() fails for odd scales");
+    }
+    if (cfg->fc_depth < 0 || cfg->fc_depth > 64) return fail(EDSNET_E_ARG, "fc_depth out of range 0..64");
+    if (cfg->precision < EDSNET_PREC_FP32 || cfg->precision > EDSNET_PREC_FP16)
+        return fail(EDSNET_E_ARG, "unknown precision");
+    return EDSNET_OK;
+}
+
+int check_batch(const edsnet_batch* b) {
+    if (!b) return fail(EDSNET_E_ARG, "batch is NULL");
+    if (b->n_videos < 1 || b->total_rows < 1 || b->max_rows < 1) return fail(EDSNET_E_ARG, "empty batch");
+    if (!b->cu_rows || !b->tiles64 || !b->tiles128) return fail(EDSNET_E_ARG, "batch tables are NULL");
+    if (b->n_videos > 65535) return fail(EDSNET_E_ARG, "at most 65535 videos per call");
+    return EDSNET_OK;
+}
+
+ScaleList make_scales(const edsnet_config* cfg, int* halo) {
+    ScaleList sl;
+    sl.n = cfg->n_scales;
+    int mx = 0;
+    for (int i = 0; i < kMaxScales; ++i) {
+        sl.s[i] = i < cfg->n_scales ? cfg->scales[i] : 0;
+        if (sl.s[i] > mx) mx = sl.s[i];
+    }
+    *halo = mx / 2;
+    return sl;
+}
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, const float* B, const void* B16,
+                  float* C, int M, int N, int K, const float* bias, const float* res, int qcols, cudaStream_t st) {
+    if (M < 1 || N < 1 || K < 1) return fail(EDSNET_E_ARG, "gemm: empty problem");
+    if (epilogue < 0 || epilogue > 3) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
+    if ((epilogue >= 2 && !bias) || (epilogue == 3 && !res)) return fail(EDSNET_E_ARG, "gemm: epilogue operand is NULL");
+    GemmEpiArgs ep{bias, res, N, qcols};
+    if (precision == EDSNET_PREC_FP32) {
+        if (!A || !B || !C) return fail(EDSNET_E_ARG, "gemm: NULL operand");
+        if (K % kGemmBK || N % 4) return fail(EDSNET_E_ARG, "gemm fp32: K must be a multiple of 16, N of 4");
+        cudaError_t e;
+        switch (epilogue) {
+            case 0: e = launch_sgemm_nt<EPI_NONE>(A, K, B, K, C, N, M, N, K, ep, st); break;
+            case 1: e = launch_sgemm_nt<EPI_QSCALE>(A, K, B, K, C, N, M, N, K, ep, st); break;
+            case 2: e = launch_sgemm_nt<EPI_BIAS>(A, K, B, K, C, N, M, N, K, ep, st); break;
+            default: e = launch_sgemm_nt<EPI_BIAS_RES>(A, K, B, K, C, N, M, N, K, ep, st); break;
+        }
+        CU_CHECK(e, "sgemm_nt_kernel");
+        return EDSNET_OK;
+    }
+    if (!A16 || !B16 || !C) return fail(EDSNET_E_ARG, "gemm tcgen05: fp16 operand planes are NULL");
+    std::string msg;
+    cudaError_t e = launch_gemm_tc(precision == EDSNET_PREC_FP16X3 ? 3 : 1, epilogue,
+                                   reinterpret_cast<const __half*>(A16), reinterpret_cast<const __half*>(B16),
+                                   C, M, N, K, ep, st, &msg);
+    if (e != cudaSuccess) {
+        g_err = "gemm_tc: " + (msg.empty() ? std::string(cudaGetErrorString(e)) : msg);
+        return EDSNET_E_CUDA;
+    }
+    return EDSNET_OK;
+}
+
+int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv_w, float* q_land, float* k_land,
+                      float* attn2, float* stats, float* a3v, float* zmat, float* wmat, float* merged,
+                      cudaStream_t st) {
+    static bool attrs_done = false;     // per-process; the attribute is per device function
+    if (!attrs_done) {
+        CU_CHECK(opt_in_smem(a3v_kernel, kA3vSmem), "smem opt-in a3v");
+        CU_CHECK(opt_in_smem(pinv_w_kernel, kPinvSmem), "smem opt-in pinv");
+        CU_CHECK(opt_in_smem(attn_out_kernel, kAttnOutSmem), "smem opt-in attn_out");
+        attrs_done = true;
+    }
+    const int V = b->n_videos;
+    landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
+    CU_CHECK(cudaGetLastError(), "landmarks_kernel");
+    attn2_kernel<<<dim3(kHeads, V), 256, 0, st>>>(q_land, k_land, attn2, stats);
+    CU_CHECK(cudaGetLastError(), "attn2_kernel");
+    a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
+    CU_CHECK(cudaGetLastError(), "a3v_kernel");
+    pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+    CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
+    attn_out_kernel<<<dim3(b->n_tiles64, kHeads), 256, kAttnOutSmem, st>>>(
+        qkv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles64), k_land, wmat, conv_w, merged);
+    CU_CHECK(cudaGetLastError(), "attn_out_kernel");
+    return EDSNET_OK;
+}
+
+int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out, int rows,
+                  cudaStream_t st) {
+    static bool attrs_done = false;
+    if (!attrs_done) {
+        CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
+        attrs_done = true;
+    }
+    fc_stack_kernel<<<(rows + 63) / 64, 256, kFcStackSmem, st>>>(u_in, w->fcb_w, w->fcb_b, w->fcb_ln_w,
+                                                                  w->fcb_ln_b, u_out, rows, cfg->fc_depth);
+    CU_CHECK(cudaGetLastError(), "fc_stack_kernel");
+    return EDSNET_OK;
+}
+
+int roi_impl(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* b, const float* u,
+             float* pred_cls, float* pred_loc, cudaStream_t st) {
+    int halo = 0;
+    ScaleList sl = make_scales(cfg, &halo);
+    const int smem = (128 + 2 * halo) * kHidden * (int)sizeof(float);
+    static int opted = 0;
+    if (smem > opted) {
+        CU_CHECK(opt_in_smem(roi_pool_heads_kernel, smem), "smem opt-in roi_pool_heads");
+        opted = smem;
+    }
+    roi_pool_heads_kernel<<<b->n_tiles128, 256, smem, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
+                                                             sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
+                                                             pred_cls, pred_loc);
+    CU_CHECK(cudaGetLastError(), "roi_pool_heads_kernel");
+    return EDSNET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* edsnet_last_error(void) { return g_err.c_str(); }
+int edsnet_abi_version(void) { return EDSNET_ABI_VERSION; }
+
+size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos,
+                              edsnet_workspace_layout* layout) {
+    edsnet_workspace_layout L;
+    std::memset(&L, 0, sizeof(L));
+    const size_t R = (size_t)(total_rows > 0 ? total_rows : 0), V = (size_t)(n_videos > 0 ? n_videos : 0);
+    const size_t head_mat = V * kHeads * 4096 * sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    L.qkv = take(R * kQkvCols * sizeof(float));
+    L.yn = L.qkv;                                    // LayerNorm output reuses the (dead) qkv region
+    L.q_land = take(head_mat);
+    L.k_land = take(head_mat);
+    L.attn2 = take(head_mat);
+    L.stats = take(V * kHeads * 2 * sizeof(float));
+    L.a3v = take(head_mat);
+    L.zmat = take(head_mat);
+    L.wmat = take(head_mat);
+    L.merged = take(R * kInner * sizeof(float));
+    L.y = take(R * kFeat * sizeof(float));
+    L.u0 = take(R * kHidden * sizeof(float));
+    L.u1 = take(R * kHidden * sizeof(float));
+    L.x16 = off;
+    if (cfg && cfg->precision != EDSNET_PREC_FP32) take(2 * R * kFeat * sizeof(__half));
+    L.total = off;
+    if (layout) *layout = L;
+    return L.total;
+}
+
+int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream) {
+    if (!src || !dst_hi_lo || rows < 1 || cols < 1 || (cols & 3)) return fail(EDSNET_E_ARG, "split_f16: bad argument");
+    cudaError_t e = launch_split_f16(src, reinterpret_cast<__half*>(dst_hi_lo), (size_t)rows * (size_t)cols,
+                                     static_cast<cudaStream_t>(stream));
+    CU_CHECK(e, "split_f16_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_debug_tc_status(int32_t reset) {
+    int flag = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&flag, tc::g_timeout_flag, sizeof(int));
+    if (e != cudaSuccess) { cuda_fail(e, "tc status read"); return -1; }
+    if (reset && flag) {
+        const int zero = 0;
+        e = cudaMemcpyToSymbol(tc::g_timeout_flag, &zero, sizeof(int));
+        if (e != cudaSuccess) { cuda_fail(e, "tc status reset"); return -1; }
+    }
+    return flag;
+}
+
+int edsnet_debug_set_tc_variant(int32_t variant) {
+    if (variant < 0 || variant > 1) return fail(EDSNET_E_ARG, "tc variant must be 0 or 1");
+    tc::variant_ref() = variant;
+    return EDSNET_OK;
+}
+
+int edsnet_gemm(int32_t precision, int32_t epilogue, const float* A, const void* A16, const float* B,
+                const void* B16, float* C, int32_t M, int32_t N, int32_t K, const float* bias, const float* res,
+                int32_t qcols, void* stream) {
+    return gemm_dispatch(precision, epilogue, A, A16, B, B16, C, M, N, K, bias, res, qcols,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int edsnet_nystrom_core(const edsnet_batch* batch, const float* qkv, const float* res_conv_w, float* q_land,
+                        float* k_land, float* attn2, float* stats, float* a3v, float* zmat, float* wmat,
+                        float* merged, void* stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (!qkv || !res_conv_w || !q_land || !k_land || !attn2 || !stats || !a3v || !wmat || !merged)
+        return fail(EDSNET_E_ARG, "nystrom_core: NULL operand");
+    return nystrom_core_impl(batch, qkv, res_conv_w, q_land, k_land, attn2, stats, a3v, zmat, wmat, merged,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int edsnet_fc_stack(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out,
+                    int32_t rows, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!w || !u_in || !u_out || rows < 1) return fail(EDSNET_E_ARG, "fc_stack: bad argument");
+    return fc_stack_impl(cfg, w, u_in, u_out, rows, static_cast<cudaStream_t>(stream));
+}
+
+int edsnet_roi_pool_heads(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch,
+                          const float* u, float* pred_cls, float* pred_loc, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!w || !u || !pred_cls || !pred_loc) return fail(EDSNET_E_ARG, "roi_pool_heads: NULL operand");
+    return roi_impl(cfg, w, batch, u, pred_cls, pred_loc, static_cast<cudaStream_t>(stream));
+}
+
+int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
+                   float* pred_cls, float* pred_loc, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!w || !x || !pred_cls || !pred_loc || !workspace) return fail(EDSNET_E_ARG, "forward: NULL operand");
+    edsnet_workspace_layout L;
+    const size_t need = edsnet_workspace_bytes(cfg, batch->total_rows, batch->n_videos, &L);
+    if (workspace_bytes < need) return fail(EDSNET_E_WORKSPACE, "forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    const int R = batch->total_rows;
+    const int prec = cfg->precision;
+    const void* x16 = nullptr;
+    if (prec != EDSNET_PREC_FP32) {
+        if (!w->to_qkv_w16 || !w->to_out_w16 || !w->fc1_w16)
+            return fail(EDSNET_E_ARG, "forward: tcgen05 precision needs the fp16 weight planes (edsnet_split_f16)");
+        rc = edsnet_split_f16(x, ws + L.x16, R, kFeat, stream);
+        if (rc) return rc;
+        x16 = ws + L.x16;
+    }
+    // 1. qkv = x Wqkv^T, q pre-scaled by 1/8                                   (nystroformer.py:82-91)
+    rc = gemm_dispatch(prec, EPI_QSCALE, x, x16, w->to_qkv_w, w->to_qkv_w16, F(L.qkv), R, kQkvCols, kFeat,
+                       nullptr, nullptr, kInner, st);
+    if (rc) return rc;
+    // 2. landmark attention core -> merged heads                                (nystroformer.py:95-142)
+    rc = nystrom_core_impl(batch, F(L.qkv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
+                           F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st);
+    if (rc) return rc;
+    // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
+    const void* merged16 = nullptr;
+    if (prec != EDSNET_PREC_FP32) {
+        // the x16 planes are dead after step 1: reuse the front of that region for merged (R x 512)
+        rc = edsnet_split_f16(F(L.merged), ws + L.x16, R, kInner, stream);
+        if (rc) return rc;
+        merged16 = ws + L.x16;
+    }
+    rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
+                       kInner, w->to_out_b, x, 0, st);
+    if (rc) return rc;
+    // 4. LayerNorm(1024) -> fc1                                                 (dsnet.py:106)
+    layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
+    CU_CHECK(cudaGetLastError(), "layernorm1024_kernel");
+    const void* yn16 = nullptr;
+    if (prec != EDSNET_PREC_FP32) {
+        rc = edsnet_split_f16(F(L.yn), ws + L.x16, R, kFeat, stream);
+        if (rc) return rc;
+        yn16 = ws + L.x16;
+    }
+    rc = gemm_dispatch(prec, EPI_BIAS, F(L.yn), yn16, w->fc1_w, w->fc1_w16, F(L.u0), R, kHidden, kFeat, w->fc1_b,
+                       nullptr, 0, st);
+    if (rc) return rc;
+    // 5. shared fc block x depth                                                (dsnet.py:107-108)
+    rc = fc_stack_impl(cfg, w, F(L.u0), F(L.u1), R, st);
+    if (rc) return rc;
+    // 6. ROI pooling + heads                                                    (dsnet.py:110-115)
+    return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st);
+}
+
+int edsnet_forward_launches(const edsnet_config* cfg) {
+    if (!cfg) return -1;
+    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add three operand splits
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 14;
+}
+
+int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,
+                        float* boxes_f32, int32_t* boxes_i32, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!pred_loc || (!boxes_f32 && !boxes_i32)) return fail(EDSNET_E_ARG, "decode_boxes: NULL operand");
+    const long long max_n = (long long)batch->max_rows * cfg->n_scales;
+    int halo = 0;
+    ScaleList sl = make_scales(cfg, &halo);
+    decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(pred_loc, batch->cu_rows, sl, boxes_f32, boxes_i32);
+    CU_CHECK(cudaGetLastError(), "decode_boxes_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls,
+                      const float* pred_loc, double nms_thresh, float* boxes_f32, int32_t* boxes_i32,
+                      int32_t* keep_count, int32_t* keep_idx, float* keep_scores, int32_t* keep_boxes,
+                      const int64_t* nms_scratch_off, void* nms_scratch, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!pred_cls || !pred_loc || !boxes_i32 || !keep_count || !keep_idx || !keep_scores || !keep_boxes)
+        return fail(EDSNET_E_ARG, "decode_nms: NULL operand");
+    const long long max_n = (long long)batch->max_rows * cfg->n_scales;
+    if (max_n > kNmsSmemCap && (!nms_scratch_off || !nms_scratch))
+        return fail(EDSNET_E_ARG, "decode_nms: a video has more than 4096 anchors, scratch is required");
+    if (max_n > (1ll << 30)) return fail(EDSNET_E_UNSUPPORTED, "decode_nms: video too long");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int halo = 0;
+    ScaleList sl = make_scales(cfg, &halo);
+    static bool attrs_done = false;
+    if (!attrs_done) {
+        CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemBytes), "smem opt-in nms");
+        attrs_done = true;
+    }
+    decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0, st>>>(
+        pred_loc, batch->cu_rows, sl, boxes_f32, boxes_i32);
+    CU_CHECK(cudaGetLastError(), "decode_boxes_kernel");
+    nms_kernel<<<batch->n_videos, kNmsThreads, kNmsSmemBytes, st>>>(
+        pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh,
+        reinterpret_cast<const long long*>(nms_scratch_off), static_cast<unsigned char*>(nms_scratch), keep_count,
+        keep_idx, keep_scores, keep_boxes);
+    CU_CHECK(cudaGetLastError(), "nms_kernel");
+    return EDSNET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// tcgen05 / TMEM / TMA GEMM for the dense projections (to_qkv, to_out, fc1):
+//   C[M,N] (fp32) = A[M,K] . B[N,K]^T,  operands given as fp16 hi/lo planes (x = hi + lo, |lo| <= ulp(hi)/2).
+//   PASSES = 3: acc += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi   (fp32-grade accuracy: drops only the lo.lo term)
+//   PASSES = 1: acc += A_hi.B_hi                           (plain fp16 operands)
+// Per CTA: one 128 x BN output tile.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 =
+// epilogue (TMEM -> registers -> global).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
+// by full/empty mbarriers; operands land in shared memory in the 128B (BK=64) / 64B (BK=32) swizzled K-major
+// layout that both TMA and the UMMA shared-memory descriptor understand; the accumulator lives in TMEM.
+// Every mbarrier wait is bounded: on timeout a global flag is raised and the kernel drains instead of hanging.
+#pragma once
+#include <cuda.h>
+#include <string>
+#include "common.cuh"
+#include "gemm_f32.cuh"   // GemmEpi / GemmEpiArgs
+
+namespace tc {
+
+__device__ int g_timeout_flag = 0;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// bounded wait: returns false (and raises g_timeout_flag) after ~2^31 cycles
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 31) || *((volatile int*)&g_timeout_flag) != 0) {
+            atomicExch(&g_timeout_flag, 1);
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand, rows of BK fp16 = one swizzle atom wide.
+//   bits  0-13 start address >> 4      bits 16-29 leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   bits 32-45 stride byte offset >> 4 (8 rows x swizzle width)            bits 46-47 descriptor version = 1
+//   bits 61-63 swizzle: 2 = 128B, 4 = 64B
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    constexpr uint64_t row_bytes = BK * 2;                 // 128 or 64
+    constexpr uint64_t sbo = (8 * row_bytes) >> 4;         // 64 or 32
+    constexpr uint64_t layout = (BK == 64) ? 2ull : 4ull;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (0), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int BK, int STAGES, int PASSES>
+struct TcCfg {
+    static constexpr int BM = 128;
+    static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
+    static constexpr int kBTile = BN * BK * 2;
+    static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
+    static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
+    static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kThreads = 192;
+};
+
+template <int BN, int BK, int STAGES, int PASSES, int EPI>
+__global__ void __launch_bounds__(192)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    unsigned char* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * Cfg::kStageBytes + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM;
+    const int nk = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                if (!mbar_wait(empty_bar(s), ph ^ 1u)) break;
+                const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                // stage layout: A_hi | B_hi | (A_lo | B_lo).  Plane p of an operand with R rows starts at row p*R.
+                tma_load_2d(st, &mapA, full_bar(s), kb * BK, m0);
+                tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
+                if (PASSES == 3) {
+                    tma_load_2d(st + Cfg::kATile + Cfg::kBTile, &mapA, full_bar(s), kb * BK, M + m0);
+                    tma_load_2d(st + 2 * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc = make_idesc(Cfg::BM, BN);
+            bool ok = true;
+            for (int kb = 0; kb < nk && ok; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                ok = mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
+                const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint32_t koff = k * 32;           // 16 fp16 = 32 bytes further along K inside the atom
+                    const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
+                    umma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (PASSES == 3) {
+                        const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
+                        umma_f16(tmem_acc, dah, dbl, idesc, 1u);
+                        umma_f16(tmem_acc, dal, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(empty_bar(s));                  // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);                     // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> one output row ----
+        const int quarter = warp & 3;
+        const int row = m0 + quarter * 32 + lane;
+        mbar_wait(tmem_full_bar, 0u);
+        tc_fence_after();
+        float* crow = C + (size_t)row * N + n0;
+        const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    const int c = n0 + c0 + j;
+                    if (EPI == EPI_QSCALE) {
+                        if (c < ep.qcols) { o.x *= 0.125f; o.y *= 0.125f; o.z *= 0.125f; o.w *= 0.125f; }
+                    }
+                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_RES) {
+                        const float4 b = ldg4(ep.bias + c);
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (EPI == EPI_BIAS_RES) {
+                        const float4 x = ldg4(rrow + c0 + j);
+                        o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                    }
+                    st4(crow + c0 + j, o);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_acc, BN);
+}
+
+// ---- fp32 -> fp16 hi/lo planes ----
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const float4 x = ldg4(src + i * 4);
+        const __half h0 = __float2half_rn(x.x), h1 = __float2half_rn(x.y), h2 = __float2half_rn(x.z), h3 = __float2half_rn(x.w);
+        const __half l0 = __float2half_rn(x.x - __half2float(h0)), l1 = __float2half_rn(x.y - __half2float(h1));
+        const __half l2 = __float2half_rn(x.z - __half2float(h2)), l3 = __float2half_rn(x.w - __half2float(h3));
+        __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+        __half2 ll[2] = {__halves2half2(l0, l1), __halves2half2(l2, l3)};
+        *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<uint2*>(ll);
+    }
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn(std::string* msg) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        if (msg) *msg = "cuTensorMapEncodeTiled entry point not available";
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] row-major, box = {BK cols, box_rows}
+inline bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                     uint32_t box_rows, std::string* msg) {
+    EncodeTiledFn fn = get_encode_fn(msg);
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (msg) *msg = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+template <int BN, int BK, int STAGES, int PASSES, int EPI>
+cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
+                           cudaStream_t st, std::string* msg) {
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, A16, 2ull * M, K, BK, Cfg::BM, msg)) return cudaErrorUnknown;
+    if (!make_map(&mapB, B16, 2ull * N, K, BK, BN, msg)) return cudaErrorUnknown;
+    auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI>;
+    static bool opted = false;
+    if (!opted) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        opted = true;
+    }
+    dim3 grid(N / BN, (M + Cfg::BM - 1) / Cfg::BM);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(mapA, mapB, C, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+// variant: 0 = BK64 / 128B swizzle (default), 1 = BK32 / 64B swizzle (two CTAs per SM)
+inline int& variant_ref() { static int v = 0; return v; }
+
+template <int PASSES, int EPI>
+cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
+                         cudaStream_t st, std::string* msg) {
+    const int variant = variant_ref();
+    if (N % 256 == 0) {
+        if (variant == 1) return launch_variant<256, 32, 2, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        return launch_variant<256, 64, PASSES == 3 ? 2 : 4, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+    }
+    if (N % 128 == 0) {
+        if (variant == 1) return launch_variant<128, 32, 3, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        return launch_variant<128, 64, 3, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+    }
+    if (msg) *msg = "N must be a multiple of 128";
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tc
+
+static cudaError_t launch_gemm_tc(int passes, int epilogue, const __half* A16, const __half* B16, float* C, int M,
+                                  int N, int K, GemmEpiArgs ep, cudaStream_t st, std::string* msg) {
+    if (K % 64 != 0) { if (msg) *msg = "K must be a multiple of 64"; return cudaErrorInvalidValue; }
+#define TC_CASE(P, E) if (passes == P && epilogue == E) return tc::launch_shape<P, E>(A16, B16, C, M, N, K, ep, st, msg);
+    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3)
+    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3)
+#undef TC_CASE
+    if (msg) *msg = "unsupported passes/epilogue";
+    return cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_split_f16(const float* src, __half* dst, size_t n, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    size_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tc::split_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, dst + n, n4);
+    return cudaGetLastError();
+}

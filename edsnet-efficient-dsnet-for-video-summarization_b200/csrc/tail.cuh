@@ -1,0 +1,192 @@
+// Scoring tail of DSNet.forward (anchor_based/dsnet.py:105-115): residual + LayerNorm(1024) -> fc1 ->
+// D x shared {Linear(128,128), ReLU, LayerNorm(128)} -> multi-scale ROI average pooling -> cls / loc heads.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over 1024 features, one warp per row, two-pass statistics in registers (dsnet.py:89,106; eps 1e-5,
+// biased variance as torch.nn.LayerNorm).  In: y = attn_out + x (already summed by the to_out epilogue).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm1024_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* __restrict__ out, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* src = y + (size_t)row * kFeat;
+    float4 x[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = ldg4(src + (i * 32 + lane) * 4);
+        s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+    const float mean = warp_sum(s) / (float)kFeat;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) / (float)kFeat + 1e-5f);
+    float* dst = out + (size_t)row * kFeat;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = ldg4(gamma + c), b = ldg4(beta + c);
+        st4(dst + c, make_float4(x[i].x * rstd * g.x + b.x, x[i].y * rstd * g.y + b.y,
+                                 x[i].z * rstd * g.z + b.z, x[i].w * rstd * g.w + b.w));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// D applications of the ONE shared fc block (dsnet.py:91-96,107-108; eval mode: Dropout = identity).
+// 64 rows per CTA; the 128x128 weight (transposed) and the activations stay in shared memory for all D rounds.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLd128 = 132;
+constexpr int kFcStackSmem = (128 * kLd128 + 64 * kLd128 + 3 * 128) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(256)
+fc_stack_kernel(const float* __restrict__ u_in, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ u_out,
+                int rows, int depth) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wt = smem;                       // [k][n] = w[n][k]
+    float* Us = Wt + 128 * kLd128;          // [row][k]
+    float* bs = Us + 64 * kLd128;
+    float* gs = bs + 128;
+    float* es = gs + 128;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int r0 = blockIdx.x * 64;
+    for (int idx = tid; idx < 128 * 32; idx += 256) {
+        int n = idx >> 5, k4 = (idx & 31) * 4;
+        float4 x = ldg4(w + n * 128 + k4);
+        Wt[(k4 + 0) * kLd128 + n] = x.x; Wt[(k4 + 1) * kLd128 + n] = x.y;
+        Wt[(k4 + 2) * kLd128 + n] = x.z; Wt[(k4 + 3) * kLd128 + n] = x.w;
+    }
+    for (int idx = tid; idx < 64 * 32; idx += 256) {
+        int r = idx >> 5, k4 = (idx & 31) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < rows) x = ldg4(u_in + (size_t)(r0 + r) * kHidden + k4);
+        st4(Us + r * kLd128 + k4, x);
+    }
+    if (tid < 128) { bs[tid] = __ldg(bias + tid); gs[tid] = __ldg(gamma + tid); es[tid] = __ldg(beta + tid); }
+    __syncthreads();
+
+    for (int d = 0; d < depth; ++d) {
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+        for (int k4 = 0; k4 < 128; k4 += 4) {
+            float4 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = lds4(Us + (ty * 4 + i) * kLd128 + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 b0 = lds4(Wt + (k4 + kk) * kLd128 + tx * 4);
+                const float4 b1 = lds4(Wt + (k4 + kk) * kLd128 + 64 + tx * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                    acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+                    acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+                    acc[i][4] = fmaf(av, b1.x, acc[i][4]); acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+                    acc[i][6] = fmaf(av, b1.z, acc[i][6]); acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+                }
+            }
+        }
+        __syncthreads();                    // all reads of Us for this round are done
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                acc[i][j] = fmaxf(acc[i][j] + bs[c], 0.f);
+                s += acc[i][j];
+            }
+            const float mean = half_warp_sum(s) / 128.f;
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[i][j] -= mean; q = fmaf(acc[i][j], acc[i][j], q); }
+            const float rstd = 1.f / sqrtf(half_warp_sum(q) / 128.f + 1e-5f);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                o[j] = acc[i][j] * rstd * gs[c] + es[c];
+            }
+            st4(Us + (ty * 4 + i) * kLd128 + tx * 4, make_float4(o[0], o[1], o[2], o[3]));
+            st4(Us + (ty * 4 + i) * kLd128 + 64 + tx * 4, make_float4(o[4], o[5], o[6], o[7]));
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < 64 * 32; idx += 256) {
+        int r = idx >> 5, k4 = (idx & 31) * 4;
+        if (r0 + r < rows) st4(u_out + (size_t)(r0 + r) * kHidden + k4, lds4(Us + r * kLd128 + k4));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-scale ROI average pooling + cls / loc heads (dsnet.py:78-80,111-115).
+//   pooled[t][s] = (1/scale_s) * sum_{j = t - scale_s/2}^{t + scale_s/2 - 1} u[j]   (u[j] = 0 outside the video;
+//   AvgPool1d(scale, 1, scale//2) with count_include_pad, last of the T+1 outputs dropped)
+//   pred_cls = sigmoid(pooled . w_cls + b_cls),  pred_loc = pooled . W_loc + b_loc
+// One CTA per 128-row tile of one video (tiles[] = {video, first row}); the tile plus a max_scale/2 halo is
+// staged in smem once (128-bit loads), one warp per output row, every lane owns 4 of the 128 channels.
+// ---------------------------------------------------------------------------------------------------------
+struct ScaleList { int n; int s[kMaxScales]; };
+
+__global__ void __launch_bounds__(256)
+roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
+                      ScaleList scales, int halo, const float* __restrict__ w_cls, const float* __restrict__ b_cls,
+                      const float* __restrict__ w_loc, const float* __restrict__ b_loc,
+                      float* __restrict__ pred_cls, float* __restrict__ pred_loc) {
+    extern __shared__ __align__(16) float smem[];      // [(128 + 2*halo)][128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int2 tile = tiles[blockIdx.x];
+    const int v = tile.x, t0 = tile.y;
+    const VidInfo vi = vid_info(cu_rows, v);
+    const int nrows = 128 + 2 * halo;
+    for (int idx = tid; idx < nrows * 32; idx += 256) {
+        int r = idx >> 5, c4 = (idx & 31) * 4;
+        int t = t0 - halo + r;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < vi.T) x = ldg4(u + (size_t)(vi.row0 + t) * kHidden + c4);
+        st4(smem + r * kHidden + c4, x);
+    }
+    const float4 wc = ldg4(w_cls + lane * 4);
+    const float4 w0 = ldg4(w_loc + lane * 4);
+    const float4 w1 = ldg4(w_loc + kHidden + lane * 4);
+    const float bc = __ldg(b_cls), bl0 = __ldg(b_loc), bl1 = __ldg(b_loc + 1);
+    __syncthreads();
+    const int S = scales.n;
+    for (int i = warp; i < 128; i += 8) {
+        const int t = t0 + i;
+        if (t >= vi.T) break;
+        for (int si = 0; si < S; ++si) {
+            const int sc = scales.s[si];
+            const float* p = smem + (i + halo - sc / 2) * kHidden + lane * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < sc; ++j) {
+                const float4 x = lds4(p + j * kHidden);
+                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            }
+            const float div = (float)sc;
+            a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+            float dc = fmaf(a.x, wc.x, fmaf(a.y, wc.y, fmaf(a.z, wc.z, a.w * wc.w)));
+            float d0 = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, a.w * w0.w)));
+            float d1 = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, a.w * w1.w)));
+            dc = warp_sum(dc); d0 = warp_sum(d0); d1 = warp_sum(d1);
+            if (lane == 0) {
+                const size_t o = (size_t)(vi.row0 + t) * S + si;
+                pred_cls[o] = 1.f / (1.f + expf(-(dc + bc)));
+                pred_loc[o * 2 + 0] = d0 + bl0;
+                pred_loc[o * 2 + 1] = d1 + bl1;
+            }
+        }
+    }
+}

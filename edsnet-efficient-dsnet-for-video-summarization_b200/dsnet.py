@@ -1,0 +1,294 @@
+"""Drop-in replacement for the reference's anchor-based scoring model.
+
+Mirrors `DSNet` of the reference (src/anchor_based/dsnet.py:65-153): same constructor signature, same
+parameter names / shapes / aliasing (so reference checkpoints load with strict=True and `model.apply(xavier_init)`
+acts identically, src/anchor_based/train.py:19-24,51), same `forward(x) -> (pred_cls, pred_loc)` and
+`predict(seq) -> (scores, left/right boxes)`.  The arithmetic is NOT torch: every call goes through the C ABI of
+libedsnet_b200.so (include/edsnet_b200.h) to hand-written sm_100a kernels.  There is no CPU path: a CPU tensor,
+a missing extension or an unsupported configuration raises.
+
+Beyond the reference surface (whose loop is one video per call, evaluate.py:19-28) the class adds packed
+multi-video entry points -- `forward_packed`, `proposals_packed` -- used by the throughput pipeline.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _capi
+from .plan import BatchPlan, DeviceBatch
+
+NUM_FEATURE = 1024
+NUM_HIDDEN = 128
+NUM_HEAD = 8
+DIM_HEAD = 64
+
+
+class NystromAttention(nn.Module):
+    """Parameter container with the layout of the reference's NystromAttention
+    (src/transformer/nystroformer.py:32-65, built at src/modules/models.py:134-135).  It has no forward of
+    its own: DSNet's fused kernels consume these parameters directly."""
+
+    def __init__(self, dim: int, dim_head: int = 64, heads: int = 8, num_landmarks: int = 64,
+                 pinv_iterations: int = 6, residual: bool = True, residual_conv_kernel: int = 33,
+                 eps: float = 1e-8, dropout: float = 0.0):
+        super().__init__()
+        inner = heads * dim_head
+        self.eps = eps
+        self.num_landmarks = num_landmarks
+        self.pinv_iterations = pinv_iterations
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+        self.residual = residual
+        if residual:
+            k = residual_conv_kernel
+            self.res_conv = nn.Conv2d(heads, heads, (k, 1), padding=(k // 2, 0), groups=heads, bias=False)
+
+    def forward(self, x, mask=None, return_attn=False):  # pragma: no cover - guarded surface
+        raise RuntimeError("edsnet_b200.NystromAttention only holds parameters; call DSNet.forward "
+                           "(the attention block is fused into the scoring kernels)")
+
+
+class DSNet(nn.Module):
+    """`DSNet(base_model, num_feature, num_hidden, anchor_scales, num_head, fc_depth=5, orientation='paper',
+    pooling_type='fft')` -- reference signature (dsnet.py:66-67).  Accelerated configuration only:
+    base_model='nystromformer', pooling_type='roi', num_feature=1024, num_hidden=128, num_head=8, even scales.
+
+    Extra keyword `precision`: arithmetic of the three big projections.
+      'fp16x3' (default) tcgen05 tensor cores, fp16 hi/lo operand split, 3 MMA passes, fp32 accumulate: fp32-grade
+      'fp16'             tcgen05 single pass, fp32 accumulate
+      'fp32'             CUDA-core FFMA
+    """
+
+    def __init__(self, base_model, num_feature, num_hidden, anchor_scales, num_head, fc_depth=5,
+                 orientation="paper", pooling_type="fft", precision: str = "fp16x3"):
+        super().__init__()
+        if type(anchor_scales) == int:                       # dsnet.py:69-70
+            anchor_scales = [anchor_scales]
+        anchor_scales = [int(s) for s in anchor_scales]
+        if base_model != "nystromformer":
+            raise ValueError(f"edsnet_b200 accelerates base_model='nystromformer' only, got {base_model!r}")
+        if pooling_type != "roi":
+            raise ValueError(f"edsnet_b200 accelerates pooling_type='roi' only, got {pooling_type!r}")
+        if (num_feature, num_hidden, num_head) != (NUM_FEATURE, NUM_HIDDEN, NUM_HEAD):
+            raise ValueError("edsnet_b200 kernels are built for num_feature=1024, num_hidden=128, num_head=8")
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_capi.PRECISIONS)}")
+        self.anchor_scales = anchor_scales
+        self.num_scales = len(anchor_scales)
+        self.base_model_type = base_model
+        self.pooling_type = pooling_type
+        self.fc_depth = int(fc_depth)
+        self.precision = precision
+        self.base_model = NystromAttention(dim=num_feature, dim_head=DIM_HEAD, heads=num_head, num_landmarks=64,
+                                           pinv_iterations=6, residual=True, residual_conv_kernel=33)
+        self.layer_norm = nn.LayerNorm(num_feature)
+        self.fc1 = nn.Linear(num_feature, num_hidden)
+        self.fc_block = nn.Sequential(nn.Linear(num_hidden, num_hidden), nn.ReLU(), nn.Dropout(0.5),
+                                      nn.LayerNorm(num_hidden))
+        self.fc = nn.ModuleList([self.fc_block for _ in range(self.fc_depth)])    # ONE shared block, dsnet.py:96
+        self.fc_cls = nn.Sequential(nn.Linear(num_hidden, 1))
+        self.fc_loc = nn.Sequential(nn.Linear(num_hidden, 2))
+        self._wcache = None
+        self._wkey = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------ weights / workspace
+    def _param_list(self):
+        bm = self.base_model
+        return [bm.to_qkv.weight, bm.to_out[0].weight, bm.to_out[0].bias, bm.res_conv.weight,
+                self.layer_norm.weight, self.layer_norm.bias, self.fc1.weight, self.fc1.bias,
+                self.fc_block[0].weight, self.fc_block[0].bias, self.fc_block[3].weight, self.fc_block[3].bias,
+                self.fc_cls[0].weight, self.fc_cls[0].bias, self.fc_loc[0].weight, self.fc_loc[0].bias]
+
+    def _config(self) -> _capi.Config:
+        # dsnet.py:113-115: an odd scale makes the reference's .view() raise RuntimeError; same surface here
+        for s in self.anchor_scales:
+            if s % 2:
+                raise RuntimeError(f"odd anchor scale {s}: shape mismatch in view (reference dsnet.py:114 fails too)")
+        return _capi.make_config(self.anchor_scales, self.fc_depth, _capi.PRECISIONS[self.precision])
+
+    def _weights(self, device, stream: int) -> _capi.Weights:
+        params = self._param_list()
+        key = (self.precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._wkey == key:
+            return self._wcache[0]
+        keep = []
+        w = _capi.Weights()
+        for name, p in zip(_capi.WEIGHT_FIELDS[:16], params):
+            if p.device != device:
+                raise RuntimeError(f"parameter {name} is on {p.device}, input is on {device}")
+            t = p.detach()
+            if t.dtype != torch.float32:
+                raise RuntimeError("edsnet_b200 parameters must be float32")
+            t = t.contiguous()
+            keep.append(t)
+            setattr(w, name, t.data_ptr())
+        if self.precision != "fp32":
+            lib = _capi.lib()
+            for name, p in (("to_qkv_w16", params[0]), ("to_out_w16", params[1]), ("fc1_w16", params[6])):
+                src = p.detach().contiguous()
+                planes = torch.empty((2,) + tuple(src.shape), dtype=torch.float16, device=device)
+                _capi.check(lib.edsnet_split_f16(src.data_ptr(), planes.data_ptr(), src.shape[0], src.shape[1],
+                                                 stream))
+                keep += [src, planes]
+                setattr(w, name, planes.data_ptr())
+        self._wcache = (w, keep)
+        self._wkey = key
+        return w
+
+    def _get_workspace(self, cfg, total_rows: int, n_videos: int, device):
+        need = _capi.lib().edsnet_workspace_bytes(cfg, total_rows, n_videos, None)
+        ws = self._workspace
+        if ws is None or ws.device != device or ws.numel() < need:
+            self._workspace = None
+            ws = torch.empty(int(need * 1.0), dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws, need
+
+    def launches_per_forward(self) -> int:
+        """Kernel launches one forward enqueues (bench bookkeeping)."""
+        return int(_capi.lib().edsnet_forward_launches(self._config()))
+
+    @staticmethod
+    def _check_input(x: torch.Tensor):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a torch.Tensor")
+        if not x.is_cuda:
+            raise RuntimeError("edsnet_b200 has no CPU path: move the input (and the model) to a CUDA device")
+        if x.dtype != torch.float32:
+            raise RuntimeError("edsnet_b200 expects float32 features")
+
+    # ------------------------------------------------------------------ packed multi-video API
+    def forward_packed(self, x: torch.Tensor, batch: Union[DeviceBatch, BatchPlan, Sequence[int]]
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x: [total_rows, 1024] float32 CUDA, rows of all videos concatenated.  Returns
+        pred_cls [total_rows, S], pred_loc [total_rows, S, 2]; rows cu[v]..cu[v+1] belong to video v and equal
+        the reference's `model(x_v[None])`."""
+        self._check_input(x)
+        if x.dim() != 2 or x.shape[1] != NUM_FEATURE:
+            raise RuntimeError(f"expected [rows, {NUM_FEATURE}] features, got {tuple(x.shape)}")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import scoring_with_grad
+            return scoring_with_grad(self, x, batch)
+        return self._forward_nograd(x, batch)
+
+    def _forward_nograd(self, x, batch):
+        if not isinstance(batch, DeviceBatch):
+            plan = batch if isinstance(batch, BatchPlan) else BatchPlan.build(batch)
+            batch = plan.to(x.device)
+        if batch.plan.total_rows != x.shape[0]:
+            raise RuntimeError(f"batch plan covers {batch.plan.total_rows} rows, x has {x.shape[0]}")
+        x = x.detach().contiguous()
+        cfg = self._config()
+        lib = _capi.lib()
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            w = self._weights(x.device, stream)
+            ws, need = self._get_workspace(cfg, x.shape[0], batch.plan.n_videos, x.device)
+            S = self.num_scales
+            pred_cls = torch.empty((x.shape[0], S), dtype=torch.float32, device=x.device)
+            pred_loc = torch.empty((x.shape[0], S, 2), dtype=torch.float32, device=x.device)
+            _capi.check(lib.edsnet_forward(cfg, w, batch.struct, x.data_ptr(), pred_cls.data_ptr(),
+                                           pred_loc.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return pred_cls, pred_loc
+
+    def decode_packed(self, pred_loc: torch.Tensor, batch: DeviceBatch) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Offsets -> (float32 left/right boxes, clipped+rounded int32 boxes), both [total_rows*S, 2]
+        (dsnet.py:146-153 + evaluate.py:26)."""
+        cfg = self._config()
+        n = batch.plan.total_rows * self.num_scales
+        dev = pred_loc.device
+        boxes_f = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        boxes_i = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().edsnet_decode_boxes(cfg, batch.struct, pred_loc.contiguous().data_ptr(),
+                                                        boxes_f.data_ptr(), boxes_i.data_ptr(), stream))
+        return boxes_f, boxes_i
+
+    def nms_packed(self, pred_cls: torch.Tensor, pred_loc: torch.Tensor, batch: DeviceBatch,
+                   nms_thresh: float = 0.5):
+        """decode + clip/round + greedy temporal NMS for every video of the batch, on device.
+        Returns dict of device tensors: keep_count [V], keep_idx / keep_scores [total_rows*S],
+        keep_boxes [total_rows*S, 2]; video v's kept proposals (descending score) start at cu_rows[v]*S."""
+        cfg = self._config()
+        plan = batch.plan
+        dev = pred_cls.device
+        S = self.num_scales
+        n = plan.total_rows * S
+        out = {
+            "boxes_i32": torch.empty((n, 2), dtype=torch.int32, device=dev),
+            "keep_count": torch.empty((plan.n_videos,), dtype=torch.int32, device=dev),
+            "keep_idx": torch.empty((n,), dtype=torch.int32, device=dev),
+            "keep_scores": torch.empty((n,), dtype=torch.float32, device=dev),
+            "keep_boxes": torch.empty((n, 2), dtype=torch.int32, device=dev),
+        }
+        off_ptr, scratch_ptr, keep = None, None, None
+        if plan.max_rows * S > 4096:
+            off, total = plan.nms_scratch(S)
+            off_t = torch.from_numpy(off).to(dev)
+            scratch = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+            keep = (off_t, scratch)
+            off_ptr, scratch_ptr = off_t.data_ptr(), scratch.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().edsnet_decode_nms(
+                cfg, batch.struct, pred_cls.contiguous().data_ptr(), pred_loc.contiguous().data_ptr(),
+                float(nms_thresh), None, out["boxes_i32"].data_ptr(), out["keep_count"].data_ptr(),
+                out["keep_idx"].data_ptr(), out["keep_scores"].data_ptr(), out["keep_boxes"].data_ptr(),
+                off_ptr, scratch_ptr, stream))
+        out["_scratch"] = keep
+        return out
+
+    def proposals_packed(self, x: torch.Tensor, batch: Union[DeviceBatch, BatchPlan, Sequence[int]],
+                         nms_thresh: float = 0.5) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """Features -> per video (keep_scores, keep_boxes) exactly as evaluate.py:24-28 produces them."""
+        if not isinstance(batch, DeviceBatch):
+            plan = batch if isinstance(batch, BatchPlan) else BatchPlan.build(batch)
+            batch = plan.to(x.device)
+        with torch.no_grad():
+            cls, loc = self._forward_nograd(x, batch)
+            r = self.nms_packed(cls, loc, batch, nms_thresh)
+        counts = r["keep_count"].cpu().numpy()
+        ks = r["keep_scores"].cpu().numpy()
+        kb = r["keep_boxes"].cpu().numpy()
+        S = self.num_scales
+        out = []
+        for v in range(batch.plan.n_videos):
+            o = int(batch.plan.cu_rows[v]) * S
+            c = int(counts[v])
+            out.append((ks[o:o + c].copy(), kb[o:o + c].copy()))
+        return out
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, x: torch.Tensor):
+        """x: (1, T, 1024) float32 on a CUDA device -> pred_cls (T, S), pred_loc (T, S, 2)   (dsnet.py:100-115)."""
+        self._check_input(x)
+        if x.dim() != 3:
+            raise ValueError(f"not enough values to unpack: expected a (1, T, {NUM_FEATURE}) tensor")
+        if x.shape[0] != 1:
+            # the reference's cat(dim=0)/view(seq_len, num_scales) (dsnet.py:113-115) only works for batch 1
+            raise RuntimeError(f"shape '[{x.shape[1]}, {self.num_scales}]' is invalid for a batch of {x.shape[0]} "
+                               "videos: DSNet.forward scores one video per call; use forward_packed for many")
+        if x.shape[1] < 1:
+            raise RuntimeError("empty sequence")
+        return self.forward_packed(x[0], [x.shape[1]])
+
+    def predict(self, seq: torch.Tensor):
+        """(scores float32 (T*S,), boxes float32 (T*S, 2) left/right), NumPy, as dsnet.py:140-153."""
+        pred_cls, pred_loc = self(seq)
+        with torch.no_grad():
+            batch = BatchPlan.build([seq.shape[1]]).to(seq.device)
+            boxes_f, _ = self.decode_packed(pred_loc.detach(), batch)
+        return pred_cls.cpu().numpy().reshape(-1), boxes_f.cpu().numpy().reshape(-1, 2)
+
+    def proposals(self, seq: torch.Tensor, nms_thresh: float = 0.5):
+        """evaluate.py:24-28 in one call: predict -> clip/round -> nms.  Returns (keep_scores, keep_boxes)."""
+        self._check_input(seq)
+        return self.proposals_packed(seq[0], [seq.shape[1]], nms_thresh)[0]

@@ -1,0 +1,180 @@
+/*
+ * edsnet_b200 -- C ABI of the B200 (sm_100a) implementation of EDSNet's anchor-based scoring path.
+ *
+ * The reference (ashish2506prasad/EDSNet-Efficient-DSNet-for-Video-Summarization) is pure Python/PyTorch and has
+ * no FFI layer; its seam for this path is the Python class `DSNet` (src/anchor_based/dsnet.py:65-153).  The
+ * entry points below are what a binding for that class needs; `edsnet_b200/dsnet.py` is that binding (ctypes) and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only.  Every pointer marked [dev] is a CUDA device pointer on the
+ * current device; `stream` is a cudaStream_t passed as void*.  No entry point allocates, frees or synchronises;
+ * all work is enqueued on `stream` and is re-entrant per stream as long as the workspaces differ.  Return value:
+ * 0 = enqueued, non-zero = error (EDSNET_E_*), message via edsnet_last_error() (thread-local).
+ * There is no CPU fallback: without a CUDA device every compute entry point returns EDSNET_E_CUDA.
+ *
+ * Packed variable-length batches: the feature rows of all videos are concatenated, x is [total_rows][1024] fp32,
+ * cu_rows[v] .. cu_rows[v+1] are the rows of video v.  One reference call `model(x[None])` (dsnet.py:100-115) is
+ * the special case n_videos == 1.
+ */
+#ifndef EDSNET_B200_H
+#define EDSNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDSNET_ABI_VERSION 1
+
+enum {
+    EDSNET_OK = 0,
+    EDSNET_E_ARG = 1,          /* bad argument (null pointer, odd anchor scale, too many scales, ...) */
+    EDSNET_E_CUDA = 2,         /* CUDA runtime error, text in edsnet_last_error() */
+    EDSNET_E_WORKSPACE = 3,    /* workspace too small */
+    EDSNET_E_UNSUPPORTED = 4   /* configuration outside the accelerated path */
+};
+
+/* arithmetic of the dense projections (to_qkv, to_out, fc1) */
+enum {
+    EDSNET_PREC_FP32 = 0,      /* CUDA-core FFMA, fp32 operands                       (<= 1e-5 vs reference) */
+    EDSNET_PREC_FP16X3 = 1,    /* tcgen05 fp16 hi/lo split, 3 MMA passes, fp32 accum  (<= 1e-5 vs reference) */
+    EDSNET_PREC_FP16 = 2       /* tcgen05 fp16 single pass, fp32 accumulate           (~ 1e-3 vs reference)  */
+};
+
+#define EDSNET_MAX_SCALES 8
+
+/* Model hyper-parameters that are not baked in.  Baked in (reference call sites): num_feature 1024, num_hidden
+ * 128, num_head 8, dim_head 64, 64 landmarks, 6 pinv iterations, 33-tap value conv (modules/models.py:134-135). */
+typedef struct {
+    int32_t fc_depth;                         /* applications of the shared fc block (dsnet.py:67,96) */
+    int32_t n_scales;                         /* len(anchor_scales), 1..8                              */
+    int32_t scales[EDSNET_MAX_SCALES];        /* even, 2..128 (odd scales crash the reference's .view) */
+    int32_t precision;                        /* EDSNET_PREC_*                                         */
+} edsnet_config;
+
+/* Weights in the reference's own state-dict layout (row-major (out, in) as nn.Linear stores them), fp32 [dev].
+ * Names: DSNet.state_dict() keys, dsnet.py:66-98 / transformer/nystroformer.py:52-65. */
+typedef struct {
+    const float* to_qkv_w;     /* base_model.to_qkv.weight      (1536, 1024) */
+    const float* to_out_w;     /* base_model.to_out.0.weight    (1024, 512)  */
+    const float* to_out_b;     /* base_model.to_out.0.bias      (1024)       */
+    const float* res_conv_w;   /* base_model.res_conv.weight    (8, 1, 33, 1)*/
+    const float* ln_w;         /* layer_norm.weight             (1024)       */
+    const float* ln_b;         /* layer_norm.bias               (1024)       */
+    const float* fc1_w;        /* fc1.weight                    (128, 1024)  */
+    const float* fc1_b;        /* fc1.bias                      (128)        */
+    const float* fcb_w;        /* fc_block.0.weight             (128, 128)   */
+    const float* fcb_b;        /* fc_block.0.bias               (128)        */
+    const float* fcb_ln_w;     /* fc_block.3.weight             (128)        */
+    const float* fcb_ln_b;     /* fc_block.3.bias               (128)        */
+    const float* cls_w;        /* fc_cls.0.weight               (1, 128)     */
+    const float* cls_b;        /* fc_cls.0.bias                 (1)          */
+    const float* loc_w;        /* fc_loc.0.weight               (2, 128)     */
+    const float* loc_b;        /* fc_loc.0.bias                 (2)          */
+    /* fp16 hi/lo splits of the three projection weights, produced by edsnet_split_f16; required for the
+     * tcgen05 precisions, ignored for EDSNET_PREC_FP32.  Each is [rows][cols] fp16, hi then lo plane. */
+    const void* to_qkv_w16;    /* 2 x (1536, 1024) fp16 */
+    const void* to_out_w16;    /* 2 x (1024, 512)  fp16 */
+    const void* fc1_w16;       /* 2 x (128, 1024)  fp16 */
+} edsnet_weights;
+
+/* A packed batch of videos.  All arrays [dev], int32.  Tile tables are built by the host (see
+ * edsnet_b200/plan.py): one {video, first_row} pair per 64-row (attention) / 128-row (pooling) tile of a video. */
+typedef struct {
+    int32_t n_videos;
+    int32_t total_rows;        /* sum of T over the batch == cu_rows[n_videos] */
+    int32_t max_rows;          /* max T in the batch */
+    const int32_t* cu_rows;    /* [n_videos + 1] */
+    const int32_t* tiles64;    /* [n_tiles64][2] */
+    int32_t n_tiles64;
+    const int32_t* tiles128;   /* [n_tiles128][2] */
+    int32_t n_tiles128;
+} edsnet_batch;
+
+/* Byte offsets of the intermediates inside the forward workspace (for tests / profiling). */
+typedef struct {
+    size_t qkv;        /* [rows][1536]  q (pre-scaled by 1/8) | k | v                */
+    size_t q_land;     /* [videos][8][64][64]                                         */
+    size_t k_land;
+    size_t attn2;      /* softmax(q_land k_land^T)                                    */
+    size_t stats;      /* [videos][8][2]                                              */
+    size_t a3v;        /* softmax(q_land k^T) v                                       */
+    size_t zmat;       /* pseudo-inverse of attn2                                     */
+    size_t wmat;       /* zmat a3v                                                    */
+    size_t merged;     /* [rows][512] head-merged attention output + value conv       */
+    size_t y;          /* [rows][1024] to_out + bias + x                              */
+    size_t yn;         /* [rows][1024] LayerNorm(y)           (aliases qkv)           */
+    size_t u0;         /* [rows][128] fc1 output                                      */
+    size_t u1;         /* [rows][128] after the fc stack                              */
+    size_t x16;        /* tcgen05 precisions: fp16 hi/lo planes of x, 2 x [rows][1024]*/
+    size_t total;
+} edsnet_workspace_layout;
+
+const char* edsnet_last_error(void);
+int edsnet_abi_version(void);
+
+/* Workspace sizing: fills *layout (may be NULL) and returns the bytes edsnet_forward needs. */
+size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos,
+                              edsnet_workspace_layout* layout);
+
+/* DSNet.forward (dsnet.py:100-115) over a packed batch: x [dev][total_rows][1024] fp32 ->
+ * pred_cls [dev][total_rows][S] (sigmoid scores), pred_loc [dev][total_rows][S][2] (centre, log-width offsets). */
+int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch,
+                   const float* x, float* pred_cls, float* pred_loc,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* DSNet.predict's decode (dsnet.py:146-153: get_anchors + offset2bbox + cw2lr), evaluate.py:26 clip/round and
+ * bbox_helper.nms (helpers/bbox_helper.py:80-118), per video.
+ *   boxes_f32 [dev][total_rows*S][2] float32 left/right (may be NULL), boxes_i32 [dev][total_rows*S][2],
+ *   keep_count [dev][n_videos]; keep_idx / keep_scores / keep_boxes are [dev] arrays of total_rows*S entries,
+ *   the kept proposals of video v (descending score) start at entry cu_rows[v]*S; keep_idx is the flat
+ *   anchor index t*S+s inside the video.
+ *   Videos with more than 4096 anchors need scratch: nms_scratch_off [dev][n_videos] byte offsets into
+ *   nms_scratch (24 bytes per anchor rounded up to a power of two); both may be NULL otherwise. */
+int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls,
+                      const float* pred_loc, double nms_thresh, float* boxes_f32, int32_t* boxes_i32,
+                      int32_t* keep_count, int32_t* keep_idx, float* keep_scores, int32_t* keep_boxes,
+                      const int64_t* nms_scratch_off, void* nms_scratch, void* stream);
+
+/* decode only (what DSNet.predict returns, dsnet.py:146-153, plus the evaluate.py:26 clip/round):
+ * boxes_f32 [dev][total_rows*S][2] (may be NULL), boxes_i32 [dev][total_rows*S][2] (may be NULL). */
+int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,
+                        float* boxes_f32, int32_t* boxes_i32, void* stream);
+
+/* Number of kernel launches one edsnet_forward call enqueues for this configuration (bench bookkeeping). */
+int edsnet_forward_launches(const edsnet_config* cfg);
+
+/* fp32 (rows, cols) -> fp16 hi plane followed by fp16 lo plane (hi = fp16(w), lo = fp16(w - hi)). */
+int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream);
+
+/* ---- stage-level entry points (tests, per-kernel timing, ncu) ---- */
+
+/* C[M][N] = A[M][K] . B[N][K]^T, epilogue: 0 none, 1 first qcols columns * 1/8, 2 + bias, 3 + bias + res. */
+int edsnet_gemm(int32_t precision, int32_t epilogue, const float* A, const void* A16, const float* B,
+                const void* B16, float* C, int32_t M, int32_t N, int32_t K, const float* bias,
+                const float* res, int32_t qcols, void* stream);
+/* qkv -> merged: landmarks, three softmax kernels, pseudo-inverse, aggregation, value conv (nystroformer.py). */
+int edsnet_nystrom_core(const edsnet_batch* batch, const float* qkv, const float* res_conv_w, float* q_land,
+                        float* k_land, float* attn2, float* stats, float* a3v, float* zmat, float* wmat,
+                        float* merged, void* stream);
+/* u0 -> u1: fc_depth applications of the shared block. */
+int edsnet_fc_stack(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out,
+                    int32_t rows, void* stream);
+/* u1 -> pred_cls / pred_loc. */
+int edsnet_roi_pool_heads(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch,
+                          const float* u, float* pred_cls, float* pred_loc, void* stream);
+
+/* ---- diagnostics ---- */
+
+/* Synchronous.  Returns 1 if a tcgen05 GEMM pipeline wait timed out since the last reset (the kernel then drained
+ * with undefined results instead of hanging), 0 if not, -1 on CUDA error.  reset != 0 clears the flag. */
+int edsnet_debug_tc_status(int32_t reset);
+/* Tile variant of the tcgen05 GEMM: 0 = BK 64 / 128-byte swizzle (default), 1 = BK 32 / 64-byte swizzle. */
+int edsnet_debug_set_tc_variant(int32_t variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

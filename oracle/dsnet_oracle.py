@@ -237,7 +237,21 @@ def anchor_grid(T: int, scales: Sequence[int]) -> np.ndarray:
     return g
 
 
-def decode_boxes(pred_loc: np.ndarray, T: int, scales: Sequence[int]) -> np.ndarray:
+def exp_f32(x: np.ndarray, mode: str = "numpy") -> np.ndarray:
+    """float32 exp.  ``numpy``: whatever ``np.exp`` does on a float32 array on THIS machine -- what the reference
+    executes (anchor_helper.py:88), but NumPy's SIMD float32 exp is not correctly rounded (<= 2.5 ulp; it differs
+    from the correctly rounded value for ~39 % of N(0, 0.7) arguments on AVX-512) and is dispatch-dependent.
+    ``cr``: correctly rounded (float64 exp, one rounding) -- machine-independent; this is what the CUDA decode
+    kernel computes and what GPU parity tests compare bit for bit."""
+    x = np.asarray(x, dtype=np.float32)
+    if mode == "numpy":
+        return np.exp(x)
+    if mode == "cr":
+        return np.exp(x.astype(np.float64)).astype(np.float32)
+    raise ValueError(mode)
+
+
+def decode_boxes(pred_loc: np.ndarray, T: int, scales: Sequence[int], exp_mode: str = "numpy") -> np.ndarray:
     """Offsets -> float32 left/right boxes, (T*S, 2).
 
     anchor_based/anchor_helper.py:74-93 then helpers/bbox_helper.py:21-31:
@@ -249,7 +263,7 @@ def decode_boxes(pred_loc: np.ndarray, T: int, scales: Sequence[int]) -> np.ndar
     anc = anchor_grid(T, scales).reshape(-1, 2)
     aw = anc[:, 1].astype(np.float64)
     centre = off[:, 0].astype(np.float64) * aw + anc[:, 0].astype(np.float64)
-    width = np.exp(off[:, 1]).astype(np.float64) * aw
+    width = exp_f32(off[:, 1], exp_mode).astype(np.float64) * aw
     c32 = centre.astype(np.float32)
     w32 = width.astype(np.float32)
     half = w32 / np.float32(2)

@@ -1,0 +1,358 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated golden vectors.
+Every test here needs a B200: `pytest -m gpu`."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dsnet_oracle as orc
+from tests.util import TOL, golden_case, load_npz, make_model
+
+pytestmark = pytest.mark.gpu
+
+FWD = load_npz("forward_golden.npz")
+DN = load_npz("decode_nms_golden.npz")
+CASES = list(FWD["forward_cases"])
+DEV = "cuda:0"
+
+
+def _lib():
+    from edsnet_b200 import _capi
+    return _capi, _capi.lib()
+
+
+def _no_tc_timeout():
+    capi, lib = _lib()
+    torch.cuda.synchronize()
+    assert lib.edsnet_debug_tc_status(1) == 0, "a tcgen05 pipeline wait timed out"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM stage
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
+@pytest.mark.parametrize("M,N,K,epi", [(320, 1536, 1024, 1), (320, 1024, 512, 3), (320, 128, 1024, 2),
+                                        (37, 1536, 1024, 1), (1000, 1024, 512, 3), (129, 128, 1024, 2),
+                                        (4096, 1536, 1024, 0)])
+def test_gemm_stage(precision, M, N, K, epi):
+    capi, lib = _lib()
+    g = torch.Generator().manual_seed(M * 7 + N + epi)
+    A = torch.randn(M, K, generator=g) * 0.05
+    B = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    bias = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g) * 0.1
+    ref = A.double() @ B.double().t()
+    if epi == 1:
+        ref[:, :512] *= 0.125
+    if epi >= 2:
+        ref += bias.double()
+    if epi == 3:
+        ref += res.double()
+    Ad, Bd, bd, rd = (t.to(DEV).contiguous() for t in (A, B, bias, res))
+    Cd = torch.full((M, N), float("nan"), device=DEV)
+    A16 = B16 = None
+    st = torch.cuda.current_stream().cuda_stream
+    if precision != "fp32":
+        A16 = torch.empty((2, M, K), dtype=torch.float16, device=DEV)
+        B16 = torch.empty((2, N, K), dtype=torch.float16, device=DEV)
+        capi.check(lib.edsnet_split_f16(Ad.data_ptr(), A16.data_ptr(), M, K, st))
+        capi.check(lib.edsnet_split_f16(Bd.data_ptr(), B16.data_ptr(), N, K, st))
+    capi.check(lib.edsnet_gemm(capi.PRECISIONS[precision], epi, Ad.data_ptr(),
+                               A16.data_ptr() if A16 is not None else None, Bd.data_ptr(),
+                               B16.data_ptr() if B16 is not None else None, Cd.data_ptr(), M, N, K,
+                               bd.data_ptr(), rd.data_ptr(), 512, st))
+    _no_tc_timeout()
+    out = Cd.cpu().double()
+    assert torch.isfinite(out).all()
+    err = float((out - ref).norm() / ref.norm())
+    # operand rounding: fp32/fp16x3 ~ 2^-22..2^-24 per product, fp16 ~ 2^-11
+    assert err < {"fp32": 2e-6, "fp16x3": 2e-6, "fp16": 1e-3}[precision], err
+
+
+# ------------------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(name, precision):
+    g, x, p = golden_case(FWD, name)
+    scales = [int(s) for s in g["scales"]]
+    model = make_model(p, scales, int(g["fc_depth"]), precision, DEV)
+    with torch.no_grad():
+        cls, loc = model(x[None].to(DEV))
+    _no_tc_timeout()
+    assert cls.shape == g["pred_cls"].shape and loc.shape == g["pred_loc"].shape
+    e_cls = orc.rel_l2(cls.cpu().numpy(), g["pred_cls"])
+    e_loc = orc.rel_l2(loc.cpu().numpy(), g["pred_loc"])
+    print(f"{name} {precision}: rel-l2 cls {e_cls:.2e} loc {e_loc:.2e}")
+    assert e_cls < TOL[precision] and e_loc < TOL[precision], (e_cls, e_loc)
+
+
+def test_forward_stages_match_oracle():
+    """Intermediates of the fp32 path, read back from the workspace, against the oracle's stages."""
+    capi, lib = _lib()
+    g, x, p = golden_case(FWD, "T450_s4_8_16_32_d7")
+    scales, depth = [int(s) for s in g["scales"]], int(g["fc_depth"])
+    T = x.shape[0]
+    stages = {}
+    with torch.no_grad():
+        orc.dsnet_forward(x, p, scales, depth, stages=stages)
+    model = make_model(p, scales, depth, "fp32", DEV)
+    with torch.no_grad():
+        model(x[None].to(DEV))
+    torch.cuda.synchronize()
+    L = capi.WorkspaceLayout()
+    lib.edsnet_workspace_bytes(model._config(), T, 1, C.byref(L))
+    ws = model._workspace
+
+    def view(off, shape):
+        n = int(np.prod(shape))
+        return ws[off:off + 4 * n].view(torch.float32).reshape(shape).cpu()
+
+    pad = (64 - T % 64) % 64
+    # qkv region is reused for LayerNorm output (yn), so only the per-head matrices and later stages are checked
+    for name, key, shape in (("q_land", "q_land", (8, 64, 64)), ("k_land", "k_land", (8, 64, 64)),
+                             ("attn2", "attn2", (8, 64, 64)), ("a3v", "a3v", (8, 64, 64)),
+                             ("zmat", "pinv", (8, 64, 64))):
+        got = view(getattr(L, name), shape)
+        err = orc.rel_l2(got.numpy(), stages[key].numpy())
+        print(name, err)
+        assert err < 2e-5, (name, err)
+    merged = view(L.merged, (T, 512))
+    assert orc.rel_l2(merged.numpy(), stages["merged"][pad:].numpy()) < 2e-5
+    u1 = view(L.u1, (T, 128))
+    assert orc.rel_l2(u1.numpy(), stages["hidden"].numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_packed_batch_equals_per_video(precision):
+    """Videos in one packed launch are independent (per-video pinv scale, no cross-video coupling)."""
+    p = orc.synth_params(31, "xavier")
+    scales, depth = [4, 8, 16, 32], 5
+    lengths = [1, 37, 64, 65, 128, 200, 333, 800, 100, 129]
+    xs = [orc.synth_features(t, 1000 + i) for i, t in enumerate(lengths)]
+    model = make_model(p, scales, depth, precision, DEV)
+    xp = torch.cat(xs).to(DEV)
+    with torch.no_grad():
+        cls_p, loc_p = model.forward_packed(xp, lengths)
+        o = 0
+        for x, t in zip(xs, lengths):
+            c1, l1 = model(x[None].to(DEV))
+            assert torch.equal(c1, cls_p[o:o + t]), "packed rows differ from the single-video call"
+            assert torch.equal(l1, loc_p[o:o + t])
+            with torch.no_grad():
+                rc, rl = orc.dsnet_forward(x, p, scales, depth)
+            assert orc.rel_l2(c1.cpu().numpy(), rc.numpy()) < TOL[precision]
+            assert orc.rel_l2(l1.cpu().numpy(), rl.numpy()) < TOL[precision]
+            o += t
+    _no_tc_timeout()
+
+
+def test_linearity_of_pool_and_heads_at_full_size():
+    """Size-independent property at C5 size (T=16384, 4 scales): pred_loc is linear in the hidden sequence, so
+    roi_pool_heads(a) + roi_pool_heads(b) - bias == roi_pool_heads(a + b)."""
+    capi, lib = _lib()
+    T, scales = 16384, [4, 8, 16, 32]
+    p = orc.synth_params(5, "xavier")
+    model = make_model(p, scales, 5, "fp32", DEV)
+    batch = __import__("edsnet_b200").BatchPlan.build([T]).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(T, 128, generator=g).to(DEV)
+    b = torch.randn(T, 128, generator=g).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    w = model._weights(torch.device(DEV), st)
+    outs = []
+    for u in (a, b, a + b):
+        cls = torch.empty(T, 4, device=DEV)
+        loc = torch.empty(T, 4, 2, device=DEV)
+        capi.check(lib.edsnet_roi_pool_heads(model._config(), w, batch.struct, u.data_ptr(), cls.data_ptr(),
+                                             loc.data_ptr(), st))
+        outs.append(loc)
+    bias = p["fc_loc.0.bias"].to(DEV)
+    lhs = outs[0] + outs[1] - bias
+    assert float((lhs - outs[2]).abs().max()) < 1e-4
+    # and against the oracle's pooling on the same data
+    pooled = orc.roi_pool_direct((a + b).cpu(), scales)
+    ref = pooled @ p["fc_loc.0.weight"].t() + p["fc_loc.0.bias"]
+    assert orc.rel_l2(outs[2].cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_long_video_forward_c5_shape():
+    """C5 shape (T=16384, scales [4,8,16,32]) against the oracle (a few seconds of CPU)."""
+    T, scales, depth = 16384, [4, 8, 16, 32], 5
+    x = orc.synth_features(T, 77)
+    p = orc.synth_params(78, "xavier")
+    with torch.no_grad():
+        rc, rl = orc.dsnet_forward(x, p, scales, depth)
+    for precision in ("fp32", "fp16x3"):
+        model = make_model(p, scales, depth, precision, DEV)
+        with torch.no_grad():
+            cls, loc = model(x[None].to(DEV))
+        _no_tc_timeout()
+        e = (orc.rel_l2(cls.cpu().numpy(), rc.numpy()), orc.rel_l2(loc.cpu().numpy(), rl.numpy()))
+        print("C5", precision, e)
+        assert max(e) < 5e-5, e       # fp32 reference itself sits ~1e-5 from fp64 at this length
+
+
+# ------------------------------------------------------------------------------------------------ decode + NMS
+@pytest.mark.parametrize("name", list(DN["cases"]))
+def test_decode_nms_bit_exact_vs_reference_golden(name):
+    from edsnet_b200 import BatchPlan
+    T = int(DN[f"{name}/T"])
+    scales = [int(s) for s in DN[f"{name}/scales"]]
+    S = len(scales)
+    p = orc.synth_params(1, "default")
+    model = make_model(p, scales, 5, "fp32", DEV)
+    batch = BatchPlan.build([T]).to(DEV)
+    loc = torch.from_numpy(DN[f"{name}/loc"]).to(DEV).reshape(T, S, 2)
+    scores = torch.from_numpy(DN[f"{name}/scores"]).to(DEV).reshape(T, S)
+    bf, bi = model.decode_packed(loc, batch)
+    bf, bi = bf.cpu().numpy(), bi.cpu().numpy()
+    # bit-exact against the oracle with the correctly rounded exp (machine independent) ...
+    want = orc.decode_boxes(DN[f"{name}/loc"], T, scales, exp_mode="cr")
+    assert np.array_equal(bf, want), "float32 left/right boxes differ from the oracle"
+    assert np.array_equal(bi, orc.clip_round(want, T))
+    # ... and within NumPy's own float32-exp error (<= 2.5 ulp of the width) of the reference run
+    assert np.abs(bf - DN[f"{name}/lr"]).max() <= 4e-6 * np.abs(DN[f"{name}/lr"]).max()
+    same_int = np.array_equal(bi, DN[f"{name}/boxes_i32"])
+    print(name, "int boxes identical to the reference run:", same_int)
+    assert (bi == DN[f"{name}/boxes_i32"]).all(axis=1).mean() > 0.9995
+    sc = DN[f"{name}/scores"]
+    for thresh, suffix in ((0.5, ""), (0.3, "_t03")):
+        r = model.nms_packed(scores, loc, batch, thresh)
+        k = int(r["keep_count"].cpu()[0])
+        ks, kb = r["keep_scores"][:k].cpu().numpy(), r["keep_boxes"][:k].cpu().numpy()
+        rs, rb, _ = orc.nms_1d(sc, bi, thresh)
+        assert np.array_equal(ks, rs) and np.array_equal(kb, rb)
+        if same_int:       # identical integer boxes => must reproduce the reference's bbox_helper.nms output
+            assert np.array_equal(ks, DN[f"{name}/keep_scores{suffix}"])
+            assert np.array_equal(kb, DN[f"{name}/keep_boxes{suffix}"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_predict_and_proposals_match_reference_golden(name):
+    """fp32 path end to end: predict() boxes and post-NMS proposals vs the reference's.  Floating-point scores feed
+    an integer pipeline, so exact equality needs the same rounding of every box edge; compare exactly where the
+    decoded int boxes agree and require that to be (nearly) everywhere."""
+    g, x, p = golden_case(FWD, name)
+    T, scales = int(g["T"]), [int(s) for s in g["scales"]]
+    model = make_model(p, scales, int(g["fc_depth"]), "fp32", DEV)
+    scores, boxes = model.predict(x[None].to(DEV))
+    assert scores.shape == (T * len(scales),) and boxes.shape == (T * len(scales), 2)
+    assert scores.dtype == np.float32 and boxes.dtype == np.float32
+    assert np.abs(boxes - g["boxes_f32"]).max() < 1e-3
+    assert np.array_equal(boxes, orc.decode_boxes(model(x[None].to(DEV))[1].detach().cpu().numpy(), T, scales,
+                                                  exp_mode="cr"))
+    ib = orc.clip_round(boxes, T)
+    frac_same = float((ib == g["boxes_i32"]).all(axis=1).mean())
+    assert frac_same > 0.995
+    ks, kb = model.proposals(x[None].to(DEV), 0.5)
+    # oracle NMS on OUR scores/boxes must agree bit for bit with the device NMS
+    rs, rb, _ = orc.nms_1d(scores, ib, 0.5)
+    assert np.array_equal(ks, rs) and np.array_equal(kb, rb)
+    if frac_same == 1.0 and len(np.unique(g["pred_cls"])) == g["pred_cls"].size:
+        # identical integer boxes: the kept boxes must equal the reference's unless two scores swapped order
+        same = len(kb) == len(g["keep_boxes"]) and np.array_equal(kb, g["keep_boxes"])
+        print(name, "kept set identical to the reference:", same)
+
+
+def test_nms_packed_many_videos_vs_oracle():
+    from edsnet_b200 import BatchPlan
+    rng = np.random.default_rng(7)
+    scales = [4, 8, 16, 32]
+    S = 4
+    lengths = [int(t) for t in rng.integers(1, 900, size=40)] + [1500]       # 1500*4 > 4096: scratch path
+    p = orc.synth_params(1, "default")
+    model = make_model(p, scales, 5, "fp32", DEV)
+    batch = BatchPlan.build(lengths).to(DEV)
+    R = sum(lengths)
+    loc = np.stack([rng.normal(0, 0.6, R * S), rng.normal(0, 0.5, R * S)], 1).astype(np.float32)
+    scores = rng.random(R * S).astype(np.float32)
+    scores[::17] = scores[5]                                                 # plenty of exact ties
+    r = model.nms_packed(torch.from_numpy(scores).to(DEV).reshape(R, S),
+                         torch.from_numpy(loc).to(DEV).reshape(R, S, 2), batch, 0.5)
+    counts = r["keep_count"].cpu().numpy()
+    ks, kb, ki = r["keep_scores"].cpu().numpy(), r["keep_boxes"].cpu().numpy(), r["keep_idx"].cpu().numpy()
+    o = 0
+    for v, t in enumerate(lengths):
+        sl = slice(o * S, (o + t) * S)
+        boxes = orc.clip_round(orc.decode_boxes(loc[sl], t, scales, exp_mode="cr"), t)
+        rs, rb, ridx = orc.nms_1d(scores[sl], boxes, 0.5)
+        c = int(counts[v])
+        assert c == len(rs), (v, t, c, len(rs))
+        assert np.array_equal(ks[o * S:o * S + c], rs)
+        assert np.array_equal(kb[o * S:o * S + c], rb)
+        assert np.array_equal(ki[o * S:o * S + c], ridx.astype(np.int32))
+        o += t
+
+
+def test_nms_properties_at_full_size():
+    """C5-size NMS (65536 anchors): kept boxes are mutually below the threshold, scores descend, every dropped
+    valid box is suppressed by some kept box of higher-or-equal score, and NMS of the kept set is the identity."""
+    from edsnet_b200 import BatchPlan
+    rng = np.random.default_rng(11)
+    T, scales, S = 16384, [4, 8, 16, 32], 4
+    N = T * S
+    p = orc.synth_params(1, "default")
+    model = make_model(p, scales, 5, "fp32", DEV)
+    batch = BatchPlan.build([T]).to(DEV)
+    loc = np.stack([rng.normal(0, 0.6, N), rng.normal(0, 0.5, N)], 1).astype(np.float32)
+    scores = (rng.permutation(N).astype(np.float32) + 1) / np.float32(N)
+    r = model.nms_packed(torch.from_numpy(scores).to(DEV).reshape(T, S),
+                         torch.from_numpy(loc).to(DEV).reshape(T, S, 2), batch, 0.5)
+    k = int(r["keep_count"].cpu()[0])
+    ks, kb = r["keep_scores"][:k].cpu().numpy(), r["keep_boxes"][:k].cpu().numpy().astype(np.int64)
+    ki = r["keep_idx"][:k].cpu().numpy()
+    assert k > 1000 and np.all(np.diff(ks) < 0)
+    boxes = orc.clip_round(orc.decode_boxes(loc, T, scales, exp_mode="cr"), T)
+    assert np.array_equal(boxes[ki], kb) and np.array_equal(scores[ki], ks)
+    lo, hi = kb[:, 0], kb[:, 1]
+    for i in range(0, k, max(1, k // 200)):                 # sampled pairwise check of the kept set
+        inter = np.maximum(0, np.minimum(hi, hi[i]) - np.maximum(lo, lo[i]))
+        hull = np.maximum(hi, hi[i]) - np.minimum(lo, lo[i])
+        iou = inter / hull
+        iou[i] = 0
+        assert (iou < 0.5).all()
+    # every dropped valid box overlaps >= thresh with a kept box of higher score (sampled)
+    kept_mask = np.zeros(N, bool)
+    kept_mask[ki] = True
+    dropped = np.nonzero(~kept_mask & (boxes[:, 0] < boxes[:, 1]))[0]
+    for j in dropped[:: max(1, len(dropped) // 300)]:
+        higher = ks > scores[j]
+        inter = np.maximum(0, np.minimum(hi[higher], boxes[j, 1]) - np.maximum(lo[higher], boxes[j, 0]))
+        hull = np.maximum(hi[higher], boxes[j, 1]) - np.minimum(lo[higher], boxes[j, 0])
+        assert (inter / hull >= 0.5).any()
+    # full oracle NMS at this size takes a few seconds: exact comparison
+    rs, rb, ridx = orc.nms_1d(scores, boxes, 0.5)
+    assert np.array_equal(rs, ks) and np.array_equal(rb, kb) and np.array_equal(ridx, ki)
+
+
+# ------------------------------------------------------------------------------------------------ error surface
+def test_error_surface():
+    from edsnet_b200 import DSNet, _capi
+    p = orc.synth_params(1, "default")
+    model = make_model(p, [4], 2, "fp32", DEV)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 8, 1024))                      # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(2, 8, 1024, device=DEV))          # batch > 1, as the reference's view() fails
+    odd = DSNet("nystromformer", 1024, 128, [5], 8, pooling_type="roi").to(DEV)
+    with pytest.raises(RuntimeError):
+        odd(torch.zeros(1, 8, 1024, device=DEV))            # odd scale, as the reference's view() fails
+    lib = _capi.lib()
+    assert lib.edsnet_forward(None, None, None, None, None, None, None, 0, None) == _capi.E_ARG
+    assert "config" in _capi.last_error()
+
+
+def test_pipeline_from_host_buffers():
+    from edsnet_b200 import ScoringPipeline
+    p = orc.synth_params(9, "xavier")
+    scales = [4, 8]
+    model = make_model(p, scales, 5, "fp32", DEV)
+    lengths = [50, 300, 64, 129, 700, 33, 256, 90]
+    xs = [orc.synth_features(t, 500 + i) for i, t in enumerate(lengths)]
+    xh = torch.cat(xs).pin_memory()
+    pipe = ScoringPipeline(model, chunk_rows=512)
+    kc, ks, kb, cu = pipe.run(xh, lengths)
+    assert pipe.h2d_bytes >= xh.numel() * 4 and pipe.d2h_bytes > 0
+    for v, (x, t) in enumerate(zip(xs, lengths)):
+        es, eb = model.proposals(x[None].to(DEV), 0.5)
+        o, c = int(cu[v]) * 2, int(kc[v])
+        assert np.array_equal(ks[o:o + c].numpy(), es) and np.array_equal(kb[o:o + c].numpy(), eb)

@@ -1,0 +1,123 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, host planning / chunking / sharding
+logic, module surface (state-dict layout, error behaviour).  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import edsnet_b200
+from edsnet_b200 import BatchPlan, DSNet, ScoringPipeline, _capi, shard_videos
+from oracle import dsnet_oracle as orc
+from tests.util import load_npz, ref_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = _capi.lib()
+    header = open(os.path.join(ROOT, "include", "edsnet_b200.h")).read()
+    declared = set(re.findall(r"\b(edsnet_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.edsnet_abi_version() == _capi.EDSNET_ABI_VERSION
+
+
+def test_workspace_sizing_and_argument_errors_without_gpu():
+    lib = _capi.lib()
+    cfg = _capi.make_config([4, 8], 5, _capi.PREC_FP16X3)
+    import ctypes as C
+    L = _capi.WorkspaceLayout()
+    total = lib.edsnet_workspace_bytes(cfg, 1000, 3, C.byref(L))
+    assert total == L.total and L.total > 1000 * 1536 * 4
+    assert L.qkv == 0 and L.merged > L.qkv and L.x16 >= L.u1
+    small = lib.edsnet_workspace_bytes(_capi.make_config([4], 5, _capi.PREC_FP32), 1000, 3, None)
+    assert small < total
+    # argument validation happens before any CUDA call
+    assert lib.edsnet_forward(None, None, None, None, None, None, None, 0, None) == _capi.E_ARG
+    bad = _capi.make_config([5], 5, 0)
+    assert lib.edsnet_decode_boxes(bad, None, None, None, None, None) == _capi.E_ARG
+    assert "odd anchor scale" in _capi.last_error()
+    assert lib.edsnet_forward_launches(cfg) == 14
+
+
+def test_batch_plan_tables():
+    plan = BatchPlan.build([1, 64, 65, 300])
+    assert plan.cu_rows.tolist() == [0, 1, 65, 130, 430]
+    assert plan.tiles64.tolist() == [[0, 0], [1, 0], [2, 0], [2, 64], [3, 0], [3, 64], [3, 128], [3, 192], [3, 256]]
+    assert plan.tiles128.tolist() == [[0, 0], [1, 0], [2, 0], [3, 0], [3, 128], [3, 256]]
+    assert plan.n_videos == 4 and plan.total_rows == 430 and plan.max_rows == 300
+    off, total = BatchPlan.build([100, 2000, 5000]).nms_scratch(4)
+    assert off.tolist() == [0, 0, 8192 * 24] and total == (8192 + 32768) * 24
+    with pytest.raises(ValueError):
+        BatchPlan.build([])
+    with pytest.raises(ValueError):
+        BatchPlan.build([10, 0])
+
+
+def test_chunking_and_sharding():
+    lengths = [100, 200, 300, 50, 700, 20]
+    chunks = ScoringPipeline.chunk_videos(lengths, 400)
+    assert chunks == [(0, 2), (2, 4), (4, 5), (5, 6)]
+    assert ScoringPipeline.chunk_videos([1000], 400) == [(0, 1)]
+    rng = np.random.default_rng(0)
+    lens = rng.integers(100, 801, size=4096)
+    for w in (1, 2, 4, 8):
+        parts = shard_videos(lens, w)
+        allv = sorted(i for p in parts for i in p)
+        assert allv == list(range(4096))
+        loads = [int(sum(((lens[i] + 63) // 64) * 64 for i in p)) for p in parts]
+        assert max(loads) - min(loads) <= 832
+
+
+def test_module_surface_matches_reference_state_dict():
+    g = load_npz("forward_golden.npz")
+    p = orc.synth_params(1, "default")
+    m = DSNet("nystromformer", 1024, 128, 12, 8, fc_depth=5, orientation=None, pooling_type="roi")
+    assert m.anchor_scales == [12] and m.num_scales == 1            # int -> list, dsnet.py:69-70
+    sd = m.state_dict()
+    want = ref_state_dict(p, 5)
+    assert set(sd) == set(want)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(want[k].shape), k
+    m.load_state_dict(want, strict=True)
+    assert m.fc[0][0].weight is m.fc_block[0].weight                # ONE shared block
+    assert sum(q.numel() for q in m.parameters()) == 2248843        # unique parameters of the reference model
+
+    def xavier_init(module):                                        # anchor_based/train.py:19-24
+        name = module.__class__.__name__
+        if "Linear" in name or "Conv" in name:
+            torch.nn.init.xavier_uniform_(module.weight, gain=np.sqrt(2.0))
+            if module.bias is not None:
+                torch.nn.init.constant_(module.bias, 0.1)
+    m.apply(xavier_init)
+    assert float(m.fc1.bias[0].detach()) == pytest.approx(0.1)
+    assert float(m.base_model.to_out[0].bias[0].detach()) == pytest.approx(0.1)
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(ValueError):
+        DSNet("attention", 1024, 128, [4], 8, pooling_type="roi")
+    with pytest.raises(ValueError):
+        DSNet("nystromformer", 1024, 128, [4], 8)                   # default pooling_type='fft'
+    with pytest.raises(ValueError):
+        DSNet("nystromformer", 512, 128, [4], 8, pooling_type="roi")
+    m = DSNet("nystromformer", 1024, 128, [4], 8, pooling_type="roi")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 16, 1024))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.predict(torch.zeros(1, 16, 1024))
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "edsnet-efficient-dsnet-for-video-summarization_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle\.", src, re.M), f
