@@ -60,6 +60,7 @@ SYMBOLS = {
                                     _P, _P, _P]),
     "edsnet_decode_boxes": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_forward_launches": (C.c_int, [C.POINTER(Config)]),
+    "edsnet_split_f16_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "edsnet_split_f16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     "edsnet_gemm": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                               C.c_int32, _P]),
@@ -67,6 +68,10 @@ SYMBOLS = {
     "edsnet_fc_stack": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), _P, _P, C.c_int32, _P]),
     "edsnet_roi_pool_heads": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_debug_tc_status": (C.c_int, [C.c_int32]),
+    "edsnet_debug_stage_timing": (C.c_int, [C.c_int32]),
+    "edsnet_debug_stage_count": (C.c_int, []),
+    "edsnet_debug_stage_name": (C.c_char_p, [C.c_int32]),
+    "edsnet_debug_stage_times": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]),
     "edsnet_debug_set_tc_variant": (C.c_int, [C.c_int32]),
 }
 
@@ -120,3 +125,13 @@ def make_config(scales, fc_depth: int, precision: int) -> Config:
         cfg.scales[i] = s
     cfg.precision = int(precision)
     return cfg
+
+
+def stage_times():
+    """{stage name: (total ms, launches)} of the recording started by edsnet_debug_stage_timing(1)."""
+    h = lib()
+    n = h.edsnet_debug_stage_count()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int32 * n)()
+    check(h.edsnet_debug_stage_times(ms, cnt, n))
+    return {h.edsnet_debug_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

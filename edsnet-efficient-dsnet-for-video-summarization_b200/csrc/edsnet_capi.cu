@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_f32.cuh"
@@ -31,6 +32,34 @@ int cuda_fail(cudaError_t e, const char* where) {
     } while (0)
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---- optional per-stage CUDA-event timing (bench / profiling only; off by default) ----
+enum Stage : int { ST_SPLIT = 0, ST_QKV, ST_LANDMARKS, ST_ATTN2, ST_A3V, ST_PINV, ST_ATTN_OUT, ST_TO_OUT, ST_LN,
+                   ST_FC1, ST_FC_STACK, ST_ROI, ST_DECODE, ST_NMS, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"split_f16", "to_qkv_gemm", "landmarks", "attn2_softmax", "a3v_stream",
+                                           "pinv_w", "attn_out_conv", "to_out_gemm", "layernorm1024", "fc1_gemm",
+                                           "fc_stack", "roi_pool_heads", "decode_boxes", "nms"};
+struct StageEvents { int stage; cudaEvent_t e0, e1; };
+bool g_stage_timing = false;
+std::vector<StageEvents> g_stage_events;
+
+struct StageScope {
+    cudaStream_t st;
+    bool on;
+    StageEvents ev;
+    StageScope(int stage, cudaStream_t s) : st(s), on(g_stage_timing) {
+        if (!on) return;
+        ev.stage = stage;
+        cudaEventCreate(&ev.e0);
+        cudaEventCreate(&ev.e1);
+        cudaEventRecord(ev.e0, st);
+    }
+    ~StageScope() {
+        if (!on) return;
+        cudaEventRecord(ev.e1, st);
+        g_stage_events.push_back(ev);
+    }
+};
 
 int check_cfg(const edsnet_config* cfg) {
     if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
@@ -75,11 +104,13 @@ cudaError_t opt_in_smem(K kernel, int bytes) {
 }
 
 int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, const float* B, const void* B16,
-                  float* C, int M, int N, int K, const float* bias, const float* res, int qcols, cudaStream_t st) {
+                  float* C, int M, int N, int K, const float* bias, const float* res, int qcols, cudaStream_t st,
+                  int stage = ST_QKV) {
+    StageScope scope(stage, st);
     if (M < 1 || N < 1 || K < 1) return fail(EDSNET_E_ARG, "gemm: empty problem");
     if (epilogue < 0 || epilogue > 3) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
     if ((epilogue >= 2 && !bias) || (epilogue == 3 && !res)) return fail(EDSNET_E_ARG, "gemm: epilogue operand is NULL");
-    GemmEpiArgs ep{bias, res, N, qcols};
+    GemmEpiArgs ep{bias, res, N, qcols, nullptr, nullptr};
     if (precision == EDSNET_PREC_FP32) {
         if (!A || !B || !C) return fail(EDSNET_E_ARG, "gemm: NULL operand");
         if (K % kGemmBK || N % 4) return fail(EDSNET_E_ARG, "gemm fp32: K must be a multiple of 16, N of 4");
@@ -94,6 +125,8 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
         return EDSNET_OK;
     }
     if (!A16 || !B16 || !C) return fail(EDSNET_E_ARG, "gemm tcgen05: fp16 operand planes are NULL");
+    ep.a_scale = split_scales(A16, M, K);
+    ep.b_scale = split_scales(B16, N, K);
     std::string msg;
     cudaError_t e = launch_gemm_tc(precision == EDSNET_PREC_FP16X3 ? 3 : 1, epilogue,
                                    reinterpret_cast<const __half*>(A16), reinterpret_cast<const __half*>(B16),
@@ -116,17 +149,32 @@ int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv
         attrs_done = true;
     }
     const int V = b->n_videos;
-    landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
-    CU_CHECK(cudaGetLastError(), "landmarks_kernel");
-    attn2_kernel<<<dim3(kHeads, V), 256, 0, st>>>(q_land, k_land, attn2, stats);
-    CU_CHECK(cudaGetLastError(), "attn2_kernel");
-    a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
-    CU_CHECK(cudaGetLastError(), "a3v_kernel");
-    pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
-    CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
-    attn_out_kernel<<<dim3(b->n_tiles64, kHeads), 256, kAttnOutSmem, st>>>(
-        qkv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles64), k_land, wmat, conv_w, merged);
-    CU_CHECK(cudaGetLastError(), "attn_out_kernel");
+    {
+        StageScope scope(ST_LANDMARKS, st);
+        landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
+        CU_CHECK(cudaGetLastError(), "landmarks_kernel");
+    }
+    {
+        StageScope scope(ST_ATTN2, st);
+        attn2_kernel<<<dim3(kHeads, V), 256, 0, st>>>(q_land, k_land, attn2, stats);
+        CU_CHECK(cudaGetLastError(), "attn2_kernel");
+    }
+    {
+        StageScope scope(ST_A3V, st);
+        a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
+        CU_CHECK(cudaGetLastError(), "a3v_kernel");
+    }
+    {
+        StageScope scope(ST_PINV, st);
+        pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
+    }
+    {
+        StageScope scope(ST_ATTN_OUT, st);
+        attn_out_kernel<<<dim3(b->n_tiles64, kHeads), 256, kAttnOutSmem, st>>>(
+            qkv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles64), k_land, wmat, conv_w, merged);
+        CU_CHECK(cudaGetLastError(), "attn_out_kernel");
+    }
     return EDSNET_OK;
 }
 
@@ -137,6 +185,7 @@ int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float
         CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
         attrs_done = true;
     }
+    StageScope scope(ST_FC_STACK, st);
     fc_stack_kernel<<<(rows + 63) / 64, 256, kFcStackSmem, st>>>(u_in, w->fcb_w, w->fcb_b, w->fcb_ln_w,
                                                                   w->fcb_ln_b, u_out, rows, cfg->fc_depth);
     CU_CHECK(cudaGetLastError(), "fc_stack_kernel");
@@ -153,6 +202,7 @@ int roi_impl(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_bat
         CU_CHECK(opt_in_smem(roi_pool_heads_kernel, smem), "smem opt-in roi_pool_heads");
         opted = smem;
     }
+    StageScope scope(ST_ROI, st);
     roi_pool_heads_kernel<<<b->n_tiles128, 256, smem, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
                                                              sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
                                                              pred_cls, pred_loc);
@@ -189,16 +239,22 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.u0 = take(R * kHidden * sizeof(float));
     L.u1 = take(R * kHidden * sizeof(float));
     L.x16 = off;
-    if (cfg && cfg->precision != EDSNET_PREC_FP32) take(2 * R * kFeat * sizeof(__half));
+    if (cfg && cfg->precision != EDSNET_PREC_FP32) take(split_f16_bytes(R, kFeat));
     L.total = off;
     if (layout) *layout = L;
     return L.total;
 }
 
+size_t edsnet_split_f16_bytes(int64_t rows, int64_t cols) {
+    if (rows < 0 || cols < 0) return 0;
+    return split_f16_bytes((size_t)rows, (size_t)cols);
+}
+
 int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream) {
-    if (!src || !dst_hi_lo || rows < 1 || cols < 1 || (cols & 3)) return fail(EDSNET_E_ARG, "split_f16: bad argument");
-    cudaError_t e = launch_split_f16(src, reinterpret_cast<__half*>(dst_hi_lo), (size_t)rows * (size_t)cols,
-                                     static_cast<cudaStream_t>(stream));
+    if (!src || !dst_hi_lo || rows < 1 || rows > (1 << 30)) return fail(EDSNET_E_ARG, "split_f16: bad argument");
+    if (cols != 512 && cols != 1024) return fail(EDSNET_E_ARG, "split_f16: cols must be 512 or 1024");
+    StageScope scope(ST_SPLIT, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_split_f16(src, dst_hi_lo, (int)rows, (int)cols, static_cast<cudaStream_t>(stream));
     CU_CHECK(e, "split_f16_kernel");
     return EDSNET_OK;
 }
@@ -213,6 +269,33 @@ int edsnet_debug_tc_status(int32_t reset) {
         if (e != cudaSuccess) { cuda_fail(e, "tc status reset"); return -1; }
     }
     return flag;
+}
+
+int edsnet_debug_stage_timing(int32_t enable) {
+    for (auto& ev : g_stage_events) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); }
+    g_stage_events.clear();
+    g_stage_timing = enable != 0;
+    return EDSNET_OK;
+}
+
+int edsnet_debug_stage_count(void) { return ST_COUNT; }
+const char* edsnet_debug_stage_name(int32_t stage) {
+    return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : "";
+}
+
+int edsnet_debug_stage_times(double* ms_sum, int32_t* launches, int32_t n) {
+    if (!ms_sum || !launches || n < ST_COUNT) return fail(EDSNET_E_ARG, "stage_times: need ST_COUNT slots");
+    for (int i = 0; i < n; ++i) { ms_sum[i] = 0.0; launches[i] = 0; }
+    for (auto& ev : g_stage_events) {
+        CU_CHECK(cudaEventSynchronize(ev.e1), "stage event sync");
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, ev.e0, ev.e1), "stage event elapsed");
+        ms_sum[ev.stage] += ms;
+        launches[ev.stage] += 1;
+    }
+    for (auto& ev : g_stage_events) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); }
+    g_stage_events.clear();
+    return EDSNET_OK;
 }
 
 int edsnet_debug_set_tc_variant(int32_t variant) {
@@ -297,11 +380,14 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         merged16 = ws + L.x16;
     }
     rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
-                       kInner, w->to_out_b, x, 0, st);
+                       kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
     if (rc) return rc;
     // 4. LayerNorm(1024) -> fc1                                                 (dsnet.py:106)
-    layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
-    CU_CHECK(cudaGetLastError(), "layernorm1024_kernel");
+    {
+        StageScope scope(ST_LN, st);
+        layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
+        CU_CHECK(cudaGetLastError(), "layernorm1024_kernel");
+    }
     const void* yn16 = nullptr;
     if (prec != EDSNET_PREC_FP32) {
         rc = edsnet_split_f16(F(L.yn), ws + L.x16, R, kFeat, stream);
@@ -309,7 +395,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         yn16 = ws + L.x16;
     }
     rc = gemm_dispatch(prec, EPI_BIAS, F(L.yn), yn16, w->fc1_w, w->fc1_w16, F(L.u0), R, kHidden, kFeat, w->fc1_b,
-                       nullptr, 0, st);
+                       nullptr, 0, st, ST_FC1);
     if (rc) return rc;
     // 5. shared fc block x depth                                                (dsnet.py:107-108)
     rc = fc_stack_impl(cfg, w, F(L.u0), F(L.u1), R, st);
@@ -362,14 +448,20 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
         CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemBytes), "smem opt-in nms");
         attrs_done = true;
     }
-    decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0, st>>>(
-        pred_loc, batch->cu_rows, sl, boxes_f32, boxes_i32);
-    CU_CHECK(cudaGetLastError(), "decode_boxes_kernel");
-    nms_kernel<<<batch->n_videos, kNmsThreads, kNmsSmemBytes, st>>>(
-        pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh,
-        reinterpret_cast<const long long*>(nms_scratch_off), static_cast<unsigned char*>(nms_scratch), keep_count,
-        keep_idx, keep_scores, keep_boxes);
-    CU_CHECK(cudaGetLastError(), "nms_kernel");
+    {
+        StageScope scope(ST_DECODE, st);
+        decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0, st>>>(
+            pred_loc, batch->cu_rows, sl, boxes_f32, boxes_i32);
+        CU_CHECK(cudaGetLastError(), "decode_boxes_kernel");
+    }
+    {
+        StageScope scope(ST_NMS, st);
+        nms_kernel<<<batch->n_videos, kNmsThreads, kNmsSmemBytes, st>>>(
+            pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh,
+            reinterpret_cast<const long long*>(nms_scratch_off), static_cast<unsigned char*>(nms_scratch), keep_count,
+            keep_idx, keep_scores, keep_boxes);
+        CU_CHECK(cudaGetLastError(), "nms_kernel");
+    }
     return EDSNET_OK;
 }
 

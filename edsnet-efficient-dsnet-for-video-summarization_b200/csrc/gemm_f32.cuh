@@ -17,6 +17,8 @@ struct GemmEpiArgs {
     const float* res;      // [M, ldr]
     int ldr;
     int qcols;
+    const float* a_scale;  // tcgen05 path: [M] power-of-two factor undoing the row scaling of A's fp16 planes
+    const float* b_scale;  // tcgen05 path: [N] same for B
 };
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmLd = 132;

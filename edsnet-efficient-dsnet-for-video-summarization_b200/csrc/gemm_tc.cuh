@@ -1,7 +1,15 @@
 // tcgen05 / TMEM / TMA GEMM for the dense projections (to_qkv, to_out, fc1):
-//   C[M,N] (fp32) = A[M,K] . B[N,K]^T,  operands given as fp16 hi/lo planes (x = hi + lo, |lo| <= ulp(hi)/2).
-//   PASSES = 3: acc += A_hi.B_hi + A_hi.B_lo + A_lo.B_hi   (fp32-grade accuracy: drops only the lo.lo term)
-//   PASSES = 1: acc += A_hi.B_hi                           (plain fp16 operands)
+//   C[M,N] (fp32) = A[M,K] . B[N,K]^T,  operands given as fp16 hi/lo planes of the ROW-SCALED operand:
+//   row r of X is multiplied by a power of two 2^s_r that puts its largest magnitude in [2^14, 2^15) (so that both
+//   hi = fp16(x 2^s) and lo = fp16(x 2^s - hi) stay normal fp16 numbers for every element that matters), and the
+//   epilogue multiplies the accumulator by 2^-s_m 2^-s_n -- exact, powers of two.
+//   PASSES = 3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi   (fp32-grade accuracy: drops only the lo.lo term)
+//   PASSES = 1: A_hi.B_hi                           (plain fp16 operands)
+// The tensor core adds each K=16 step into the fp32 accumulator with TRUNCATION (measured: a relative bias of about
+// 2e-8 per tcgen05.mma, 3.7e-6 after the 192 steps of a K=1024 three-pass product).  PASSES = 3 therefore keeps FOUR
+// accumulators in TMEM (4 x 128 columns = all 512): the hi.hi products rotate over three of them by K block (<= 24
+// steps each for K = 1024), the two small cross terms go to the fourth, and the epilogue adds the four in fp32 with
+// round-to-nearest.
 // Per CTA: one 128 x BN output tile.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 =
 // epilogue (TMEM -> registers -> global).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
 // by full/empty mbarriers; operands land in shared memory in the 128B (BK=64) / 64B (BK=32) swizzled K-major
@@ -88,6 +96,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor, K-major operand, rows of BK fp16 = one swizzle atom wide.
 //   bits  0-13 start address >> 4      bits 16-29 leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   bits 32-45 stride byte offset >> 4 (8 rows x swizzle width)            bits 46-47 descriptor version = 1
@@ -110,6 +128,9 @@ struct TcCfg {
     static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
     static constexpr int kBTile = BN * BK * 2;
     static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
+    static constexpr int kAccs = PASSES == 3 ? 4 : 1;      // TMEM accumulators (see the header comment)
+    static constexpr int kTmemCols = kAccs * BN;
+    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
     static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr int kThreads = 192;
@@ -144,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,15 +202,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t st = smem_base + s * Cfg::kStageBytes;
                 const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
                 const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
+                // PASSES == 3: hi.hi of K block kb -> accumulator kb % 3, both cross terms -> accumulator 3
+                const uint32_t acc_main = tmem_acc + (PASSES == 3 ? (uint32_t)((kb % 3) * BN) : 0u);
+                const uint32_t acc_lo = tmem_acc + 3u * BN;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint32_t koff = k * 32;           // 16 fp16 = 32 bytes further along K inside the atom
                     const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
-                    umma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                    const bool first_main = PASSES == 3 ? (kb < 3 && k == 0) : ((kb | k) == 0);
+                    umma_f16(acc_main, dah, dbh, idesc, first_main ? 0u : 1u);
                     if (PASSES == 3) {
                         const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
-                        umma_f16(tmem_acc, dah, dbl, idesc, 1u);
-                        umma_f16(tmem_acc, dal, dbh, idesc, 1u);
+                        umma_f16(acc_lo, dah, dbl, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16(acc_lo, dal, dbh, idesc, 1u);
                     }
                 }
                 umma_commit(empty_bar(s));                  // frees the smem slot once these MMAs have read it
@@ -203,17 +228,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(tmem_full_bar, 0u);
         tc_fence_after();
         float* crow = C + (size_t)row * N + n0;
+        const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
         const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
+        const int n_main = PASSES == 3 ? (nk < 3 ? nk : 3) : 1;     // accumulators that received hi.hi products
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            const uint32_t t0 = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            uint32_t r[16];
+            float v[16];
+            tmem_ld16_nowait(t0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (PASSES == 3) {
+                // (acc0 + acc1) + (acc2 + acc3), every add rounded to nearest
+                uint32_t r1[16], r2[16], r3[16];
+                tmem_ld16_nowait(t0 + 3u * BN, r3);
+                if (n_main > 1) tmem_ld16_nowait(t0 + 1u * BN, r1);
+                if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN, r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a01 = n_main > 1 ? __fadd_rn(v[j], __uint_as_float(r1[j])) : v[j];
+                    const float a23 = n_main > 2 ? __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j]))
+                                                 : __uint_as_float(r3[j]);
+                    v[j] = __fadd_rn(a01, a23);
+                }
+            }
             if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     const int c = n0 + c0 + j;
+                    {
+                        const float4 rb = ldg4(ep.b_scale + c);
+                        o.x *= ra * rb.x; o.y *= ra * rb.y; o.z *= ra * rb.z; o.w *= ra * rb.w;
+                    }
                     if (EPI == EPI_QSCALE) {
                         if (c < ep.qcols) { o.x *= 0.125f; o.y *= 0.125f; o.z *= 0.125f; o.w *= 0.125f; }
                     }
@@ -232,21 +282,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_acc, BN);
+    if (warp == 2) tmem_dealloc(tmem_acc, Cfg::kTmemCols);
 }
 
-// ---- fp32 -> fp16 hi/lo planes ----
+// ---- fp32 [rows][cols] -> row-scaled fp16 hi/lo planes + per-row inverse scale ----
+// One warp per row; COLS in {512, 1024}.  scale = 2^(14 - floor(log2(max|x|))) (1 for an all-zero row).
+template <int COLS>
 __global__ void __launch_bounds__(256)
-split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n4) {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-        const float4 x = ldg4(src + i * 4);
-        const __half h0 = __float2half_rn(x.x), h1 = __float2half_rn(x.y), h2 = __float2half_rn(x.z), h3 = __float2half_rn(x.w);
-        const __half l0 = __float2half_rn(x.x - __half2float(h0)), l1 = __float2half_rn(x.y - __half2float(h1));
-        const __half l2 = __float2half_rn(x.z - __half2float(h2)), l3 = __float2half_rn(x.w - __half2float(h3));
-        __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
-        __half2 ll[2] = {__halves2half2(l0, l1), __halves2half2(l2, l3)};
-        *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<uint2*>(hh);
-        *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<uint2*>(ll);
+split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
+                 float* __restrict__ inv_scale, int rows) {
+    constexpr int V = COLS / 128;                       // float4 per lane
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = src + (size_t)row * COLS;
+    float4 x[V];
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        x[i] = ldg4(s + (i * 32 + lane) * 4);
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x[i].x), fabsf(x[i].y)), fmaxf(fabsf(x[i].z), fabsf(x[i].w))));
+    }
+    mx = warp_max(mx);
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+    e = max(-100, min(100, e));
+    const float sc = ldexpf(1.f, e);
+    if (lane == 0) inv_scale[row] = ldexpf(1.f, -e);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float v[4] = {x[i].x * sc, x[i].y * sc, x[i].z * sc, x[i].w * sc};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2half_rn(v[j]);
+            l[j] = __float2half_rn(v[j] - __half2float(h[j]));
+        }
+        __half2 hh[2] = {__halves2half2(h[0], h[1]), __halves2half2(h[2], h[3])};
+        __half2 ll[2] = {__halves2half2(l[0], l[1]), __halves2half2(l[2], l[3])};
+        const size_t o = (size_t)row * COLS + (i * 32 + lane) * 4;
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(ll);
     }
 }
 
@@ -315,13 +390,21 @@ template <int PASSES, int EPI>
 cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                          cudaStream_t st, std::string* msg) {
     const int variant = variant_ref();
-    if (N % 256 == 0) {
-        if (variant == 1) return launch_variant<256, 32, 2, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-        return launch_variant<256, 64, PASSES == 3 ? 2 : 4, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-    }
-    if (N % 128 == 0) {
-        if (variant == 1) return launch_variant<128, 32, 3, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-        return launch_variant<128, 64, 3, PASSES, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+    if (PASSES == 3) {
+        // four 128-column accumulators fill TMEM: BN is 128
+        if (N % 128 == 0) {
+            if (variant == 1) return launch_variant<128, 32, 4, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            return launch_variant<128, 64, 3, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        }
+    } else {
+        if (N % 256 == 0) {
+            if (variant == 1) return launch_variant<256, 32, 2, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            return launch_variant<256, 64, 4, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        }
+        if (N % 128 == 0) {
+            if (variant == 1) return launch_variant<128, 32, 3, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            return launch_variant<128, 64, 3, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        }
     }
     if (msg) *msg = "N must be a multiple of 128";
     return cudaErrorInvalidValue;
@@ -340,10 +423,19 @@ static cudaError_t launch_gemm_tc(int passes, int epilogue, const __half* A16, c
     return cudaErrorInvalidValue;
 }
 
-static cudaError_t launch_split_f16(const float* src, __half* dst, size_t n, cudaStream_t st) {
-    const size_t n4 = n / 4;
-    size_t blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    tc::split_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, dst + n, n4);
+// dst layout: hi plane [rows][cols] fp16 | lo plane [rows][cols] fp16 | inverse row scales [rows] fp32
+static inline size_t split_f16_bytes(size_t rows, size_t cols) { return rows * cols * 4 + rows * 4; }
+static inline const float* split_scales(const void* planes, size_t rows, size_t cols) {
+    return reinterpret_cast<const float*>(static_cast<const unsigned char*>(planes) + rows * cols * 4);
+}
+
+static cudaError_t launch_split_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st) {
+    __half* hi = static_cast<__half*>(dst);
+    __half* lo = hi + (size_t)rows * cols;
+    float* sc = reinterpret_cast<float*>(lo + (size_t)rows * cols);
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
+    else if (cols == 512) tc::split_f16_kernel<512><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

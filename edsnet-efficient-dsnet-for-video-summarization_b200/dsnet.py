@@ -133,7 +133,8 @@ class DSNet(nn.Module):
             lib = _capi.lib()
             for name, p in (("to_qkv_w16", params[0]), ("to_out_w16", params[1]), ("fc1_w16", params[6])):
                 src = p.detach().contiguous()
-                planes = torch.empty((2,) + tuple(src.shape), dtype=torch.float16, device=device)
+                planes = torch.empty(lib.edsnet_split_f16_bytes(src.shape[0], src.shape[1]), dtype=torch.uint8,
+                                     device=device)
                 _capi.check(lib.edsnet_split_f16(src.data_ptr(), planes.data_ptr(), src.shape[0], src.shape[1],
                                                  stream))
                 keep += [src, planes]
@@ -173,9 +174,14 @@ class DSNet(nn.Module):
         self._check_input(x)
         if x.dim() != 2 or x.shape[1] != NUM_FEATURE:
             raise RuntimeError(f"expected [rows, {NUM_FEATURE}] features, got {tuple(x.shape)}")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training:
+            # train(): Dropout(0.5) inside the shared fc block is active (dsnet.py:91-95) -> differentiable torch-op
+            # graph on the GPU (training is the next row to go native, see autograd.py)
             from .autograd import scoring_with_grad
             return scoring_with_grad(self, x, batch)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import kernel_forward_with_grad
+            return kernel_forward_with_grad(self, x, batch)
         return self._forward_nograd(x, batch)
 
     def _forward_nograd(self, x, batch):

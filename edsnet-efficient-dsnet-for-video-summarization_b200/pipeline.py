@@ -24,6 +24,7 @@ class ScoringPipeline:
         self.depth = max(2, int(depth))
         self._dev_x = None
         self._streams = None
+        self._out = None                 # pinned result buffers, reused while the batch geometry is unchanged
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.kernel_launches = 0
@@ -54,7 +55,7 @@ class ScoringPipeline:
     def run(self, x_host: torch.Tensor, lengths: Sequence[int], device=None):
         """x_host: [sum(lengths), 1024] float32 in (preferably pinned) host memory.
         Returns (keep_count int32 [V], keep_scores float32 [R*S], keep_boxes int32 [R*S, 2], cu_rows int32 [V+1]) as
-        pinned host tensors; video v's proposals are entries cu_rows[v]*S .. +keep_count[v], descending score --
+        pinned host tensors (owned by the pipeline and overwritten by the next run); video v's proposals are entries cu_rows[v]*S .. +keep_count[v], descending score --
         the (keep_scores, keep_boxes) pair evaluate.py:28 gets from bbox_helper.nms."""
         model = self.model
         device = torch.device(device) if device is not None else next(model.parameters()).device
@@ -73,9 +74,11 @@ class ScoringPipeline:
         max_rows = max(int(cu[b] - cu[a]) for a, b in chunks)
         self._setup(device, max_rows)
         s_in, s_cmp, s_out = self._streams
-        keep_count = torch.empty(V, dtype=torch.int32).pin_memory()
-        keep_scores = torch.empty(R * S, dtype=torch.float32).pin_memory()
-        keep_boxes = torch.empty((R * S, 2), dtype=torch.int32).pin_memory()
+        if self._out is None or self._out[0].numel() != V or self._out[1].numel() != R * S:
+            self._out = (torch.empty(V, dtype=torch.int32).pin_memory(),
+                         torch.empty(R * S, dtype=torch.float32).pin_memory(),
+                         torch.empty((R * S, 2), dtype=torch.int32).pin_memory())
+        keep_count, keep_scores, keep_boxes = self._out
         free_ev = [None] * self.depth           # buffer reusable once its chunk's kernels are done
         self.h2d_bytes = self.d2h_bytes = self.kernel_launches = 0
         cur = torch.cuda.current_stream(device)

@@ -60,8 +60,10 @@ class BatchPlan:
         return int(self.lengths.max())
 
     def packed_tables(self) -> np.ndarray:
-        """cu_rows | tiles64 | tiles128 in one int32 array (one H2D copy)."""
-        return np.concatenate([self.cu_rows, self.tiles64.reshape(-1), self.tiles128.reshape(-1)])
+        """cu_rows (padded to an even count: the tile tables are read as 8-byte int2) | tiles64 | tiles128 in one
+        int32 array (one H2D copy)."""
+        pad = np.zeros(self.cu_rows.size % 2, dtype=np.int32)
+        return np.concatenate([self.cu_rows, pad, self.tiles64.reshape(-1), self.tiles128.reshape(-1)])
 
     def nms_scratch(self, n_scales: int):
         """Byte offsets (int64 [V]) and total bytes of the global NMS scratch, needed only by videos with more than
@@ -87,9 +89,9 @@ class DeviceBatch:
             host = host.pin_memory()
         self._host = host                      # keeps the pinned staging buffer alive until the async copy ran
         self.tables = host.to(device, non_blocking=True)
-        n_cu = plan.cu_rows.size
+        n_cu = plan.cu_rows.size + plan.cu_rows.size % 2
         n64 = plan.tiles64.shape[0]
-        self.cu_rows = self.tables[:n_cu]
+        self.cu_rows = self.tables[:plan.cu_rows.size]
         self.tiles64 = self.tables[n_cu:n_cu + 2 * n64]
         self.tiles128 = self.tables[n_cu + 2 * n64:]
         b = _capi.Batch()

@@ -74,10 +74,10 @@ typedef struct {
     const float* loc_w;        /* fc_loc.0.weight               (2, 128)     */
     const float* loc_b;        /* fc_loc.0.bias                 (2)          */
     /* fp16 hi/lo splits of the three projection weights, produced by edsnet_split_f16; required for the
-     * tcgen05 precisions, ignored for EDSNET_PREC_FP32.  Each is [rows][cols] fp16, hi then lo plane. */
-    const void* to_qkv_w16;    /* 2 x (1536, 1024) fp16 */
-    const void* to_out_w16;    /* 2 x (1024, 512)  fp16 */
-    const void* fc1_w16;       /* 2 x (128, 1024)  fp16 */
+     * tcgen05 precisions, ignored for EDSNET_PREC_FP32.  Layout: see edsnet_split_f16. */
+    const void* to_qkv_w16;    /* planes of (1536, 1024) */
+    const void* to_out_w16;    /* planes of (1024, 512)  */
+    const void* fc1_w16;       /* planes of (128, 1024)  */
 } edsnet_weights;
 
 /* A packed batch of videos.  All arrays [dev], int32.  Tile tables are built by the host (see
@@ -108,7 +108,7 @@ typedef struct {
     size_t yn;         /* [rows][1024] LayerNorm(y)           (aliases qkv)           */
     size_t u0;         /* [rows][128] fc1 output                                      */
     size_t u1;         /* [rows][128] after the fc stack                              */
-    size_t x16;        /* tcgen05 precisions: fp16 hi/lo planes of x, 2 x [rows][1024]*/
+    size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
     size_t total;
 } edsnet_workspace_layout;
 
@@ -146,7 +146,11 @@ int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, con
 /* Number of kernel launches one edsnet_forward call enqueues for this configuration (bench bookkeeping). */
 int edsnet_forward_launches(const edsnet_config* cfg);
 
-/* fp32 (rows, cols) -> fp16 hi plane followed by fp16 lo plane (hi = fp16(w), lo = fp16(w - hi)). */
+/* fp32 (rows, cols), cols in {512, 1024} -> operand planes for the tcgen05 precisions.  Every row is first scaled
+ * by a power of two that puts its largest magnitude in [2^14, 2^15) (keeps hi AND lo in fp16's normal range).
+ * dst layout, edsnet_split_f16_bytes(rows, cols) bytes: hi plane [rows][cols] fp16 (hi = fp16(x 2^s)) |
+ * lo plane [rows][cols] fp16 (lo = fp16(x 2^s - hi)) | inverse scales [rows] fp32 (2^-s). */
+size_t edsnet_split_f16_bytes(int64_t rows, int64_t cols);
 int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream);
 
 /* ---- stage-level entry points (tests, per-kernel timing, ncu) ---- */
@@ -171,6 +175,14 @@ int edsnet_roi_pool_heads(const edsnet_config* cfg, const edsnet_weights* w, con
 /* Synchronous.  Returns 1 if a tcgen05 GEMM pipeline wait timed out since the last reset (the kernel then drained
  * with undefined results instead of hanging), 0 if not, -1 on CUDA error.  reset != 0 clears the flag. */
 int edsnet_debug_tc_status(int32_t reset);
+/* Per-stage CUDA-event timing of every kernel the entry points launch (bench / profiling; off by default, adds two
+ * event records per launch, not thread safe).  enable != 0 starts a fresh recording, 0 stops and discards.
+ * edsnet_debug_stage_times synchronises on the recorded events, fills ms_sum[stage] / launches[stage] for
+ * stage < edsnet_debug_stage_count() and clears the recording. */
+int edsnet_debug_stage_timing(int32_t enable);
+int edsnet_debug_stage_count(void);
+const char* edsnet_debug_stage_name(int32_t stage);
+int edsnet_debug_stage_times(double* ms_sum, int32_t* launches, int32_t n);
 /* Tile variant of the tcgen05 GEMM: 0 = BK 64 / 128-byte swizzle (default), 1 = BK 32 / 64-byte swizzle. */
 int edsnet_debug_set_tc_variant(int32_t variant);
 

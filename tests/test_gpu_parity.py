@@ -52,8 +52,8 @@ def test_gemm_stage(precision, M, N, K, epi):
     A16 = B16 = None
     st = torch.cuda.current_stream().cuda_stream
     if precision != "fp32":
-        A16 = torch.empty((2, M, K), dtype=torch.float16, device=DEV)
-        B16 = torch.empty((2, N, K), dtype=torch.float16, device=DEV)
+        A16 = torch.empty(lib.edsnet_split_f16_bytes(M, K), dtype=torch.uint8, device=DEV)
+        B16 = torch.empty(lib.edsnet_split_f16_bytes(N, K), dtype=torch.uint8, device=DEV)
         capi.check(lib.edsnet_split_f16(Ad.data_ptr(), A16.data_ptr(), M, K, st))
         capi.check(lib.edsnet_split_f16(Bd.data_ptr(), B16.data_ptr(), N, K, st))
     capi.check(lib.edsnet_gemm(capi.PRECISIONS[precision], epi, Ad.data_ptr(),
@@ -65,7 +65,7 @@ def test_gemm_stage(precision, M, N, K, epi):
     assert torch.isfinite(out).all()
     err = float((out - ref).norm() / ref.norm())
     # operand rounding: fp32/fp16x3 ~ 2^-22..2^-24 per product, fp16 ~ 2^-11
-    assert err < {"fp32": 2e-6, "fp16x3": 2e-6, "fp16": 1e-3}[precision], err
+    assert err < {"fp32": 1e-6, "fp16x3": 1e-6, "fp16": 1e-3}[precision], err
 
 
 # ------------------------------------------------------------------------------------------------ forward
@@ -114,7 +114,8 @@ def test_forward_stages_match_oracle():
         got = view(getattr(L, name), shape)
         err = orc.rel_l2(got.numpy(), stages[key].numpy())
         print(name, err)
-        assert err < 2e-5, (name, err)
+        # the Newton-Schulz chain amplifies rounding differences of an ill-conditioned attn2 (cond ~1e3..1e4)
+        assert err < (2e-3 if name == "zmat" else 2e-5), (name, err)
     merged = view(L.merged, (T, 512))
     assert orc.rel_l2(merged.numpy(), stages["merged"][pad:].numpy()) < 2e-5
     u1 = view(L.u1, (T, 128))
@@ -237,7 +238,7 @@ def test_predict_and_proposals_match_reference_golden(name):
     scores, boxes = model.predict(x[None].to(DEV))
     assert scores.shape == (T * len(scales),) and boxes.shape == (T * len(scales), 2)
     assert scores.dtype == np.float32 and boxes.dtype == np.float32
-    assert np.abs(boxes - g["boxes_f32"]).max() < 1e-3
+    assert np.abs(boxes - g["boxes_f32"]).max() < 1e-3 + 2e-6 * np.abs(g["boxes_f32"]).max()
     assert np.array_equal(boxes, orc.decode_boxes(model(x[None].to(DEV))[1].detach().cpu().numpy(), T, scales,
                                                   exp_mode="cr"))
     ib = orc.clip_round(boxes, T)
@@ -333,7 +334,7 @@ def test_error_surface():
         model(torch.zeros(1, 8, 1024))                      # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         model(torch.zeros(2, 8, 1024, device=DEV))          # batch > 1, as the reference's view() fails
-    odd = DSNet("nystromformer", 1024, 128, [5], 8, pooling_type="roi").to(DEV)
+    odd = DSNet("nystromformer", 1024, 128, [5], 8, pooling_type="roi").to(DEV).eval()
     with pytest.raises(RuntimeError):
         odd(torch.zeros(1, 8, 1024, device=DEV))            # odd scale, as the reference's view() fails
     lib = _capi.lib()
@@ -356,3 +357,31 @@ def test_pipeline_from_host_buffers():
         es, eb = model.proposals(x[None].to(DEV), 0.5)
         o, c = int(cu[v]) * 2, int(kc[v])
         assert np.array_equal(ks[o:o + c].numpy(), es) and np.array_equal(kb[o:o + c].numpy(), eb)
+
+
+def test_gradients_match_the_oracle_graph():
+    """eval()-mode call with grad enabled: values from the kernels, gradients of a cls+loc loss must equal the
+    gradients of the oracle's torch graph (fp32, CPU) -- the parity check config 3's all-reduce builds on."""
+    p = orc.synth_params(21, "xavier")
+    scales, depth, T = [4, 8], 3, 90
+    x = orc.synth_features(T, 5)
+    g = torch.Generator().manual_seed(0)
+    wc = torch.randn(T, 2, generator=g)
+    wl = torch.randn(T, 2, 2, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    rc, rl = orc.dsnet_forward(x, pr, scales, depth)
+    ((rc * wc).sum() + (rl * wl).sum()).backward()
+    model = make_model(p, scales, depth, "fp32", DEV)
+    cls, loc = model(x[None].to(DEV))
+    assert cls.requires_grad and orc.rel_l2(cls.detach().cpu().numpy(), rc.detach().numpy()) < 1e-5
+    ((cls * wc.to(DEV)).sum() + (loc * wl.to(DEV)).sum()).backward()
+    names = {"base_model.to_qkv.weight": model.base_model.to_qkv.weight, "fc1.weight": model.fc1.weight,
+             "fc_block.0.weight": model.fc_block[0].weight, "fc_loc.0.weight": model.fc_loc[0].weight,
+             "base_model.res_conv.weight": model.base_model.res_conv.weight, "layer_norm.bias": model.layer_norm.bias}
+    for k, q in names.items():
+        e = orc.rel_l2(q.grad.cpu().numpy(), pr[k].grad.numpy())
+        assert e < 2e-3, (k, e)          # fp32 backward through the pinv chain: CPU vs GPU summation order
+    # train(): dropout active, outputs differ from eval and carry a graph
+    model.train()
+    c2, _ = model(x[None].to(DEV))
+    assert c2.requires_grad and not torch.equal(c2.detach(), cls.detach())
