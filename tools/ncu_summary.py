@@ -1,0 +1,68 @@
+"""Summarise ncu outputs for profiles/:  launch list (gpu__time_duration per launch) -> per-kernel shares, and the key
+counters of a `--set full` report.
+
+    python tools/ncu_summary.py launches gpurun_out/launches.csv > profiles/rNN_launches.md
+    python tools/ncu_summary.py report gpurun_out/prof.ncu-rep > profiles/rNN_kernel.md
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum", "smsp__cycles_active.avg",
+        "sm__cycles_elapsed.avg.per_second", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
+        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        name = re.sub(r"^void ", "", name)[:90]
+        a = agg.setdefault(name, [0, 0.0, 1e30, 0.0])
+        a[0] += 1
+        a[1] += v
+        a[2] = min(a[2], v)
+        a[3] = max(a[3], v)
+    tot = sum(a[1] for a in agg.values())
+    print("| kernel | launches | total ms | avg us | min us | max us | share |")
+    print("|---|---:|---:|---:|---:|---:|---:|")
+    for k, (n, t, lo, hi) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {n} | {t / 1e3:.2f} | {t / n:.1f} | {lo:.1f} | {hi:.1f} | {t / tot:.1%} |")
+    print(f"\ntotal {tot / 1e3:.2f} ms over {sum(a[0] for a in agg.values())} launches "
+          "(ncu serialises launches and runs them cold-cache: compare shares, not absolutes)")
+
+
+def report(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    name_i = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        print(f"### `{r[name_i][:110]}`\n")
+        print("| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"| {k} | {r[i]} | {units[i]} |")
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
