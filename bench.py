@@ -152,7 +152,8 @@ def main():
     ap.add_argument("--videos", type=int, default=N_VIDEOS, help="videos per GPU per step")
     ap.add_argument("--scales", type=int, nargs="+", default=[12])
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "fp16"])
-    ap.add_argument("--chunk-rows", type=int, default=32768)
+    ap.add_argument("--chunk-rows", type=int, default=32768, help="rows per chunk of the host->device pipeline (e2e)")
+    ap.add_argument("--device-chunk-rows", type=int, default=262144, help="rows per launch sequence, device-resident arm")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -215,7 +216,7 @@ def main():
     log(f"[rank {rank}] {args.videos} videos, {R} frames, x = {R * 4096 / 2**30:.2f} GiB")
     x_dev = synth_features_device(R, dev, SEED + 1000 + rank)
     pipe = ScoringPipeline(model, chunk_rows=args.chunk_rows, nms_thresh=NMS_THRESH)
-    chunks = pipe.chunk_videos(lengths, args.chunk_rows)
+    chunks = pipe.chunk_videos(lengths, args.device_chunk_rows)
     cu = np.concatenate([[0], np.cumsum(lengths)])
     dplans = [BatchPlan.build(lengths[a:b]).to(dev) for a, b in chunks]
     launches_per_step = len(chunks) * (model.launches_per_forward() + 2)
@@ -320,12 +321,14 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "frames_per_sec": frames_all * args.steps / (ms_dev * 1e-3),
             "config": {"workload": workload, "videos_per_gpu": args.videos, "frames_per_gpu": R,
-                       "chunk_rows": args.chunk_rows, "chunks_per_step": len(chunks), "parallelism": f"video-wise x{world}",
+                       "device_chunk_rows": args.device_chunk_rows, "chunks_per_step": len(chunks),
+                       "e2e_chunk_rows": args.chunk_rows, "parallelism": f"video-wise x{world}",
                        "l2": "inputs (7.5 GB/GPU) exceed L2; no flush needed", "weights": "xavier random init",
                        "kept_proposals": kept_total},
             "e2e": {"value": e2e_v, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "frames_per_sec": frames_all * args.steps / (ms_e2e * 1e-3)},
             "gpu_launches": launches_per_step * args.steps,
+            "e2e_gpu_launches": pipe.kernel_launches * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -443,10 +443,14 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int halo = 0;
     ScaleList sl = make_scales(cfg, &halo);
-    static bool attrs_done = false;
-    if (!attrs_done) {
-        CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemBytes), "smem opt-in nms");
-        attrs_done = true;
+    // shared memory per CTA: 24 bytes per anchor of the largest video, rounded up to a power of two (<= 4096 anchors)
+    int cap = 32;
+    while (cap < max_n && cap < kNmsSmemCap) cap <<= 1;
+    const int nms_smem = cap * 24;
+    static int nms_opted = 0;
+    if (nms_smem > nms_opted) {
+        CU_CHECK(opt_in_smem(nms_kernel, nms_smem), "smem opt-in nms");
+        nms_opted = nms_smem;
     }
     {
         StageScope scope(ST_DECODE, st);
@@ -456,8 +460,8 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     }
     {
         StageScope scope(ST_NMS, st);
-        nms_kernel<<<batch->n_videos, kNmsThreads, kNmsSmemBytes, st>>>(
-            pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh,
+        nms_kernel<<<batch->n_videos, kNmsThreads, nms_smem, st>>>(
+            pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh, cap,
             reinterpret_cast<const long long*>(nms_scratch_off), static_cast<unsigned char*>(nms_scratch), keep_count,
             keep_idx, keep_scores, keep_boxes);
         CU_CHECK(cudaGetLastError(), "nms_kernel");

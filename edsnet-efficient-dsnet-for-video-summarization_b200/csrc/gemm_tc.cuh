@@ -10,7 +10,7 @@
 // accumulators in TMEM (4 x 128 columns = all 512): the hi.hi products rotate over three of them by K block (<= 24
 // steps each for K = 1024), the two small cross terms go to the fourth, and the epilogue adds the four in fp32 with
 // round-to-nearest.
-// Per CTA: one 128 x BN output tile.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 =
+// Persistent CTAs, 128 x 128 output tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 =
 // epilogue (TMEM -> registers -> global).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
 // by full/empty mbarriers; operands land in shared memory in the 128B (BK=64) / 64B (BK=32) swizzled K-major
 // layout that both TMA and the UMMA shared-memory descriptor understand; the accumulator lives in TMEM.
@@ -32,6 +32,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -128,33 +131,43 @@ struct TcCfg {
     static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
     static constexpr int kBTile = BN * BK * 2;
     static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
-    static constexpr int kAccs = PASSES == 3 ? 4 : 1;      // TMEM accumulators (see the header comment)
-    static constexpr int kTmemCols = kAccs * BN;
+    static constexpr int kAccs = PASSES == 3 ? 4 : 1;      // TMEM accumulators per tile (see the header comment)
+    static constexpr int kBufs = PASSES == 3 ? 1 : 2;      // tiles in flight in TMEM
+    static constexpr int kTmemCols = kAccs * kBufs * BN;
+    static_assert(BN == 128, "one thread keeps a 128-column output row in registers");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
     static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr int kThreads = 192;
 };
 
+// Persistent kernel: grid = min(#tiles, #SMs); CTA b owns tiles b, b + grid, ...  (n fastest, so the CTAs that run
+// together share one A row block and the L2-resident weight planes).  The TMA producer runs ahead across tile
+// boundaries, so the smem ring is full again by the time the epilogue has drained TMEM.  The epilogue pulls the
+// whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
+// residual and stores -- the next tile's MMAs overlap those global accesses.
 template <int BN, int BK, int STAGES, int PASSES, int EPI>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
     using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
-    // barriers: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address slot
+    // barriers: full[STAGES], empty[STAGES], tmem_full[kBufs], tmem_empty[kBufs], then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + Cfg::kBufs + b); };
+    constexpr int kSlotOff = 8 * (2 * STAGES + 2 * Cfg::kBufs);
+    const uint32_t tmem_slot = bar_base + kSlotOff;
     unsigned char* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * Cfg::kStageBytes + 8 * (2 * STAGES + 1));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * Cfg::kStageBytes + kSlotOff);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM;
     const int nk = K / BK;
+    const int tiles_n = N / BN;
+    const int n_tiles = tiles_n * ((M + Cfg::BM - 1) / Cfg::BM);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
@@ -162,30 +175,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_acc = *tmem_slot_ptr;
+    const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
         if (lane == 0) {
             // ---- TMA producer ----
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                if (!mbar_wait(empty_bar(s), ph ^ 1u)) break;
-                const uint32_t st = smem_base + s * Cfg::kStageBytes;
-                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                // stage layout: A_hi | B_hi | (A_lo | B_lo).  Plane p of an operand with R rows starts at row p*R.
-                tma_load_2d(st, &mapA, full_bar(s), kb * BK, m0);
-                tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
-                if (PASSES == 3) {
-                    tma_load_2d(st + Cfg::kATile + Cfg::kBTile, &mapA, full_bar(s), kb * BK, M + m0);
-                    tma_load_2d(st + 2 * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
+            int it = 0;                                     // k-block counter across all tiles of this CTA
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * Cfg::BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+                    const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                    mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                    // stage layout: A_hi | B_hi | (A_lo | B_lo).  Plane p of an operand with R rows starts at row p*R.
+                    tma_load_2d(st, &mapA, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
+                    if (PASSES == 3) {
+                        tma_load_2d(st + Cfg::kATile + Cfg::kBTile, &mapA, full_bar(s), kb * BK, M + m0);
+                        tma_load_2d(st + 2 * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
+                    }
                 }
             }
         }
@@ -194,76 +212,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // ---- MMA issuer ----
             constexpr uint32_t idesc = make_idesc(Cfg::BM, BN);
             bool ok = true;
-            for (int kb = 0; kb < nk && ok; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                ok = mbar_wait(full_bar(s), ph);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
+                const int buf = t % Cfg::kBufs;
+                const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
+                ok = mbar_wait(tempty_bar(buf), tph ^ 1u);  // epilogue has drained this buffer (first use: free)
                 tc_fence_after();
-                const uint32_t st = smem_base + s * Cfg::kStageBytes;
-                const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
-                const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
-                // PASSES == 3: hi.hi of K block kb -> accumulator kb % 3, both cross terms -> accumulator 3
-                const uint32_t acc_main = tmem_acc + (PASSES == 3 ? (uint32_t)((kb % 3) * BN) : 0u);
-                const uint32_t acc_lo = tmem_acc + 3u * BN;
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN);
+                for (int kb = 0; kb < nk && ok; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    ok = mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                    const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
+                    const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
+                    // PASSES == 3: hi.hi of K block kb -> accumulator kb % 3, both cross terms -> accumulator 3
+                    const uint32_t acc_main = tmem_acc + (PASSES == 3 ? (uint32_t)((kb % 3) * BN) : 0u);
+                    const uint32_t acc_lo = tmem_acc + 3u * BN;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint32_t koff = k * 32;           // 16 fp16 = 32 bytes further along K inside the atom
-                    const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
-                    const bool first_main = PASSES == 3 ? (kb < 3 && k == 0) : ((kb | k) == 0);
-                    umma_f16(acc_main, dah, dbh, idesc, first_main ? 0u : 1u);
-                    if (PASSES == 3) {
-                        const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
-                        umma_f16(acc_lo, dah, dbl, idesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_f16(acc_lo, dal, dbh, idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t koff = k * 32;       // 16 fp16 = 32 bytes further along K inside the atom
+                        const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
+                        const bool first_main = PASSES == 3 ? (kb < 3 && k == 0) : ((kb | k) == 0);
+                        umma_f16(acc_main, dah, dbh, idesc, first_main ? 0u : 1u);
+                        if (PASSES == 3) {
+                            const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
+                            umma_f16(acc_lo, dah, dbl, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(acc_lo, dal, dbh, idesc, 1u);
+                        }
                     }
+                    umma_commit(empty_bar(s));              // frees the smem slot once these MMAs have read it
                 }
-                umma_commit(empty_bar(s));                  // frees the smem slot once these MMAs have read it
+                umma_commit(tfull_bar(buf));                // tile complete
             }
-            umma_commit(tmem_full_bar);                     // accumulator complete
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> one output row ----
         const int quarter = warp & 3;
-        const int row = m0 + quarter * 32 + lane;
-        mbar_wait(tmem_full_bar, 0u);
-        tc_fence_after();
-        float* crow = C + (size_t)row * N + n0;
-        const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
-        const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
         const int n_main = PASSES == 3 ? (nk < 3 ? nk : 3) : 1;     // accumulators that received hi.hi products
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            const uint32_t t0 = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-            uint32_t r[16];
-            float v[16];
-            tmem_ld16_nowait(t0, r);
-            tmem_ld_wait();
+        bool ok = true;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
+            const int m0 = (tile / tiles_n) * Cfg::BM, n0 = (tile % tiles_n) * BN;
+            const int buf = t % Cfg::kBufs;
+            const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
+            const int row = m0 + quarter * 32 + lane;
+            ok = mbar_wait(tfull_bar(buf), tph);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16);
+            float v[BN];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (PASSES == 3) {
-                // (acc0 + acc1) + (acc2 + acc3), every add rounded to nearest
-                uint32_t r1[16], r2[16], r3[16];
-                tmem_ld16_nowait(t0 + 3u * BN, r3);
-                if (n_main > 1) tmem_ld16_nowait(t0 + 1u * BN, r1);
-                if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN, r2);
-                tmem_ld_wait();
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r0[16];
+                tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
+                if (PASSES == 3) {
+                    // (acc0 + acc1) + (acc2 + acc3), every add rounded to nearest
+                    uint32_t r1[16], r2[16], r3[16];
+                    tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
+                    if (n_main > 1) tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
+                    if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a01 = n_main > 1 ? __fadd_rn(v[j], __uint_as_float(r1[j])) : v[j];
-                    const float a23 = n_main > 2 ? __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j]))
-                                                 : __uint_as_float(r3[j]);
-                    v[j] = __fadd_rn(a01, a23);
+                    for (int j = 0; j < 16; ++j) {
+                        const float a0 = __uint_as_float(r0[j]);
+                        const float a01 = n_main > 1 ? __fadd_rn(a0, __uint_as_float(r1[j])) : a0;
+                        const float a23 = n_main > 2 ? __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j]))
+                                                     : __uint_as_float(r3[j]);
+                        v[c0 + j] = __fadd_rn(a01, a23);
+                    }
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(r0[j]);
                 }
             }
+            // TMEM is drained: hand the buffer back to the MMA warp before touching global memory
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
             if (row < M) {
+                float* crow = C + (size_t)row * N + n0;
+                const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
+                const float ra = __ldg(ep.a_scale + row);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    const int c = n0 + c0 + j;
-                    {
-                        const float4 rb = ldg4(ep.b_scale + c);
-                        o.x *= ra * rb.x; o.y *= ra * rb.y; o.z *= ra * rb.z; o.w *= ra * rb.w;
-                    }
+                for (int j = 0; j < BN; j += 4) {
+                    const int c = n0 + j;
+                    const float4 rb = ldg4(ep.b_scale + c);
+                    float4 o = make_float4(v[j] * (ra * rb.x), v[j + 1] * (ra * rb.y), v[j + 2] * (ra * rb.z),
+                                           v[j + 3] * (ra * rb.w));
                     if (EPI == EPI_QSCALE) {
                         if (c < ep.qcols) { o.x *= 0.125f; o.y *= 0.125f; o.z *= 0.125f; o.w *= 0.125f; }
                     }
@@ -272,17 +309,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
                     if (EPI == EPI_BIAS_RES) {
-                        const float4 x = ldg4(rrow + c0 + j);
+                        const float4 x = ldg4(rrow + j);
                         o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
                     }
-                    st4(crow + c0 + j, o);
+                    st4(crow + j, o);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_acc, Cfg::kTmemCols);
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ---- fp32 [rows][cols] -> row-scaled fp16 hi/lo planes + per-row inverse scale ----
@@ -364,6 +401,16 @@ inline bool make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64
     return true;
 }
 
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 template <int BN, int BK, int STAGES, int PASSES, int EPI>
 cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                            cudaStream_t st, std::string* msg) {
@@ -378,7 +425,8 @@ cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M
         if (e != cudaSuccess) return e;
         opted = true;
     }
-    dim3 grid(N / BN, (M + Cfg::BM - 1) / Cfg::BM);
+    const int n_tiles = (N / BN) * ((M + Cfg::BM - 1) / Cfg::BM);
+    const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(mapA, mapB, C, M, N, K, ep);
     return cudaGetLastError();
 }
@@ -390,20 +438,14 @@ template <int PASSES, int EPI>
 cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                          cudaStream_t st, std::string* msg) {
     const int variant = variant_ref();
-    if (PASSES == 3) {
-        // four 128-column accumulators fill TMEM: BN is 128
-        if (N % 128 == 0) {
+    if (N % 128 == 0) {
+        if (PASSES == 3) {
+            // four 128-column accumulators fill TMEM
             if (variant == 1) return launch_variant<128, 32, 4, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 3, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-        }
-    } else {
-        if (N % 256 == 0) {
-            if (variant == 1) return launch_variant<256, 32, 2, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-            return launch_variant<256, 64, 4, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-        }
-        if (N % 128 == 0) {
-            if (variant == 1) return launch_variant<128, 32, 3, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-            return launch_variant<128, 64, 3, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        } else {
+            if (variant == 1) return launch_variant<128, 32, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            return launch_variant<128, 64, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         }
     }
     if (msg) *msg = "N must be a multiple of 128";

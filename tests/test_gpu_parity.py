@@ -235,7 +235,8 @@ def test_predict_and_proposals_match_reference_golden(name):
     g, x, p = golden_case(FWD, name)
     T, scales = int(g["T"]), [int(s) for s in g["scales"]]
     model = make_model(p, scales, int(g["fc_depth"]), "fp32", DEV)
-    scores, boxes = model.predict(x[None].to(DEV))
+    with torch.no_grad():               # as evaluate.py:17 / infer.py:27 call it
+        scores, boxes = model.predict(x[None].to(DEV))
     assert scores.shape == (T * len(scales),) and boxes.shape == (T * len(scales), 2)
     assert scores.dtype == np.float32 and boxes.dtype == np.float32
     assert np.abs(boxes - g["boxes_f32"]).max() < 1e-3 + 2e-6 * np.abs(g["boxes_f32"]).max()
@@ -244,7 +245,8 @@ def test_predict_and_proposals_match_reference_golden(name):
     ib = orc.clip_round(boxes, T)
     frac_same = float((ib == g["boxes_i32"]).all(axis=1).mean())
     assert frac_same > 0.995
-    ks, kb = model.proposals(x[None].to(DEV), 0.5)
+    with torch.no_grad():
+        ks, kb = model.proposals(x[None].to(DEV), 0.5)
     # oracle NMS on OUR scores/boxes must agree bit for bit with the device NMS
     rs, rb, _ = orc.nms_1d(scores, ib, 0.5)
     assert np.array_equal(ks, rs) and np.array_equal(kb, rb)
