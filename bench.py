@@ -143,6 +143,16 @@ def run_cpu_sample(score, x_host, lengths, budget_s, max_videos):
     return n, frames, dt
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, warnings from
+    libraries that print to fd 1) is redirected to stderr for the whole run."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,7 +199,7 @@ def main():
         dt = time.perf_counter() - t0
         v = vids / dt
         desc = f"first {sample} videos of the workload per step ({sum(lengths[:sample])} frames), one video per call"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "videos_per_sec", "value": v, "unit": "videos/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -331,7 +341,7 @@ def main():
             "e2e_gpu_launches": pipe.kernel_launches * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

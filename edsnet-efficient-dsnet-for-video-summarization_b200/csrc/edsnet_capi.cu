@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "fc_stack_tc.cuh"
 #include "nystrom.cuh"
 #include "tail.cuh"
 #include "decode_nms.cuh"
@@ -180,12 +181,20 @@ int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv
 
 int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out, int rows,
                   cudaStream_t st) {
+    StageScope scope(ST_FC_STACK, st);
+    if (cfg->precision != EDSNET_PREC_FP32) {
+        // tensor-core version (fp16 hi/lo split, fp32-grade) for both tcgen05 precisions: the block is too small
+        // and too error-sensitive for a single-pass variant to be worth having
+        if (!w->fcb_w16) return fail(EDSNET_E_ARG, "fc_stack: tcgen05 precision needs fcb_w16 (edsnet_split_f16)");
+        CU_CHECK(launch_fc_stack_tc(u_in, w->fcb_w16, w->fcb_b, w->fcb_ln_w, w->fcb_ln_b, u_out, rows, cfg->fc_depth,
+                                    st), "fc_stack_tc_kernel");
+        return EDSNET_OK;
+    }
     static bool attrs_done = false;
     if (!attrs_done) {
         CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
         attrs_done = true;
     }
-    StageScope scope(ST_FC_STACK, st);
     fc_stack_kernel<<<(rows + 63) / 64, 256, kFcStackSmem, st>>>(u_in, w->fcb_w, w->fcb_b, w->fcb_ln_w,
                                                                   w->fcb_ln_b, u_out, rows, cfg->fc_depth);
     CU_CHECK(cudaGetLastError(), "fc_stack_kernel");
@@ -252,7 +261,8 @@ size_t edsnet_split_f16_bytes(int64_t rows, int64_t cols) {
 
 int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream) {
     if (!src || !dst_hi_lo || rows < 1 || rows > (1 << 30)) return fail(EDSNET_E_ARG, "split_f16: bad argument");
-    if (cols != 512 && cols != 1024) return fail(EDSNET_E_ARG, "split_f16: cols must be 512 or 1024");
+    if (cols != 128 && cols != 512 && cols != 1024)
+        return fail(EDSNET_E_ARG, "split_f16: cols must be 128, 512 or 1024");
     StageScope scope(ST_SPLIT, static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_split_f16(src, dst_hi_lo, (int)rows, (int)cols, static_cast<cudaStream_t>(stream));
     CU_CHECK(e, "split_f16_kernel");
@@ -357,7 +367,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     const int prec = cfg->precision;
     const void* x16 = nullptr;
     if (prec != EDSNET_PREC_FP32) {
-        if (!w->to_qkv_w16 || !w->to_out_w16 || !w->fc1_w16)
+        if (!w->to_qkv_w16 || !w->to_out_w16 || !w->fc1_w16 || !w->fcb_w16)
             return fail(EDSNET_E_ARG, "forward: tcgen05 precision needs the fp16 weight planes (edsnet_split_f16)");
         rc = edsnet_split_f16(x, ws + L.x16, R, kFeat, stream);
         if (rc) return rc;

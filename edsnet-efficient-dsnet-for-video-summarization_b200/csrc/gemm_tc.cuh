@@ -323,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---- fp32 [rows][cols] -> row-scaled fp16 hi/lo planes + per-row inverse scale ----
-// One warp per row; COLS in {512, 1024}.  scale = 2^(14 - floor(log2(max|x|))) (1 for an all-zero row).
+// One warp per row; COLS in {128, 512, 1024}.  scale = 2^(14 - floor(log2(max|x|))) (1 for an all-zero row).
 template <int COLS>
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
@@ -477,6 +477,7 @@ static cudaError_t launch_split_f16(const float* src, void* dst, int rows, int c
     float* sc = reinterpret_cast<float*>(lo + (size_t)rows * cols);
     const unsigned blocks = (unsigned)((rows + 7) / 8);
     if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
+    else if (cols == 128) tc::split_f16_kernel<128><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else if (cols == 512) tc::split_f16_kernel<512><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();

@@ -131,7 +131,8 @@ class DSNet(nn.Module):
             setattr(w, name, t.data_ptr())
         if self.precision != "fp32":
             lib = _capi.lib()
-            for name, p in (("to_qkv_w16", params[0]), ("to_out_w16", params[1]), ("fc1_w16", params[6])):
+            for name, p in (("to_qkv_w16", params[0]), ("to_out_w16", params[1]), ("fc1_w16", params[6]),
+                            ("fcb_w16", params[8])):
                 src = p.detach().contiguous()
                 planes = torch.empty(lib.edsnet_split_f16_bytes(src.shape[0], src.shape[1]), dtype=torch.uint8,
                                      device=device)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 1
+#define EDSNET_ABI_VERSION 2
 
 enum {
     EDSNET_OK = 0,
@@ -78,6 +78,7 @@ typedef struct {
     const void* to_qkv_w16;    /* planes of (1536, 1024) */
     const void* to_out_w16;    /* planes of (1024, 512)  */
     const void* fc1_w16;       /* planes of (128, 1024)  */
+    const void* fcb_w16;       /* planes of (128, 128)   */
 } edsnet_weights;
 
 /* A packed batch of videos.  All arrays [dev], int32.  Tile tables are built by the host (see
@@ -146,7 +147,7 @@ int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, con
 /* Number of kernel launches one edsnet_forward call enqueues for this configuration (bench bookkeeping). */
 int edsnet_forward_launches(const edsnet_config* cfg);
 
-/* fp32 (rows, cols), cols in {512, 1024} -> operand planes for the tcgen05 precisions.  Every row is first scaled
+/* fp32 (rows, cols), cols in {128, 512, 1024} -> operand planes for the tcgen05 precisions.  Every row is first scaled
  * by a power of two that puts its largest magnitude in [2^14, 2^15) (keeps hi AND lo in fp16's normal range).
  * dst layout, edsnet_split_f16_bytes(rows, cols) bytes: hi plane [rows][cols] fp16 (hi = fp16(x 2^s)) |
  * lo plane [rows][cols] fp16 (lo = fp16(x 2^s - hi)) | inverse scales [rows] fp32 (2^-s). */

@@ -387,3 +387,28 @@ def test_gradients_match_the_oracle_graph():
     model.train()
     c2, _ = model(x[None].to(DEV))
     assert c2.requires_grad and not torch.equal(c2.detach(), cls.detach())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("rows,depth", [(1, 1), (129, 5), (1000, 7), (40000, 5)])
+def test_fc_stack_stage(precision, rows, depth):
+    """The shared fc block (anchor_based/dsnet.py:91-96,107-108) alone: CUDA-core and tcgen05 versions vs fp64."""
+    capi, lib = _lib()
+    p = orc.synth_params(41, "xavier")
+    model = make_model(p, [4], depth, precision, DEV)
+    g = torch.Generator().manual_seed(rows)
+    u = torch.randn(rows, 128, generator=g) * 1.5
+    ref = u.double()
+    W, b = p["fc_block.0.weight"].double(), p["fc_block.0.bias"].double()
+    gw, gb = p["fc_block.3.weight"].double(), p["fc_block.3.bias"].double()
+    for _ in range(depth):
+        ref = orc.layer_norm(torch.relu(ref @ W.t() + b), gw, gb)
+    ud = u.to(DEV)
+    out = torch.full((rows, 128), float("nan"), device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    w = model._weights(torch.device(DEV), st)
+    capi.check(lib.edsnet_fc_stack(model._config(), w, ud.data_ptr(), out.data_ptr(), rows, st))
+    _no_tc_timeout()
+    err = orc.rel_l2(out.cpu().numpy(), ref.numpy())
+    print(precision, rows, depth, err)
+    assert err < 3e-6, err
