@@ -40,7 +40,7 @@ class Batch(C.Structure):
                 ("tiles128", C.c_void_p), ("n_tiles128", C.c_int32)]
 
 
-LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "a3v", "zmat", "wmat", "merged", "y", "yn",
+LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",
                  "u0", "u1", "x16", "total")
 
 
@@ -64,7 +64,7 @@ SYMBOLS = {
     "edsnet_split_f16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     "edsnet_gemm": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                               C.c_int32, _P]),
-    "edsnet_nystrom_core": (C.c_int, [C.POINTER(Batch), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "edsnet_nystrom_core": (C.c_int, [C.c_int32, C.POINTER(Batch), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "edsnet_fc_stack": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), _P, _P, C.c_int32, _P]),
     "edsnet_roi_pool_heads": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_debug_tc_status": (C.c_int, [C.c_int32]),

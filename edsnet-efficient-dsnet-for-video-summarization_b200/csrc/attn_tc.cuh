@@ -1,0 +1,502 @@
+// Tensor-core (tcgen05, fp16 hi/lo split, fp32-grade) landmark attention (transformer/nystroformer.py:95-142).
+//
+// Input format: the to_qkv GEMM (gemm_tc.cuh, EPI_QKV_PLANES) leaves q | k | v as two fp16 planes [R][1536]
+// (hi = fp16(x 2^s), lo = fp16(x 2^s - hi)) plus inverse scales inv[R][24] (slot = part * 8 + head; q's slot carries
+// the 1/8 of nystroformer.py:91).  A 64-column head slice of a plane row is exactly one 128-byte swizzle row, so TMA
+// drops K-major / MN-major UMMA operands straight into shared memory -- no conversion, no register staging.
+//
+//   landmarks_planes_kernel  segment means of q, k                              (HBM bound, CUDA cores)
+//   a3v_tc_kernel            softmax_keys(q_land k^T) v, streamed over 64-key tiles, two heads per CTA
+//   attn_out_tc_kernel       softmax(q k_land^T) W per (video, head), streamed over 128-row tiles
+//   value_conv_kernel        + depth-wise 33-tap FIR of v, thread <-> column, register sliding window
+//
+// Thread <-> accumulator row everywhere, so every softmax is a register-only row reduction.  Right operands that are
+// naturally [k][n] row-major (v, W) are passed MN-major: same bytes, different descriptor.  An MN-major operand must
+// not be scaled along K, so v's per-key scale is folded into the probabilities and W uses one scale per matrix.
+#pragma once
+#include "fc_stack_tc.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int scale_exp(float mx) {
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+    return max(-100, min(100, e));
+}
+// byte offset of 16-byte chunk c (0..7) of row r in a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void store_row64(unsigned char* hi, unsigned char* lo, int r, const float (&v)[64], float sc) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        __half2 hh[4], ll[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float v0 = v[c * 8 + 2 * q] * sc, v1 = v[c * 8 + 2 * q + 1] * sc;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            hh[q] = __halves2half2(h0, h1);
+            ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+        }
+        const uint32_t off = sw128_off(r, c);
+        *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(hh);
+        *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(ll);
+    }
+}
+__device__ __forceinline__ void load_row64(float (&v)[64], const float* __restrict__ src) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+        const float4 x = ldg4(src + j);
+        v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
+    }
+}
+__device__ __forceinline__ float absmax64(const float (&v)[64]) {
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) mx = fmaxf(mx, fabsf(v[j]));
+    return mx;
+}
+// MN-major right operand stored as [k rows][128 B = 64 n values], SWIZZLE_128B: 8-row atoms of 1024 B along K
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (64ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
+
+// sum of the hi.hi and cross-term accumulators for 64 columns of this thread's row
+__device__ __forceinline__ void tmem_read64_sum(uint32_t t_main, uint32_t t_lo, float (&v)[64]) {
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(t_main + (uint32_t)c0, r0);
+        tmem_ld16_nowait(t_lo + (uint32_t)c0, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+    }
+}
+// three-pass product of [M=128][K=64] (K-major A planes) with a [N=64][K=64] K-major or [K=64][N=64] MN-major B
+template <bool B_MN>
+__device__ __forceinline__ void issue_split_mma64(uint32_t acc_main, uint32_t acc_lo, uint32_t a_hi, uint32_t a_lo,
+                                                  uint32_t b_hi, uint32_t b_lo) {
+    constexpr uint32_t idesc = B_MN ? make_idesc_bmn(128, 64) : make_idesc(128, 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ka = (uint32_t)k * 32u, kb = B_MN ? (uint32_t)k * 2048u : (uint32_t)k * 32u;
+        const uint64_t dah = make_smem_desc<64>(a_hi + ka), dal = make_smem_desc<64>(a_lo + ka);
+        const uint64_t dbh = B_MN ? make_smem_desc_mn(b_hi + kb) : make_smem_desc<64>(b_hi + kb);
+        const uint64_t dbl = B_MN ? make_smem_desc_mn(b_lo + kb) : make_smem_desc<64>(b_lo + kb);
+        umma_f16(acc_main, dah, dbh, idesc, k != 0 ? 1u : 0u);
+        umma_f16(acc_lo, dah, dbl, idesc, k != 0 ? 1u : 0u);
+        umma_f16(acc_lo, dal, dbh, idesc, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// landmarks from the planes: q_land / k_land [V][8][64][64] fp32 = mean over each block of `seg` padded rows.
+// grid (64 landmarks, V), 256 threads; thread owns 4 consecutive columns of the 1024 q|k columns.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const float* __restrict__ inv,
+                        const int* __restrict__ cu_rows, float* __restrict__ q_land, float* __restrict__ k_land) {
+    const int v = blockIdx.y, j = blockIdx.x;
+    const VidInfo vi = vid_info(cu_rows, v);
+    const int c4 = threadIdx.x * 4;
+    const int slot = c4 >> 6;                                   // part * 8 + head, part in {q, k}
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r_lo = j * vi.seg - vi.pad, r_hi = r_lo + vi.seg;
+    if (r_lo < 0) r_lo = 0;
+    for (int r = r_lo; r < r_hi; ++r) {
+        const size_t row = (size_t)(vi.row0 + r);
+        const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + row * kQkvCols + c4));
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + row * kQkvCols + c4));
+        const float s = __ldg(inv + row * 24 + slot);
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+        acc.x += (h0.x + l0.x) * s; acc.y += (h0.y + l0.y) * s;
+        acc.z += (h1.x + l1.x) * s; acc.w += (h1.y + l1.y) * s;
+    }
+    const float div = (float)vi.seg;
+    acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+    const int is_k = c4 >= kInner;
+    const int cc = c4 & (kInner - 1);
+    const int hd = cc >> 6, d = cc & 63;
+    float* dst = (is_k ? k_land : q_land) + ((((size_t)v * kHeads + hd) * kLandmark + j) * kDimHead + d);
+    st4(dst, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a3v = softmax_over_keys(q_land k^T) v for TWO heads of one video per CTA (nystroformer.py:118,130,133).
+// Accumulator row t: head (t / 64) of the pair, landmark t % 64.  Both heads' landmarks form one 128-row A operand;
+// S_hh = A k_hh^T and O_hh = P v_hh are issued for both heads and every thread reads the product of ITS head (the other
+// half of each product is never read).  Keys stream in 64-row tiles through a 2-stage TMA ring; the running
+// max / sum / output row live in registers (flash-attention style), the zero pad keys of the reference are folded
+// into the start state (logit 0, value 0).
+// 160 threads: warps 0..3 = rows, warp 4 = TMA producer.  TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kA3Stage = 8 * 8192;                                          // k_h0 k_h1 v_h0 v_h1, hi and lo
+constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + 2 * 4 * 64 * 4 + 128 + 1024;
+
+__global__ void __launch_bounds__(160, 1)
+a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+              const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
+              float* __restrict__ a3v) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int oQl = 0, oKV = 32768, oP = 32768 + 2 * kA3Stage, oVec = oP + 32768;
+    float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
+    const uint32_t bars = base + oVec + 2 * 4 * 64 * 4;                       // full[2] empty[2] mma
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 2 * 4 * 64 * 4 + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair = blockIdx.x, v = blockIdx.y;
+    const VidInfo vi = vid_info(cu_rows, v);
+    const int n_tiles = (vi.T + 63) / 64;
+    const int h0 = pair * 2;
+
+    if (tid == 0) {
+        mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // full
+        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // empty
+        mbar_init(bars + 32, 1);                                            // mma
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(bars + 64, 512);
+    float inv_ql = 1.f;
+    if (tid < 128) {
+        // landmark queries of both heads -> A operand planes (row t), per-row scale
+        float q[64];
+        load_row64(q, q_land + (((size_t)v * kHeads + h0 + (tid >> 6)) * kLandmark + (tid & 63)) * kDimHead);
+        const int e = scale_exp(absmax64(q));
+        inv_ql = ldexpf(1.f, -e);
+        store_row64(g + oQl, g + oQl + 16384, tid, q, ldexpf(1.f, e));
+        // scales of tile 0: thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
+        const int key = tid & 63, part = 1 + (tid >> 6);
+        const bool in = key < vi.T;
+        const float* ip = inv + (size_t)(vi.row0 + (in ? key : 0)) * 24 + part * 8 + h0;
+        sc_vec[((tid >> 6) * 2 + 0) * 64 + key] = in ? __ldg(ip) : 0.f;
+        sc_vec[((tid >> 6) * 2 + 1) * 64 + key] = in ? __ldg(ip + 1) : 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---- TMA producer: 8 boxes of 64 rows x 64 columns per tile ----
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i & 1;
+                if (!mbar_wait(bars + 16 + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u)) break;
+                const uint32_t st = base + oKV + s * kA3Stage;
+                mbar_expect_tx(bars + 8 * s, kA3Stage);
+                const int row = vi.row0 + i * 64;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {                               // k_h0 k_h1 v_h0 v_h1
+                    const int col = (1 + (b >> 1)) * kInner + (h0 + (b & 1)) * kDimHead;
+                    tma_load_2d(st + b * 16384, &map_hi, bars + 8 * s, col, row);
+                    tma_load_2d(st + b * 16384 + 8192, &map_lo, bars + 8 * s, col, row);
+                }
+            }
+        }
+    } else {
+        const int hh = tid >> 6;                                            // which head of the pair this row belongs to
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(hh * 128), tO = tS + 256u;
+        float o[64];
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o[d] = 0.f;
+        float run_max = vi.pad > 0 ? 0.f : -INFINITY, run_sum = (float)vi.pad;
+        uint32_t mma_phase = 0;
+        bool ok = true;
+        for (int i = 0; i < n_tiles && ok; ++i) {
+            const int s = i & 1;
+            // prefetch the next tile's scales (written to the other stage's slot at the end of this iteration)
+            float nsc0 = 0.f, nsc1 = 0.f;
+            {
+                const int key = (i + 1) * 64 + (tid & 63), part = 1 + (tid >> 6);
+                if (key < vi.T) {
+                    const float* ip = inv + (size_t)(vi.row0 + key) * 24 + part * 8 + h0;
+                    nsc0 = __ldg(ip); nsc1 = __ldg(ip + 1);
+                }
+            }
+            ok = mbar_wait(bars + 8 * s, (uint32_t)(i >> 1) & 1u);
+            const uint32_t st = base + oKV + s * kA3Stage;
+            if (tid == 0) {
+                tc_fence_after();
+                issue_split_mma64<false>(tmem_base, tmem_base + 64u, base + oQl, base + oQl + 16384, st, st + 8192);
+                issue_split_mma64<false>(tmem_base + 128u, tmem_base + 192u, base + oQl, base + oQl + 16384,
+                                         st + 16384, st + 16384 + 8192);
+                umma_commit(bars + 32);
+            }
+            ok = ok && mbar_wait(bars + 32, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            // ---- this row's logits against the 64 keys of the tile ----
+            float p[64];
+            tmem_read64_sum(tS, tS + 64u, p);
+            const float* isk = sc_vec + (s * 4 + hh) * 64;
+            const float* isv = sc_vec + (s * 4 + 2 + hh) * 64;
+            const int kvalid = vi.T - i * 64;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                p[j] = j < kvalid ? p[j] * (inv_ql * isk[j]) : -INFINITY;
+                mx = fmaxf(mx, p[j]);
+            }
+            const float new_max = fmaxf(run_max, mx);
+            const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
+            float ps = 0.f, pmx = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float e = expf(p[j] - new_max);                       // 0 for masked keys
+                ps += e;
+                p[j] = e * isv[j];                                          // fold v's per-key scale into P
+                pmx = fmaxf(pmx, p[j]);
+            }
+            run_sum = run_sum * alpha + ps;
+            run_max = new_max;
+            const int ep = scale_exp(pmx);
+            store_row64(g + oP, g + oP + 16384, tid, p, ldexpf(1.f, ep));
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1, 128);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_split_mma64<true>(tmem_base + 256u, tmem_base + 320u, base + oP, base + oP + 16384,
+                                        st + 32768, st + 32768 + 8192);
+                issue_split_mma64<true>(tmem_base + 384u, tmem_base + 448u, base + oP, base + oP + 16384,
+                                        st + 49152, st + 49152 + 8192);
+                umma_commit(bars + 32);
+                umma_commit(bars + 16 + 8 * s);                             // K/V stage free once these MMAs are done
+            }
+            // next tile's scales into the other stage's slot (its previous readers finished before the barrier above)
+            sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
+            sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
+            ok = ok && mbar_wait(bars + 32, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            float pv[64];
+            tmem_read64_sum(tO, tO + 64u, pv);
+            const float inv_p = ldexpf(1.f, -ep);
+#pragma unroll
+            for (int d = 0; d < 64; ++d) o[d] = fmaf(o[d], alpha, pv[d] * inv_p);
+            tc_fence_before();
+            named_bar_sync(1, 128);          // scales visible; everyone is done with S / O before the next tile's MMAs
+        }
+        if (ok) {
+            float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (tid & 63)) * kDimHead;
+            const float rs = 1.f / run_sum;
+#pragma unroll
+            for (int d = 0; d < 64; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// attn_out = softmax(q k_land^T) W for one (video, head) per CTA (nystroformer.py:115,130,133), q streamed in 128-row
+// tiles through a 2-stage TMA ring.  k_land and W are converted to operand planes once per CTA.  The probabilities
+// overwrite the q stage they were computed from (q is dead once S is in TMEM), so a CTA needs 96 KB: two per SM.
+// Writes attn[R][512] (head-merged columns h*64..); value_conv_kernel adds the convolution afterwards.
+// 160 threads: warps 0..3 = rows, warp 4 = TMA producer.  TMEM 256 columns: S main | S cross | O main | O cross.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + 64 * 4 + 128 + 1024;
+
+__global__ void __launch_bounds__(160, 2)
+attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                   const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ k_land,
+                   const float* __restrict__ w_mat, float* __restrict__ attn) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int oK = 0, oW = 16384, oQ = 32768, oVec = 32768 + 65536;
+    float* inv_kl = reinterpret_cast<float*>(g + oVec);                     // [64]
+    unsigned* s_wmax = reinterpret_cast<unsigned*>(g + oVec + 256);
+    const uint32_t bars = base + oVec + 256 + 16;                             // full[2] empty[2] mma
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 256 + 16 + 48);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, v = blockIdx.y;
+    const VidInfo vi = vid_info(cu_rows, v);
+    const int n_tiles = (vi.T + 127) / 128;
+    const size_t hoff = ((size_t)v * kHeads + h) * 4096;
+
+    if (tid == 0) {
+        mbar_init(bars, 1); mbar_init(bars + 8, 1);
+        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);
+        mbar_init(bars + 32, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *s_wmax = 0u;
+    }
+    if (warp == 4) tmem_alloc(bars + 48, 256);
+    __syncthreads();
+    float wrow[64];
+    if (tid < 64) {
+        float kl[64];
+        load_row64(kl, k_land + hoff + tid * 64);
+        const int e = scale_exp(absmax64(kl));
+        inv_kl[tid] = ldexpf(1.f, -e);
+        store_row64(g + oK, g + oK + 8192, tid, kl, ldexpf(1.f, e));
+    } else if (tid < 128) {
+        load_row64(wrow, w_mat + hoff + (tid - 64) * 64);
+        atomicMax(s_wmax, __float_as_uint(absmax64(wrow)));
+    }
+    __syncthreads();
+    const int ew = scale_exp(__uint_as_float(*s_wmax));
+    if (tid >= 64 && tid < 128) store_row64(g + oW, g + oW + 8192, tid - 64, wrow, ldexpf(1.f, ew));
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i & 1;
+                if (!mbar_wait(bars + 16 + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u)) break;
+                const uint32_t st = base + oQ + s * 32768;
+                mbar_expect_tx(bars + 8 * s, 32768);
+                const int row = vi.row0 + i * 128, col = h * kDimHead;
+                tma_load_2d(st, &map_hi, bars + 8 * s, col, row);
+                tma_load_2d(st + 8192, &map_hi, bars + 8 * s, col, row + 64);
+                tma_load_2d(st + 16384, &map_lo, bars + 8 * s, col, row);
+                tma_load_2d(st + 24576, &map_lo, bars + 8 * s, col, row + 64);
+            }
+        }
+    } else {
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr, tO = tS + 128u;
+        const float o_scale = ldexpf(1.f, -ew) * (1.f / 16384.f);
+        uint32_t mma_phase = 0;
+        bool ok = true;
+        float inv_q = tid < vi.T ? __ldg(inv + (size_t)(vi.row0 + tid) * 24 + h) : 0.f;
+        for (int i = 0; i < n_tiles && ok; ++i) {
+            const int s = i & 1;
+            const int row = i * 128 + tid;
+            const float inv_q_next = (row + 128 < vi.T) ? __ldg(inv + (size_t)(vi.row0 + row + 128) * 24 + h) : 0.f;
+            ok = mbar_wait(bars + 8 * s, (uint32_t)(i >> 1) & 1u);
+            const uint32_t st = base + oQ + s * 32768;
+            unsigned char* stp = g + oQ + s * 32768;
+            if (tid == 0) {
+                tc_fence_after();
+                issue_split_mma64<false>(tmem_base, tmem_base + 64u, st, st + 16384, base + oK, base + oK + 8192);
+                umma_commit(bars + 32);
+            }
+            ok = ok && mbar_wait(bars + 32, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            float p[64];
+            tmem_read64_sum(tS, tS + 64u, p);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { p[j] *= inv_q * inv_kl[j]; mx = fmaxf(mx, p[j]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
+            const float rs = 1.f / sum;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) p[j] *= rs;
+            store_row64(stp, stp + 16384, tid, p, 16384.f);                 // probabilities <= 1: fixed scale 2^14
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1, 128);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_split_mma64<true>(tmem_base + 128u, tmem_base + 192u, st, st + 16384, base + oW, base + oW + 8192);
+                umma_commit(bars + 32);
+                umma_commit(bars + 16 + 8 * s);                             // stage free once P has been consumed
+            }
+            ok = ok && mbar_wait(bars + 32, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            float ov[64];
+            tmem_read64_sum(tO, tO + 64u, ov);
+            if (row < vi.T) {
+                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4)
+                    st4(dst + j, make_float4(ov[j] * o_scale, ov[j + 1] * o_scale, ov[j + 2] * o_scale, ov[j + 3] * o_scale));
+            }
+            inv_q = inv_q_next;
+            tc_fence_before();
+            named_bar_sync(1, 128);          // all rows done with S / O before the next tile's MMAs overwrite them
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// value convolution + merge: merged[r][h*64+c] = attn[r][h*64+c] + sum_t w[h][t] * v[r + t - 16][h*64+c], rows
+// outside the video are zero (nystroformer.py:61-65,137-138).
+// grid (n_tiles128, 4): a CTA owns 128 rows x 128 value columns (two heads).  The 160 x 128 input window is rebuilt
+// from the planes ((hi + lo) * inv, 128-bit loads) into shared memory once; then thread <-> (column, 64-row half) walks
+// its rows in blocks of 8 with a 40-deep register window: 33 FMA per shared-memory load, attn rows prefetched.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kConvRowsIn = 128 + kTaps - 1;                                 // 160
+constexpr int kConvSmemBytes = kConvRowsIn * 128 * 4;
+
+__global__ void __launch_bounds__(256, 2)
+value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const float* __restrict__ inv,
+                  const int* __restrict__ cu_rows, const int2* __restrict__ tiles, const float* __restrict__ conv_w,
+                  float* __restrict__ merged) {
+    extern __shared__ __align__(16) float vs[];                              // [160][128]
+    const int2 tile = tiles[blockIdx.x];
+    const VidInfo vi = vid_info(cu_rows, tile.x);
+    const int r0 = tile.y, cb = blockIdx.y * 128, tid = threadIdx.x;
+    for (int task = tid; task < kConvRowsIn * 16; task += 256) {
+        const int rr = task >> 4, ch = task & 15;
+        const int r = r0 - 16 + rr;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (r >= 0 && r < vi.T) {
+            const size_t row = (size_t)(vi.row0 + r);
+            const size_t off = row * kQkvCols + 2 * kInner + cb + ch * 8;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+            const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+            const float s = __ldg(inv + row * 24 + 16 + ((cb + ch * 8) >> 6));
+            const __half2* hp = reinterpret_cast<const __half2*>(&h);
+            const __half2* lp = reinterpret_cast<const __half2*>(&l);
+            const float2 h0 = __half22float2(hp[0]), h1 = __half22float2(hp[1]), h2 = __half22float2(hp[2]), h3 = __half22float2(hp[3]);
+            const float2 l0 = __half22float2(lp[0]), l1 = __half22float2(lp[1]), l2 = __half22float2(lp[2]), l3 = __half22float2(lp[3]);
+            a = make_float4((h0.x + l0.x) * s, (h0.y + l0.y) * s, (h1.x + l1.x) * s, (h1.y + l1.y) * s);
+            b = make_float4((h2.x + l2.x) * s, (h2.y + l2.y) * s, (h3.x + l3.x) * s, (h3.y + l3.y) * s);
+        }
+        st4(vs + rr * 128 + ch * 8, a);
+        st4(vs + rr * 128 + ch * 8 + 4, b);
+    }
+    const int c = tid & 127, base = (tid >> 7) * 64;
+    float w[kTaps];
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) w[t] = __ldg(conv_w + ((cb + c) >> 6) * kTaps + t);
+    float* out = merged + (size_t)(vi.row0 + r0 + base) * kInner + cb + c;
+    const int rows = min(64, vi.T - r0 - base);                              // output rows of this thread (may be <= 0)
+    float an[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) an[j] = j < rows ? out[(size_t)j * kInner] : 0.f;
+    __syncthreads();
+    float win[40];                           // win[i] = input row (base + b + i) of the staged window
+#pragma unroll
+    for (int i = 0; i < 32; ++i) win[i] = vs[(base + i) * 128 + c];
+    for (int b = 0; b < rows; b += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { win[32 + j] = vs[(base + b + 32 + j) * 128 + c]; acc[j] = an[j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) an[j] = (b + 8 + j < rows) ? out[(size_t)(b + 8 + j) * kInner] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int i = 0; i < kTaps; ++i) acc[j] = fmaf(w[i], win[j + i], acc[j]);
+            if (b + j < rows) out[(size_t)(b + j) * kInner] = acc[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) win[i] = win[i + 8];
+    }
+}
+
+}  // namespace tc

@@ -10,6 +10,7 @@
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
 #include "fc_stack_tc.cuh"
+#include "attn_tc.cuh"
 #include "nystrom.cuh"
 #include "tail.cuh"
 #include "decode_nms.cuh"
@@ -35,11 +36,11 @@ int cuda_fail(cudaError_t e, const char* where) {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- optional per-stage CUDA-event timing (bench / profiling only; off by default) ----
-enum Stage : int { ST_SPLIT = 0, ST_QKV, ST_LANDMARKS, ST_ATTN2, ST_A3V, ST_PINV, ST_ATTN_OUT, ST_TO_OUT, ST_LN,
+enum Stage : int { ST_SPLIT = 0, ST_QKV, ST_LANDMARKS, ST_ATTN2, ST_A3V, ST_PINV, ST_CONV, ST_ATTN_OUT, ST_TO_OUT, ST_LN,
                    ST_FC1, ST_FC_STACK, ST_ROI, ST_DECODE, ST_NMS, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"split_f16", "to_qkv_gemm", "landmarks", "attn2_softmax", "a3v_stream",
-                                           "pinv_w", "attn_out_conv", "to_out_gemm", "layernorm1024", "fc1_gemm",
-                                           "fc_stack", "roi_pool_heads", "decode_boxes", "nms"};
+                                           "pinv_w", "value_conv", "attn_out", "to_out_gemm", "layernorm1024",
+                                           "fc1_gemm", "fc_stack", "roi_pool_heads", "decode_boxes", "nms"};
 struct StageEvents { int stage; cudaEvent_t e0, e1; };
 bool g_stage_timing = false;
 std::vector<StageEvents> g_stage_events;
@@ -106,12 +107,14 @@ cudaError_t opt_in_smem(K kernel, int bytes) {
 
 int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, const float* B, const void* B16,
                   float* C, int M, int N, int K, const float* bias, const float* res, int qcols, cudaStream_t st,
-                  int stage = ST_QKV) {
+                  int stage = ST_QKV, float* aux = nullptr) {
     StageScope scope(stage, st);
     if (M < 1 || N < 1 || K < 1) return fail(EDSNET_E_ARG, "gemm: empty problem");
-    if (epilogue < 0 || epilogue > 3) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
-    if ((epilogue >= 2 && !bias) || (epilogue == 3 && !res)) return fail(EDSNET_E_ARG, "gemm: epilogue operand is NULL");
-    GemmEpiArgs ep{bias, res, N, qcols, nullptr, nullptr};
+    if (epilogue < 0 || epilogue > 4) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
+    if (epilogue == 4 && (precision == EDSNET_PREC_FP32 || !aux || N != kQkvCols))
+        return fail(EDSNET_E_ARG, "gemm: the plane epilogue needs a tcgen05 precision, N = 1536 and the scale output");
+    if (((epilogue == 2 || epilogue == 3) && !bias) || (epilogue == 3 && !res)) return fail(EDSNET_E_ARG, "gemm: epilogue operand is NULL");
+    GemmEpiArgs ep{bias, res, N, qcols, nullptr, nullptr, aux};
     if (precision == EDSNET_PREC_FP32) {
         if (!A || !B || !C) return fail(EDSNET_E_ARG, "gemm: NULL operand");
         if (K % kGemmBK || N % 4) return fail(EDSNET_E_ARG, "gemm fp32: K must be a multiple of 16, N of 4");
@@ -139,9 +142,29 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
     return EDSNET_OK;
 }
 
-int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv_w, float* q_land, float* k_land,
-                      float* attn2, float* stats, float* a3v, float* zmat, float* wmat, float* merged,
-                      cudaStream_t st) {
+// qkv: fp32 [R][1536] for EDSNET_PREC_FP32; for the tcgen05 precisions the hi plane [R][1536] fp16 followed by the lo
+// plane, with qkv_inv [R][24] (gemm_tc.cuh EPI_QKV_PLANES).
+int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, const float* qkv_inv,
+                      const float* conv_w, float* q_land, float* k_land, float* attn2, float* stats, float* a3v,
+                      float* zmat, float* wmat, float* merged, cudaStream_t st) {
+    const bool tcp = precision != EDSNET_PREC_FP32;
+    const __half* p_hi = reinterpret_cast<const __half*>(qkv);
+    const __half* p_lo = p_hi + (size_t)b->total_rows * kQkvCols;
+    CUtensorMap map_hi, map_lo;
+    if (tcp) {
+        if (!qkv_inv) return fail(EDSNET_E_ARG, "nystrom_core: tcgen05 precision needs the plane scales");
+        std::string msg;
+        if (!tc::make_map(&map_hi, p_hi, (uint64_t)b->total_rows, kQkvCols, 64, 64, &msg) ||
+            !tc::make_map(&map_lo, p_lo, (uint64_t)b->total_rows, kQkvCols, 64, 64, &msg))
+            return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
+        static bool tc_attr = false;
+        if (!tc_attr) {
+            CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
+            CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
+            CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
+            tc_attr = true;
+        }
+    }
     static bool attrs_done = false;     // per-process; the attribute is per device function
     if (!attrs_done) {
         CU_CHECK(opt_in_smem(a3v_kernel, kA3vSmem), "smem opt-in a3v");
@@ -152,7 +175,8 @@ int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv
     const int V = b->n_videos;
     {
         StageScope scope(ST_LANDMARKS, st);
-        landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
+        if (tcp) tc::landmarks_planes_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(p_hi, p_lo, qkv_inv, b->cu_rows, q_land, k_land);
+        else landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
         CU_CHECK(cudaGetLastError(), "landmarks_kernel");
     }
     {
@@ -162,7 +186,8 @@ int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv
     }
     {
         StageScope scope(ST_A3V, st);
-        a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
+        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 160, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
+        else a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
         CU_CHECK(cudaGetLastError(), "a3v_kernel");
     }
     {
@@ -170,7 +195,18 @@ int nystrom_core_impl(const edsnet_batch* b, const float* qkv, const float* conv
         pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
     }
-    {
+    if (tcp) {
+        {
+            StageScope scope(ST_ATTN_OUT, st);
+            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 160, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+                                                                                  k_land, wmat, merged);
+            CU_CHECK(cudaGetLastError(), "attn_out_tc_kernel");
+        }
+        StageScope scope(ST_CONV, st);
+        tc::value_conv_kernel<<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
+            p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged);
+        CU_CHECK(cudaGetLastError(), "value_conv_kernel");
+    } else {
         StageScope scope(ST_ATTN_OUT, st);
         attn_out_kernel<<<dim3(b->n_tiles64, kHeads), 256, kAttnOutSmem, st>>>(
             qkv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles64), k_land, wmat, conv_w, merged);
@@ -240,6 +276,7 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.k_land = take(head_mat);
     L.attn2 = take(head_mat);
     L.stats = take(V * kHeads * 2 * sizeof(float));
+    L.qkv_inv = take(R * 24 * sizeof(float));
     L.a3v = take(head_mat);
     L.zmat = take(head_mat);
     L.wmat = take(head_mat);
@@ -321,15 +358,17 @@ int edsnet_gemm(int32_t precision, int32_t epilogue, const float* A, const void*
                          static_cast<cudaStream_t>(stream));
 }
 
-int edsnet_nystrom_core(const edsnet_batch* batch, const float* qkv, const float* res_conv_w, float* q_land,
+int edsnet_nystrom_core(int32_t precision, const edsnet_batch* batch, const float* qkv, const float* qkv_inv,
+                        const float* res_conv_w, float* q_land,
                         float* k_land, float* attn2, float* stats, float* a3v, float* zmat, float* wmat,
                         float* merged, void* stream) {
     int rc = check_batch(batch);
     if (rc) return rc;
     if (!qkv || !res_conv_w || !q_land || !k_land || !attn2 || !stats || !a3v || !wmat || !merged)
         return fail(EDSNET_E_ARG, "nystrom_core: NULL operand");
-    return nystrom_core_impl(batch, qkv, res_conv_w, q_land, k_land, attn2, stats, a3v, zmat, wmat, merged,
-                             static_cast<cudaStream_t>(stream));
+    if (precision < EDSNET_PREC_FP32 || precision > EDSNET_PREC_FP16) return fail(EDSNET_E_ARG, "unknown precision");
+    return nystrom_core_impl(precision, batch, qkv, qkv_inv, res_conv_w, q_land, k_land, attn2, stats, a3v, zmat, wmat,
+                             merged, static_cast<cudaStream_t>(stream));
 }
 
 int edsnet_fc_stack(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out,
@@ -374,11 +413,12 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         x16 = ws + L.x16;
     }
     // 1. qkv = x Wqkv^T, q pre-scaled by 1/8                                   (nystroformer.py:82-91)
-    rc = gemm_dispatch(prec, EPI_QSCALE, x, x16, w->to_qkv_w, w->to_qkv_w16, F(L.qkv), R, kQkvCols, kFeat,
-                       nullptr, nullptr, kInner, st);
+    //    (tcgen05: written as fp16 operand planes + per-(row, head) scales, see attn_tc.cuh)
+    rc = gemm_dispatch(prec, prec == EDSNET_PREC_FP32 ? EPI_QSCALE : EPI_QKV_PLANES, x, x16, w->to_qkv_w, w->to_qkv_w16,
+                       F(L.qkv), R, kQkvCols, kFeat, nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
     if (rc) return rc;
     // 2. landmark attention core -> merged heads                                (nystroformer.py:95-142)
-    rc = nystrom_core_impl(batch, F(L.qkv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
+    rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
                            F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st);
     if (rc) return rc;
     // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
@@ -417,7 +457,8 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
 int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
     // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add three operand splits
-    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 14;
+    // and run the value convolution as its own kernel
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 15;
 }
 
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

@@ -9,7 +9,9 @@ enum GemmEpi : int {
     EPI_NONE = 0,
     EPI_QSCALE = 1,        // columns < qcols multiplied by 1/8 (q = q * dim_head^-0.5, nystroformer.py:91)
     EPI_BIAS = 2,          // + bias[n]
-    EPI_BIAS_RES = 3       // + bias[n] + res[m, n]   (to_out bias + residual x, dsnet.py:105)
+    EPI_BIAS_RES = 3,      // + bias[n] + res[m, n]   (to_out bias + residual x, dsnet.py:105)
+    EPI_QKV_PLANES = 4     // tcgen05 path only: q|k|v written as row-scaled fp16 hi/lo planes per (row, head), the
+                           // operand format of the tensor-core attention kernels (nystrom_tc.cuh); C = hi plane base
 };
 
 struct GemmEpiArgs {
@@ -19,6 +21,7 @@ struct GemmEpiArgs {
     int qcols;
     const float* a_scale;  // tcgen05 path: [M] power-of-two factor undoing the row scaling of A's fp16 planes
     const float* b_scale;  // tcgen05 path: [N] same for B
+    float* aux;            // EPI_QKV_PLANES: [M][24] inverse scales, index part*8 + head (q's include the 1/8)
 };
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmLd = 132;

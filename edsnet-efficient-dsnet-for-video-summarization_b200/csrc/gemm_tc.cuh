@@ -291,7 +291,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
-            if (row < M) {
+            if (row < M && EPI == EPI_QKV_PLANES) {
+                // q|k|v as operand planes: per (row, head) power-of-two scale, hi = fp16(x 2^s), lo = fp16(x 2^s - hi)
+                const float ra = __ldg(ep.a_scale + row);
+                __half* hi_row = reinterpret_cast<__half*>(C) + (size_t)row * N + n0;
+                __half* lo_row = hi_row + (size_t)M * N;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4) {
+                        const float4 rb = ldg4(ep.b_scale + n0 + half * 64 + j);
+                        v[half * 64 + j] *= ra * rb.x; v[half * 64 + j + 1] *= ra * rb.y;
+                        v[half * 64 + j + 2] *= ra * rb.z; v[half * 64 + j + 3] *= ra * rb.w;
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[half * 64 + j]), fabsf(v[half * 64 + j + 1])),
+                                             fmaxf(fabsf(v[half * 64 + j + 2]), fabsf(v[half * 64 + j + 3]))));
+                    }
+                    int e = 0;
+                    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+                    e = max(-100, min(100, e));
+                    const float sc = ldexpf(1.f, e);
+                    const int slot = (n0 >> 6) + half;                      // part * 8 + head
+                    ep.aux[(size_t)row * 24 + slot] = ldexpf(1.f, -e) * (slot < 8 ? 0.125f : 1.f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        __half2 hh[4], ll[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float v0 = v[half * 64 + c * 8 + 2 * q] * sc, v1 = v[half * 64 + c * 8 + 2 * q + 1] * sc;
+                            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                            hh[q] = __halves2half2(h0, h1);
+                            ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
+                                                   __float2half_rn(v1 - __half2float(h1)));
+                        }
+                        *reinterpret_cast<uint4*>(hi_row + half * 64 + c * 8) = *reinterpret_cast<uint4*>(hh);
+                        *reinterpret_cast<uint4*>(lo_row + half * 64 + c * 8) = *reinterpret_cast<uint4*>(ll);
+                    }
+                }
+            } else if (row < M) {
                 float* crow = C + (size_t)row * N + n0;
                 const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
                 const float ra = __ldg(ep.a_scale + row);
@@ -458,8 +495,8 @@ static cudaError_t launch_gemm_tc(int passes, int epilogue, const __half* A16, c
                                   int N, int K, GemmEpiArgs ep, cudaStream_t st, std::string* msg) {
     if (K % 64 != 0) { if (msg) *msg = "K must be a multiple of 64"; return cudaErrorInvalidValue; }
 #define TC_CASE(P, E) if (passes == P && epilogue == E) return tc::launch_shape<P, E>(A16, B16, C, M, N, K, ep, st, msg);
-    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3)
-    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3)
+    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3) TC_CASE(3, 4)
+    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3) TC_CASE(1, 4)
 #undef TC_CASE
     if (msg) *msg = "unsupported passes/epilogue";
     return cudaErrorInvalidValue;

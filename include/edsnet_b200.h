@@ -96,11 +96,12 @@ typedef struct {
 
 /* Byte offsets of the intermediates inside the forward workspace (for tests / profiling). */
 typedef struct {
-    size_t qkv;        /* [rows][1536]  q (pre-scaled by 1/8) | k | v                */
+    size_t qkv;        /* fp32 mode: [rows][1536] q (pre-scaled by 1/8) | k | v; tcgen05: fp16 hi plane, lo plane */
     size_t q_land;     /* [videos][8][64][64]                                         */
     size_t k_land;
     size_t attn2;      /* softmax(q_land k_land^T)                                    */
     size_t stats;      /* [videos][8][2]                                              */
+    size_t qkv_inv;    /* tcgen05 precisions: [rows][24] inverse scales of the q|k|v planes */
     size_t a3v;        /* softmax(q_land k^T) v                                       */
     size_t zmat;       /* pseudo-inverse of attn2                                     */
     size_t wmat;       /* zmat a3v                                                    */
@@ -156,12 +157,15 @@ int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t co
 
 /* ---- stage-level entry points (tests, per-kernel timing, ncu) ---- */
 
-/* C[M][N] = A[M][K] . B[N][K]^T, epilogue: 0 none, 1 first qcols columns * 1/8, 2 + bias, 3 + bias + res. */
+/* C[M][N] = A[M][K] . B[N][K]^T, epilogue: 0 none, 1 first qcols columns * 1/8, 2 + bias, 3 + bias + res
+ * (4, the q|k|v plane epilogue, is internal to edsnet_forward). */
 int edsnet_gemm(int32_t precision, int32_t epilogue, const float* A, const void* A16, const float* B,
                 const void* B16, float* C, int32_t M, int32_t N, int32_t K, const float* bias,
                 const float* res, int32_t qcols, void* stream);
-/* qkv -> merged: landmarks, three softmax kernels, pseudo-inverse, aggregation, value conv (nystroformer.py). */
-int edsnet_nystrom_core(const edsnet_batch* batch, const float* qkv, const float* res_conv_w, float* q_land,
+/* qkv -> merged: landmarks, three softmax kernels, pseudo-inverse, aggregation, value conv (nystroformer.py).
+ * precision selects the CUDA-core (EDSNET_PREC_FP32) or the tcgen05 split-fp16 kernels for the row stages. */
+int edsnet_nystrom_core(int32_t precision, const edsnet_batch* batch, const float* qkv, const float* qkv_inv,
+                        const float* res_conv_w, float* q_land,
                         float* k_land, float* attn2, float* stats, float* a3v, float* zmat, float* wmat,
                         float* merged, void* stream);
 /* u0 -> u1: fc_depth applications of the shared block. */

@@ -85,8 +85,9 @@ def test_forward_matches_reference_golden(name, precision):
     assert e_cls < TOL[precision] and e_loc < TOL[precision], (e_cls, e_loc)
 
 
-def test_forward_stages_match_oracle():
-    """Intermediates of the fp32 path, read back from the workspace, against the oracle's stages."""
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_forward_stages_match_oracle(precision):
+    """Intermediates of the forward, read back from the workspace, against the oracle's stages."""
     capi, lib = _lib()
     g, x, p = golden_case(FWD, "T450_s4_8_16_32_d7")
     scales, depth = [int(s) for s in g["scales"]], int(g["fc_depth"])
@@ -94,10 +95,10 @@ def test_forward_stages_match_oracle():
     stages = {}
     with torch.no_grad():
         orc.dsnet_forward(x, p, scales, depth, stages=stages)
-    model = make_model(p, scales, depth, "fp32", DEV)
+    model = make_model(p, scales, depth, precision, DEV)
     with torch.no_grad():
         model(x[None].to(DEV))
-    torch.cuda.synchronize()
+    _no_tc_timeout()
     L = capi.WorkspaceLayout()
     lib.edsnet_workspace_bytes(model._config(), T, 1, C.byref(L))
     ws = model._workspace
