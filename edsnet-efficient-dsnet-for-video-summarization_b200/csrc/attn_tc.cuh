@@ -432,6 +432,160 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Iterative Moore-Penrose pseudo-inverse of attn2 (nystroformer.py:13-28) and W = Z a3v on tensor cores, TWO heads of
+// one video per CTA.  Every 64 x 64 matrix of the chain is kept as a [128 rows][128 B] plane tile (head 0 rows 0..63,
+// head 1 rows 64..127) with ONE power-of-two scale per head.  The same bytes serve as left operand (K-major, the two
+// heads stacked along M) and as right operand (MN-major, the two heads side by side along N, LBO = 8 KB): each
+// 128 x 128 product holds the two wanted 64 x 64 products on its block diagonal, thread t reads row t of its own block.
+// Per product: row -> registers -> (7I - ., 15I - ., ...) -> matrix max (shuffle + one barrier) -> planes -> MMA.
+// grid (4 head pairs, V), 128 threads, 5 tiles = 160 KB shared memory, TMEM 256 columns (main | cross).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPinvTile = 32768;
+constexpr int kPinvTcSmemBytes = 5 * kPinvTile + 256 + 1024;
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn2(uint32_t addr) {      // two MN atoms, 8 KB apart
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void issue_pinv_product(uint32_t tmem_base, uint32_t left, uint32_t right) {
+    constexpr uint32_t idesc = make_idesc_bmn(128, 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ka = (uint32_t)k * 32u, kb = (uint32_t)k * 2048u;
+        const uint64_t dah = make_smem_desc<64>(left + ka), dal = make_smem_desc<64>(left + 16384 + ka);
+        const uint64_t dbh = make_smem_desc_mn2(right + kb), dbl = make_smem_desc_mn2(right + 16384 + kb);
+        umma_f16(tmem_base, dah, dbh, idesc, k != 0 ? 1u : 0u);
+        umma_f16(tmem_base + 128u, dah, dbl, idesc, k != 0 ? 1u : 0u);
+        umma_f16(tmem_base + 128u, dal, dbh, idesc, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(128, 1)
+pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
+                 float* __restrict__ w_out, float* __restrict__ z_out, int iters) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int oA = 0, oZ = kPinvTile, oXZ = 2 * kPinvTile, oT = 3 * kPinvTile, oU = 4 * kPinvTile, oVec = 5 * kPinvTile;
+    float* s_mx = reinterpret_cast<float*>(g + oVec);                       // [2 parities][2 slots][4 warps]
+    const uint32_t bar = base + oVec + 128;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 144);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hh = tid >> 6, i = tid & 63;
+    const int v = blockIdx.y, h = blockIdx.x * 2 + hh;
+    const size_t off = ((size_t)v * kHeads + h) * 4096;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(base + oVec + 144, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(hh * 64), t_lo = t_main + 128u;
+    uint32_t phase = 0, par = 0;
+    bool ok = true;
+
+    // head-wide maximum of up to two per-row values (one shuffle reduction + one barrier)
+    auto head_max2 = [&](float m0, float m1, float& o0, float& o1) {
+        m0 = warp_max(m0); m1 = warp_max(m1);
+        float* slot = s_mx + par * 8;
+        if (lane == 0) { slot[warp] = m0; slot[4 + warp] = m1; }
+        tc_fence_before();
+        named_bar_sync(1, 128);
+        o0 = fmaxf(slot[2 * hh], slot[2 * hh + 1]);
+        o1 = fmaxf(slot[4 + 2 * hh], slot[4 + 2 * hh + 1]);
+        par ^= 1u;
+    };
+    // store this thread's row of a matrix into tile `o` with the head-wide scale 2^e; returns 2^-e
+    auto put = [&](int o, const float (&row)[64], float head_mx) -> float {
+        const int e = scale_exp(head_mx);
+        store_row64(g + o, g + o + 16384, tid, row, ldexpf(1.f, e));
+        return ldexpf(1.f, -e);
+    };
+    auto product = [&](int left, int right, float (&out)[64], float scale) {
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1, 128);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_pinv_product(tmem_base, base + left, base + right);
+            umma_commit(bar);
+        }
+        ok = mbar_wait(bar, phase) && ok;
+        phase ^= 1u;
+        tc_fence_after();
+        tmem_read64_sum(t_main, t_lo, out);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) out[j] *= scale;
+    };
+
+    // ---- start: A = attn2, Z0 = A^T / (max row sum * max column sum over ALL 8 heads of the video) ----
+    float mrow = 0.f, mcol = 0.f;
+#pragma unroll
+    for (int q = 0; q < kHeads; ++q) {
+        mrow = fmaxf(mrow, __ldg(stats + ((size_t)v * kHeads + q) * 2 + 0));
+        mcol = fmaxf(mcol, __ldg(stats + ((size_t)v * kHeads + q) * 2 + 1));
+    }
+    const float denom = mrow * mcol;
+    float z[64], t[64];
+    load_row64(t, attn2 + off + i * 64);                                   // row i of A
+#pragma unroll
+    for (int j = 0; j < 64; ++j) z[j] = __ldg(attn2 + off + j * 64 + i) / denom;    // row i of A^T
+    float mA, mZ;
+    head_max2(absmax64(t), absmax64(z), mA, mZ);
+    const float invA = put(oA, t, mA);
+    float invZ = put(oZ, z, mZ);
+
+    for (int it = 0; it < iters && ok; ++it) {
+        // XZ = A Z ; T1 = 7I - XZ
+        float xz[64];
+        product(oA, oZ, xz, invA * invZ);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 7.f : 0.f) - xz[j];
+        float mXZ, mT;
+        head_max2(absmax64(xz), absmax64(t), mXZ, mT);
+        const float invXZ = put(oXZ, xz, mXZ);
+        float invT = put(oT, t, mT);
+        // U = 15I - XZ T1
+        product(oXZ, oT, t, invXZ * invT);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 15.f : 0.f) - t[j];
+        float mU, dummy;
+        head_max2(absmax64(t), 0.f, mU, dummy);
+        const float invU = put(oU, t, mU);
+        // T2 = 13I - XZ U
+        product(oXZ, oU, t, invXZ * invU);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 13.f : 0.f) - t[j];
+        head_max2(absmax64(t), 0.f, mT, dummy);
+        invT = put(oT, t, mT);
+        // Z' = 0.25 Z T2
+        product(oZ, oT, z, 0.25f * invZ * invT);
+        head_max2(absmax64(z), 0.f, mZ, dummy);
+        invZ = put(oZ, z, mZ);
+    }
+    if (z_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) st4(z_out + off + i * 64 + j, make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]));
+    }
+    // ---- W = Z a3v ----
+    load_row64(t, a3v + off + i * 64);
+    float mV, dummy2;
+    head_max2(absmax64(t), 0.f, mV, dummy2);
+    const float invV = put(oU, t, mV);
+    product(oZ, oU, t, invZ * invV);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) st4(w_out + off + i * 64 + j, make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // value convolution + merge: merged[r][h*64+c] = attn[r][h*64+c] + sum_t w[h][t] * v[r + t - 16][h*64+c], rows
 // outside the video are zero (nystroformer.py:61-65,137-138).
 // grid (n_tiles128, 4): a CTA owns 128 rows x 128 value columns (two heads).  The 160 x 128 input window is rebuilt

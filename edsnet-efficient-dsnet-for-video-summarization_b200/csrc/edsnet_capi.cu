@@ -162,6 +162,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
             CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
+            CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
             tc_attr = true;
         }
     }
@@ -192,7 +193,8 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     }
     {
         StageScope scope(ST_PINV, st);
-        pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        if (tcp) tc::pinv_w_tc_kernel<<<dim3(kHeads / 2, V), 128, tc::kPinvTcSmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        else pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
     }
     if (tcp) {
@@ -433,16 +435,20 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
                        kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
     if (rc) return rc;
     // 4. LayerNorm(1024) -> fc1                                                 (dsnet.py:106)
+    const void* yn16 = nullptr;
     {
         StageScope scope(ST_LN, st);
-        layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
+        if (prec != EDSNET_PREC_FP32) {
+            // LayerNorm output goes straight into the operand planes of fc1 (no fp32 yn, no separate split)
+            __half* hi = reinterpret_cast<__half*>(ws + L.x16);
+            __half* lo = hi + (size_t)R * kFeat;
+            layernorm1024_planes_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, hi, lo,
+                                                                     reinterpret_cast<float*>(lo + (size_t)R * kFeat), R);
+            yn16 = ws + L.x16;
+        } else {
+            layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
+        }
         CU_CHECK(cudaGetLastError(), "layernorm1024_kernel");
-    }
-    const void* yn16 = nullptr;
-    if (prec != EDSNET_PREC_FP32) {
-        rc = edsnet_split_f16(F(L.yn), ws + L.x16, R, kFeat, stream);
-        if (rc) return rc;
-        yn16 = ws + L.x16;
     }
     rc = gemm_dispatch(prec, EPI_BIAS, F(L.yn), yn16, w->fc1_w, w->fc1_w16, F(L.u0), R, kHidden, kFeat, w->fc1_b,
                        nullptr, 0, st, ST_FC1);
@@ -456,9 +462,9 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
 
 int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
-    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add three operand splits
-    // and run the value convolution as its own kernel
-    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 15;
+    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add two operand splits (x,
+    // merged) and run the value convolution as its own kernel
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 14;
 }
 
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

@@ -39,6 +39,62 @@ layernorm1024_kernel(const float* __restrict__ y, const float* __restrict__ gamm
     }
 }
 
+// Same LayerNorm, but the result is written directly as the row-scaled fp16 hi/lo operand planes (+ inverse row scale)
+// that the tcgen05 fc1 GEMM consumes (layout of edsnet_split_f16): saves the fp32 round trip and one launch.
+__global__ void __launch_bounds__(256)
+layernorm1024_planes_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ inv_scale, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* src = y + (size_t)row * kFeat;
+    float4 x[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = ldg4(src + (i * 32 + lane) * 4);
+        s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+    const float mean = warp_sum(s) / (float)kFeat;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) / (float)kFeat + 1e-5f);
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = ldg4(gamma + c), b = ldg4(beta + c);
+        x[i] = make_float4(x[i].x * rstd * g.x + b.x, x[i].y * rstd * g.y + b.y, x[i].z * rstd * g.z + b.z,
+                           x[i].w * rstd * g.w + b.w);
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x[i].x), fabsf(x[i].y)), fmaxf(fabsf(x[i].z), fabsf(x[i].w))));
+    }
+    mx = warp_max(mx);
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+    e = max(-100, min(100, e));
+    const float sc = ldexpf(1.f, e);
+    if (lane == 0) inv_scale[row] = ldexpf(1.f, -e);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float v[4] = {x[i].x * sc, x[i].y * sc, x[i].z * sc, x[i].w * sc};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2half_rn(v[j]);
+            l[j] = __float2half_rn(v[j] - __half2float(h[j]));
+        }
+        __half2 hh[2] = {__halves2half2(h[0], h[1]), __halves2half2(h[2], h[3])};
+        __half2 ll[2] = {__halves2half2(l[0], l[1]), __halves2half2(l[2], l[3])};
+        const size_t o = (size_t)row * kFeat + (i * 32 + lane) * 4;
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(ll);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // D applications of the ONE shared fc block (dsnet.py:91-96,107-108; eval mode: Dropout = identity).
 // 64 rows per CTA; the 128x128 weight (transposed) and the activations stay in shared memory for all D rounds.
