@@ -5,9 +5,11 @@ Public surface:
   BatchPlan        packed variable-length batch tables
   shard_videos     video-wise partition across ranks (no collective on the data path)
   ScoringPipeline  host-buffer -> proposals throughput path (pinned H2D / compute / D2H overlapped)
+  training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
 from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
 from .dsnet import DSNet, NystromAttention                      # noqa: F401
 from .pipeline import ScoringPipeline                            # noqa: F401
+from . import training                                           # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]
