@@ -8,7 +8,7 @@ Public surface:
   training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
 from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
-from .dsnet import DSNet, NystromAttention                      # noqa: F401
+from .dsnet import DSNet, NystromAttention, AttentionExtractor                      # noqa: F401
 from .pipeline import ScoringPipeline                            # noqa: F401
 from . import training                                           # noqa: F401
 

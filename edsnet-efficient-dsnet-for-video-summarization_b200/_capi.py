@@ -12,22 +12,24 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 2
+EDSNET_ABI_VERSION = 3
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
 PREC_FP32, PREC_FP16X3, PREC_FP16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16}
+BASE_MODELS = {"nystromformer": 0, "attention": 1}
 
 
 class Config(C.Structure):
     _fields_ = [("fc_depth", C.c_int32), ("n_scales", C.c_int32),
-                ("scales", C.c_int32 * EDSNET_MAX_SCALES), ("precision", C.c_int32)]
+                ("scales", C.c_int32 * EDSNET_MAX_SCALES), ("precision", C.c_int32), ("base_model", C.c_int32)]
 
 
 WEIGHT_FIELDS = ("to_qkv_w", "to_out_w", "to_out_b", "res_conv_w", "ln_w", "ln_b", "fc1_w", "fc1_b",
                  "fcb_w", "fcb_b", "fcb_ln_w", "fcb_ln_b", "cls_w", "cls_b", "loc_w", "loc_b",
-                 "to_qkv_w16", "to_out_w16", "fc1_w16", "fcb_w16")
+                 "to_qkv_w16", "to_out_w16", "fc1_w16", "fcb_w16",
+                 "mha_qkv_w", "mha_fc_w", "mha_qkv_w16", "mha_fc_w16")
 
 
 class Weights(C.Structure):
@@ -41,7 +43,7 @@ class Batch(C.Structure):
 
 
 LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",
-                 "u0", "u1", "x16", "total")
+                 "u0", "u1", "x16", "zeros", "total")
 
 
 class WorkspaceLayout(C.Structure):
@@ -114,7 +116,7 @@ def check(rc: int) -> None:
         raise EdsnetError(rc, last_error())
 
 
-def make_config(scales, fc_depth: int, precision: int) -> Config:
+def make_config(scales, fc_depth: int, precision: int, base_model: int = 0) -> Config:
     scales = [int(s) for s in scales]
     if not 1 <= len(scales) <= EDSNET_MAX_SCALES:
         raise ValueError(f"1..{EDSNET_MAX_SCALES} anchor scales supported, got {len(scales)}")
@@ -124,6 +126,7 @@ def make_config(scales, fc_depth: int, precision: int) -> Config:
     for i, s in enumerate(scales):
         cfg.scales[i] = s
     cfg.precision = int(precision)
+    cfg.base_model = int(base_model)
     return cfg
 
 

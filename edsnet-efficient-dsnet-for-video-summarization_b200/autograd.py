@@ -39,8 +39,19 @@ def _attention(bm, x):
     return bm.to_out(out)[pad:]
 
 
+def _mha(bm, x):
+    """Full multi-head attention base (src/modules/models.py:46-65); both Dropout(0.5) follow the module's mode."""
+    T, Fd = x.shape
+    h, dk = bm.num_head, bm.d_k
+    q, k, v = (m(x).reshape(T, h, dk).permute(1, 0, 2) for m in (bm.Q, bm.K, bm.V))
+    attn = torch.softmax((q @ k.transpose(1, 2)) / dk ** 0.5, dim=-1)
+    attn = F.dropout(attn, 0.5, bm.training)
+    y = (attn @ v).permute(1, 0, 2).reshape(T, Fd)
+    return bm.fc(y)
+
+
 def _score_one(model, x):
-    out = _attention(model.base_model, x) + x
+    out = (_mha(model.base_model, x) if model.base_model_type == "attention" else _attention(model.base_model, x)) + x
     out = model.fc1(model.layer_norm(out))
     for fc in model.fc:
         out = fc(out)

@@ -11,6 +11,7 @@
 #include "gemm_tc.cuh"
 #include "fc_stack_tc.cuh"
 #include "attn_tc.cuh"
+#include "mha.cuh"
 #include "nystrom.cuh"
 #include "tail.cuh"
 #include "decode_nms.cuh"
@@ -77,6 +78,8 @@ int check_cfg(const edsnet_config* cfg) {
     if (cfg->fc_depth < 0 || cfg->fc_depth > 64) return fail(EDSNET_E_ARG, "fc_depth out of range 0..64");
     if (cfg->precision < EDSNET_PREC_FP32 || cfg->precision > EDSNET_PREC_FP16)
         return fail(EDSNET_E_ARG, "unknown precision");
+    if (cfg->base_model != EDSNET_BASE_NYSTROM && cfg->base_model != EDSNET_BASE_ATTENTION)
+        return fail(EDSNET_E_UNSUPPORTED, "base model outside the accelerated path (nystromformer, attention)");
     return EDSNET_OK;
 }
 
@@ -272,7 +275,8 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     const size_t head_mat = V * kHeads * 4096 * sizeof(float);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-    L.qkv = take(R * kQkvCols * sizeof(float));
+    const bool mha = cfg && cfg->base_model == EDSNET_BASE_ATTENTION;
+    L.qkv = take(R * (mha ? kMhaQkvCols : kQkvCols) * sizeof(float));
     L.yn = L.qkv;                                    // LayerNorm output reuses the (dead) qkv region
     L.q_land = take(head_mat);
     L.k_land = take(head_mat);
@@ -282,12 +286,13 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.a3v = take(head_mat);
     L.zmat = take(head_mat);
     L.wmat = take(head_mat);
-    L.merged = take(R * kInner * sizeof(float));
+    L.merged = take(R * (mha ? kMhaFeat : kInner) * sizeof(float));
     L.y = take(R * kFeat * sizeof(float));
     L.u0 = take(R * kHidden * sizeof(float));
     L.u1 = take(R * kHidden * sizeof(float));
     L.x16 = off;
     if (cfg && cfg->precision != EDSNET_PREC_FP32) take(split_f16_bytes(R, kFeat));
+    L.zeros = take(kFeat * sizeof(float));
     L.total = off;
     if (layout) *layout = L;
     return L.total;
@@ -408,32 +413,64 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     const int prec = cfg->precision;
     const void* x16 = nullptr;
     if (prec != EDSNET_PREC_FP32) {
-        if (!w->to_qkv_w16 || !w->to_out_w16 || !w->fc1_w16 || !w->fcb_w16)
+        const bool nys = cfg->base_model == EDSNET_BASE_NYSTROM;
+        if ((nys && (!w->to_qkv_w16 || !w->to_out_w16)) || !w->fc1_w16 || !w->fcb_w16)
             return fail(EDSNET_E_ARG, "forward: tcgen05 precision needs the fp16 weight planes (edsnet_split_f16)");
         rc = edsnet_split_f16(x, ws + L.x16, R, kFeat, stream);
         if (rc) return rc;
         x16 = ws + L.x16;
     }
-    // 1. qkv = x Wqkv^T, q pre-scaled by 1/8                                   (nystroformer.py:82-91)
-    //    (tcgen05: written as fp16 operand planes + per-(row, head) scales, see attn_tc.cuh)
-    rc = gemm_dispatch(prec, prec == EDSNET_PREC_FP32 ? EPI_QSCALE : EPI_QKV_PLANES, x, x16, w->to_qkv_w, w->to_qkv_w16,
-                       F(L.qkv), R, kQkvCols, kFeat, nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
-    if (rc) return rc;
-    // 2. landmark attention core -> merged heads                                (nystroformer.py:95-142)
-    rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
-                           F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st);
-    if (rc) return rc;
-    // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
-    const void* merged16 = nullptr;
-    if (prec != EDSNET_PREC_FP32) {
-        // the x16 planes are dead after step 1: reuse the front of that region for merged (R x 512)
-        rc = edsnet_split_f16(F(L.merged), ws + L.x16, R, kInner, stream);
+    if (cfg->base_model == EDSNET_BASE_ATTENTION) {
+        // full multi-head attention base (modules/models.py:46-65): Q|K|V projection, flash attention, output
+        // projection (bias-free) + residual x
+        if (!w->mha_qkv_w || !w->mha_fc_w || (prec != EDSNET_PREC_FP32 && (!w->mha_qkv_w16 || !w->mha_fc_w16)))
+            return fail(EDSNET_E_ARG, "forward: attention base needs the mha_* weights");
+        rc = gemm_dispatch(prec, EPI_NONE, x, x16, w->mha_qkv_w, w->mha_qkv_w16, F(L.qkv), R, kMhaQkvCols, kFeat,
+                           nullptr, nullptr, 0, st);
         if (rc) return rc;
-        merged16 = ws + L.x16;
+        {
+            static bool mha_attr = false;
+            if (!mha_attr) {
+                CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
+                mha_attr = true;
+            }
+            StageScope scope(ST_A3V, st);
+            mha_flash_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kMhaSmem, st>>>(
+                F(L.qkv), batch->cu_rows, reinterpret_cast<const int2*>(batch->tiles64), F(L.merged));
+            CU_CHECK(cudaGetLastError(), "mha_flash_kernel");
+        }
+        const void* m16 = nullptr;
+        if (prec != EDSNET_PREC_FP32) {
+            rc = edsnet_split_f16(F(L.merged), ws + L.x16, R, kMhaFeat, stream);
+            if (rc) return rc;
+            m16 = ws + L.x16;
+        }
+        CU_CHECK(cudaMemsetAsync(ws + L.zeros, 0, kFeat * sizeof(float), st), "zero bias");
+        rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), m16, w->mha_fc_w, w->mha_fc_w16, F(L.y), R, kFeat, kMhaFeat,
+                           F(L.zeros), x, 0, st, ST_TO_OUT);
+        if (rc) return rc;
+    } else {
+        // 1. qkv = x Wqkv^T, q pre-scaled by 1/8                                   (nystroformer.py:82-91)
+        //    (tcgen05: written as fp16 operand planes + per-(row, head) scales, see attn_tc.cuh)
+        rc = gemm_dispatch(prec, prec == EDSNET_PREC_FP32 ? EPI_QSCALE : EPI_QKV_PLANES, x, x16, w->to_qkv_w, w->to_qkv_w16,
+                           F(L.qkv), R, kQkvCols, kFeat, nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
+        if (rc) return rc;
+        // 2. landmark attention core -> merged heads                                (nystroformer.py:95-142)
+        rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
+                               F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st);
+        if (rc) return rc;
+        // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
+        const void* merged16 = nullptr;
+        if (prec != EDSNET_PREC_FP32) {
+            // the x16 planes are dead after step 1: reuse the front of that region for merged (R x 512)
+            rc = edsnet_split_f16(F(L.merged), ws + L.x16, R, kInner, stream);
+            if (rc) return rc;
+            merged16 = ws + L.x16;
+        }
+        rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
+                           kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
+        if (rc) return rc;
     }
-    rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
-                       kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
-    if (rc) return rc;
     // 4. LayerNorm(1024) -> fc1                                                 (dsnet.py:106)
     const void* yn16 = nullptr;
     {
@@ -464,6 +501,7 @@ int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
     // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add two operand splits (x,
     // merged) and run the value convolution as its own kernel
+    if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 9;
     return cfg->precision == EDSNET_PREC_FP32 ? 11 : 14;
 }
 

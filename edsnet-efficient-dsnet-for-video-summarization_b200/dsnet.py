@@ -54,6 +54,23 @@ class NystromAttention(nn.Module):
                            "(the attention block is fused into the scoring kernels)")
 
 
+class AttentionExtractor(nn.Module):
+    """Parameter container with the layout of the reference's full multi-head attention base
+    (src/modules/models.py:29-74: bias-free Q / K / V / fc projections).  BASELINE.json config 4 only."""
+
+    def __init__(self, num_head: int = 8, num_feature: int = 1024):
+        super().__init__()
+        self.num_head = num_head
+        self.d_k = num_feature // num_head
+        self.Q = nn.Linear(num_feature, num_feature, bias=False)
+        self.K = nn.Linear(num_feature, num_feature, bias=False)
+        self.V = nn.Linear(num_feature, num_feature, bias=False)
+        self.fc = nn.Sequential(nn.Linear(num_feature, num_feature, bias=False), nn.Dropout(0.5))
+
+    def forward(self, *inputs):  # pragma: no cover - guarded surface
+        raise RuntimeError("edsnet_b200.AttentionExtractor only holds parameters; call DSNet.forward")
+
+
 class DSNet(nn.Module):
     """`DSNet(base_model, num_feature, num_hidden, anchor_scales, num_head, fc_depth=5, orientation='paper',
     pooling_type='fft')` -- reference signature (dsnet.py:66-67).  Accelerated configuration only:
@@ -71,8 +88,9 @@ class DSNet(nn.Module):
         if type(anchor_scales) == int:                       # dsnet.py:69-70
             anchor_scales = [anchor_scales]
         anchor_scales = [int(s) for s in anchor_scales]
-        if base_model != "nystromformer":
-            raise ValueError(f"edsnet_b200 accelerates base_model='nystromformer' only, got {base_model!r}")
+        if base_model not in _capi.BASE_MODELS:
+            raise ValueError(f"edsnet_b200 accelerates base_model='nystromformer' (and 'attention' for the "
+                             f"comparison config) only, got {base_model!r}")
         if pooling_type != "roi":
             raise ValueError(f"edsnet_b200 accelerates pooling_type='roi' only, got {pooling_type!r}")
         if (num_feature, num_hidden, num_head) != (NUM_FEATURE, NUM_HIDDEN, NUM_HEAD):
@@ -85,8 +103,11 @@ class DSNet(nn.Module):
         self.pooling_type = pooling_type
         self.fc_depth = int(fc_depth)
         self.precision = precision
-        self.base_model = NystromAttention(dim=num_feature, dim_head=DIM_HEAD, heads=num_head, num_landmarks=64,
-                                           pinv_iterations=6, residual=True, residual_conv_kernel=33)
+        if base_model == "attention":
+            self.base_model = AttentionExtractor(num_head, num_feature)
+        else:
+            self.base_model = NystromAttention(dim=num_feature, dim_head=DIM_HEAD, heads=num_head, num_landmarks=64,
+                                               pinv_iterations=6, residual=True, residual_conv_kernel=33)
         self.layer_norm = nn.LayerNorm(num_feature)
         self.fc1 = nn.Linear(num_feature, num_hidden)
         self.fc_block = nn.Sequential(nn.Linear(num_hidden, num_hidden), nn.ReLU(), nn.Dropout(0.5),
@@ -99,47 +120,60 @@ class DSNet(nn.Module):
         self._workspace = None
 
     # ------------------------------------------------------------------ weights / workspace
-    def _param_list(self):
+    def _named_weights(self):
+        """edsnet_weights field -> parameter (fp32 tensors in the reference's state-dict layout)."""
+        w = {"ln_w": self.layer_norm.weight, "ln_b": self.layer_norm.bias, "fc1_w": self.fc1.weight,
+             "fc1_b": self.fc1.bias, "fcb_w": self.fc_block[0].weight, "fcb_b": self.fc_block[0].bias,
+             "fcb_ln_w": self.fc_block[3].weight, "fcb_ln_b": self.fc_block[3].bias,
+             "cls_w": self.fc_cls[0].weight, "cls_b": self.fc_cls[0].bias, "loc_w": self.fc_loc[0].weight,
+             "loc_b": self.fc_loc[0].bias}
         bm = self.base_model
-        return [bm.to_qkv.weight, bm.to_out[0].weight, bm.to_out[0].bias, bm.res_conv.weight,
-                self.layer_norm.weight, self.layer_norm.bias, self.fc1.weight, self.fc1.bias,
-                self.fc_block[0].weight, self.fc_block[0].bias, self.fc_block[3].weight, self.fc_block[3].bias,
-                self.fc_cls[0].weight, self.fc_cls[0].bias, self.fc_loc[0].weight, self.fc_loc[0].bias]
+        if self.base_model_type == "attention":
+            w.update(Q=bm.Q.weight, K=bm.K.weight, V=bm.V.weight, mha_fc_w=bm.fc[0].weight)
+        else:
+            w.update(to_qkv_w=bm.to_qkv.weight, to_out_w=bm.to_out[0].weight, to_out_b=bm.to_out[0].bias,
+                     res_conv_w=bm.res_conv.weight)
+        return w
 
     def _config(self) -> _capi.Config:
         # dsnet.py:113-115: an odd scale makes the reference's .view() raise RuntimeError; same surface here
         for s in self.anchor_scales:
             if s % 2:
                 raise RuntimeError(f"odd anchor scale {s}: shape mismatch in view (reference dsnet.py:114 fails too)")
-        return _capi.make_config(self.anchor_scales, self.fc_depth, _capi.PRECISIONS[self.precision])
+        return _capi.make_config(self.anchor_scales, self.fc_depth, _capi.PRECISIONS[self.precision],
+                                 _capi.BASE_MODELS[self.base_model_type])
 
     def _weights(self, device, stream: int) -> _capi.Weights:
-        params = self._param_list()
-        key = (self.precision, str(device)) + tuple((p.data_ptr(), p._version) for p in params)
+        named = self._named_weights()
+        key = (self.precision, str(device)) + tuple((n, p.data_ptr(), p._version) for n, p in named.items())
         if self._wkey == key:
             return self._wcache[0]
         keep = []
         w = _capi.Weights()
-        for name, p in zip(_capi.WEIGHT_FIELDS[:16], params):
+        tensors = {}
+        for name, p in named.items():
             if p.device != device:
                 raise RuntimeError(f"parameter {name} is on {p.device}, input is on {device}")
-            t = p.detach()
-            if t.dtype != torch.float32:
+            if p.dtype != torch.float32:
                 raise RuntimeError("edsnet_b200 parameters must be float32")
-            t = t.contiguous()
+            tensors[name] = p.detach().contiguous()
+        if self.base_model_type == "attention":
+            tensors["mha_qkv_w"] = torch.cat([tensors.pop("Q"), tensors.pop("K"), tensors.pop("V")], dim=0).contiguous()
+        for name, t in tensors.items():
             keep.append(t)
             setattr(w, name, t.data_ptr())
         if self.precision != "fp32":
             lib = _capi.lib()
-            for name, p in (("to_qkv_w16", params[0]), ("to_out_w16", params[1]), ("fc1_w16", params[6]),
-                            ("fcb_w16", params[8])):
-                src = p.detach().contiguous()
+            planes_of = (("mha_qkv_w16", "mha_qkv_w"), ("mha_fc_w16", "mha_fc_w")) \
+                if self.base_model_type == "attention" else (("to_qkv_w16", "to_qkv_w"), ("to_out_w16", "to_out_w"))
+            for field, src_name in planes_of + (("fc1_w16", "fc1_w"), ("fcb_w16", "fcb_w")):
+                src = tensors[src_name]
                 planes = torch.empty(lib.edsnet_split_f16_bytes(src.shape[0], src.shape[1]), dtype=torch.uint8,
                                      device=device)
                 _capi.check(lib.edsnet_split_f16(src.data_ptr(), planes.data_ptr(), src.shape[0], src.shape[1],
                                                  stream))
-                keep += [src, planes]
-                setattr(w, name, planes.data_ptr())
+                keep.append(planes)
+                setattr(w, field, planes.data_ptr())
         self._wcache = (w, keep)
         self._wkey = key
         return w

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 2
+#define EDSNET_ABI_VERSION 3
 
 enum {
     EDSNET_OK = 0,
@@ -43,6 +43,12 @@ enum {
     EDSNET_PREC_FP16 = 2       /* tcgen05 fp16 single pass, fp32 accumulate           (~ 1e-3 vs reference)  */
 };
 
+/* base model in front of the shared scoring tail (modules/models.py:118-147) */
+enum {
+    EDSNET_BASE_NYSTROM = 0,   /* NystromAttention, the accelerated hot path                                      */
+    EDSNET_BASE_ATTENTION = 1  /* full multi-head attention (AttentionExtractor), comparison config 4 only        */
+};
+
 #define EDSNET_MAX_SCALES 8
 
 /* Model hyper-parameters that are not baked in.  Baked in (reference call sites): num_feature 1024, num_hidden
@@ -52,6 +58,7 @@ typedef struct {
     int32_t n_scales;                         /* len(anchor_scales), 1..8                              */
     int32_t scales[EDSNET_MAX_SCALES];        /* even, 2..128 (odd scales crash the reference's .view) */
     int32_t precision;                        /* EDSNET_PREC_*                                         */
+    int32_t base_model;                       /* EDSNET_BASE_*                                         */
 } edsnet_config;
 
 /* Weights in the reference's own state-dict layout (row-major (out, in) as nn.Linear stores them), fp32 [dev].
@@ -79,6 +86,11 @@ typedef struct {
     const void* to_out_w16;    /* planes of (1024, 512)  */
     const void* fc1_w16;       /* planes of (128, 1024)  */
     const void* fcb_w16;       /* planes of (128, 128)   */
+    /* EDSNET_BASE_ATTENTION only (modules/models.py:33-44, all bias-free): */
+    const float* mha_qkv_w;    /* rows 0..1023 base_model.Q.weight, 1024..2047 K.weight, 2048..3071 V.weight (3072, 1024) */
+    const float* mha_fc_w;     /* base_model.fc.0.weight        (1024, 1024) */
+    const void* mha_qkv_w16;   /* planes of (3072, 1024) */
+    const void* mha_fc_w16;    /* planes of (1024, 1024) */
 } edsnet_weights;
 
 /* A packed batch of videos.  All arrays [dev], int32.  Tile tables are built by the host (see
@@ -105,12 +117,13 @@ typedef struct {
     size_t a3v;        /* softmax(q_land k^T) v                                       */
     size_t zmat;       /* pseudo-inverse of attn2                                     */
     size_t wmat;       /* zmat a3v                                                    */
-    size_t merged;     /* [rows][512] head-merged attention output + value conv       */
+    size_t merged;     /* [rows][512] head-merged attention output + value conv ([rows][1024] for the attention base) */
     size_t y;          /* [rows][1024] to_out + bias + x                              */
     size_t yn;         /* [rows][1024] LayerNorm(y)           (aliases qkv)           */
     size_t u0;         /* [rows][128] fc1 output                                      */
     size_t u1;         /* [rows][128] after the fc stack                              */
     size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
+    size_t zeros;      /* [1024] zero bias (attention base: its projections have no bias) */
     size_t total;
 } edsnet_workspace_layout;
 

@@ -170,6 +170,40 @@ def nystrom_attention(x: torch.Tensor, p: Dict[str, torch.Tensor], heads: int = 
 
 
 # --------------------------------------------------------------------------
+# Full multi-head attention base (config 4 only)  (modules/models.py:12-74)
+# --------------------------------------------------------------------------
+
+MHA_PARAM_SHAPES = {
+    "base_model.Q.weight": (1024, 1024), "base_model.K.weight": (1024, 1024), "base_model.V.weight": (1024, 1024),
+    "base_model.fc.0.weight": (1024, 1024),
+}
+
+
+def synth_params_mha(seed: int, init: str = "default") -> Dict[str, torch.Tensor]:
+    """Weights of DSNet(base_model='attention'): the shared tail of ``synth_params`` plus the four bias-free
+    1024 x 1024 projections of modules/models.py:33-44."""
+    p = {k: v for k, v in synth_params(seed, init).items() if not k.startswith("base_model.")}
+    g = torch.Generator().manual_seed(seed + 7919)
+    for name, (fo, fi) in MHA_PARAM_SHAPES.items():
+        b = math.sqrt(2.0) * math.sqrt(6.0 / (fi + fo)) if init == "xavier" else 1.0 / math.sqrt(fi)
+        p[name] = ((torch.rand((fo, fi), generator=g) * 2 - 1) * b).float().contiguous()
+    return p
+
+
+def mha_attention(x: torch.Tensor, p: Dict[str, torch.Tensor], heads: int = HEADS) -> torch.Tensor:
+    """x: (T, F) -> (T, F).  modules/models.py:46-65 in eval mode (both Dropout(0.5) are the identity):
+    Q/K/V = x W^T, heads split along the feature axis (d_k = F / heads), softmax(Q K^T / sqrt(d_k)) V,
+    heads merged, bias-free output projection."""
+    T, Fdim = x.shape
+    dk = Fdim // heads
+    q, k, v = (x @ p[f"base_model.{n}.weight"].t() for n in ("Q", "K", "V"))
+    q, k, v = (t.reshape(T, heads, dk).permute(1, 0, 2) for t in (q, k, v))          # (h, T, dk)
+    attn = torch.softmax((q @ k.transpose(1, 2)) / math.sqrt(dk), dim=-1)
+    y = (attn @ v).permute(1, 0, 2).reshape(T, Fdim)
+    return y @ p["base_model.fc.0.weight"].t()
+
+
+# --------------------------------------------------------------------------
 # DSNet forward (anchor_based/dsnet.py:100-115)
 # --------------------------------------------------------------------------
 
@@ -207,11 +241,14 @@ def roi_pool_direct(u: torch.Tensor, scales: Sequence[int]) -> torch.Tensor:
 
 
 def dsnet_forward(x: torch.Tensor, p: Dict[str, torch.Tensor], scales: Sequence[int],
-                  fc_depth: int = 5, heads: int = HEADS, stages: dict | None = None
+                  fc_depth: int = 5, heads: int = HEADS, stages: dict | None = None, base: str = "nystromformer"
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
     """x: (T, F) float -> pred_cls (T, S), pred_loc (T, S, 2).  Eval mode
     (Dropout is the identity).  anchor_based/dsnet.py:100-115."""
-    y = nystrom_attention(x, p, heads, stages) + x
+    if base == "attention":
+        y = mha_attention(x, p, heads) + x
+    else:
+        y = nystrom_attention(x, p, heads, stages) + x
     u = layer_norm(y, p["layer_norm.weight"], p["layer_norm.bias"])
     u = u @ p["fc1.weight"].t() + p["fc1.bias"]
     for _ in range(fc_depth):          # ONE shared block applied fc_depth times (dsnet.py:91-96)

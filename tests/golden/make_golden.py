@@ -126,6 +126,27 @@ def main():
     out["forward_cases"] = np.asarray([c[0] for c in FORWARD_CASES])
     np.savez_compressed(os.path.join(ROOT, "tests/golden/forward_golden.npz"), **out)
 
+    # ---- full multi-head attention base (config 4), reference DSNet(base_model='attention') ----
+    mha = {}
+    mha_cases = [("mha_T300_s4_8", 300, [4, 8], 5, "xavier", 21, 22), ("mha_T77_s12", 77, [12], 3, "default", 23, 24),
+                 ("mha_T2048_s4_8_16_32", 2048, [4, 8, 16, 32], 5, "xavier", 25, 26)]
+    for name, T, scales, depth, init, xs, ws in mha_cases:
+        x = orc.synth_features(T, xs)
+        p = orc.synth_params_mha(ws, init)
+        model = DSNet("attention", 1024, 128, list(scales), 8, fc_depth=depth, orientation=None,
+                      pooling_type="roi").eval()
+        model.load_state_dict(ref_state_dict(p, depth), strict=True)
+        with torch.no_grad():
+            cls, loc = model(x[None])
+        rec = dict(T=T, scales=np.asarray(scales), fc_depth=depth, x_seed=xs, w_seed=ws, x_sha=sha(x.numpy()),
+                   w_sha=params_sha(p), pred_cls=cls.numpy(), pred_loc=loc.numpy())
+        for k, v in rec.items():
+            mha[f"{name}/{k}"] = np.asarray(v)
+        mha[f"{name}/init"] = np.asarray(init)
+        print(name, "done")
+    mha["forward_cases"] = np.asarray([c[0] for c in mha_cases])
+    np.savez_compressed(os.path.join(ROOT, "tests/golden/forward_mha_golden.npz"), **mha)
+
     # ---- stand-alone decode / NMS / summary vectors from the reference's host helpers ----
     rng = np.random.default_rng(2024)
     dn = {}

@@ -442,3 +442,45 @@ def test_training_step_single_gpu():
     with torch.no_grad():
         c1, _ = model(seqs[0][None])
     assert torch.isfinite(c1).all()
+
+
+# ------------------------------------------------------------------------------------------------ config 4: full MHA base
+MHA = load_npz("forward_mha_golden.npz")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("name", list(MHA["forward_cases"]))
+def test_mha_base_matches_reference_golden(name, precision):
+    """DSNet(base_model='attention') (modules/models.py:12-74), the T=2048 comparison config: flash attention without
+    the (8, T, T) score tensor the reference materialises."""
+    g = {k.split("/", 1)[1]: MHA[k] for k in MHA.files if k.startswith(name + "/")}
+    x = orc.synth_features(int(g["T"]), int(g["x_seed"]))
+    p = orc.synth_params_mha(int(g["w_seed"]), str(g["init"]))
+    scales = [int(s) for s in g["scales"]]
+    model = make_model(p, scales, int(g["fc_depth"]), precision, DEV, base="attention")
+    with torch.no_grad():
+        cls, loc = model(x[None].to(DEV))
+    _no_tc_timeout()
+    e = (orc.rel_l2(cls.cpu().numpy(), g["pred_cls"]), orc.rel_l2(loc.cpu().numpy(), g["pred_loc"]))
+    print(name, precision, e)
+    assert max(e) < TOL[precision], e
+
+
+def test_mha_base_packed_and_gradients():
+    p = orc.synth_params_mha(61, "xavier")
+    scales = [4, 8]
+    model = make_model(p, scales, 3, "fp32", DEV, base="attention")
+    lengths = [50, 130, 64]
+    xs = [orc.synth_features(t, 700 + i) for i, t in enumerate(lengths)]
+    with torch.no_grad():
+        cp, lp = model.forward_packed(torch.cat(xs).to(DEV), lengths)
+    o = 0
+    for x, t in zip(xs, lengths):
+        with torch.no_grad():
+            rc, rl = orc.dsnet_forward(x, p, scales, 3, base="attention")
+        assert orc.rel_l2(cp[o:o + t].cpu().numpy(), rc.numpy()) < 1e-5
+        assert orc.rel_l2(lp[o:o + t].cpu().numpy(), rl.numpy()) < 1e-5
+        o += t
+    cls, loc = model(xs[0][None].to(DEV))                      # eval + grad enabled: kernel values, torch-graph gradients
+    (cls.sum() + loc.sum()).backward()
+    assert model.base_model.Q.weight.grad is not None and torch.isfinite(model.base_model.Q.weight.grad).all()

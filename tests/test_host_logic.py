@@ -102,7 +102,7 @@ def test_module_surface_matches_reference_state_dict():
 
 def test_unsupported_configurations_raise():
     with pytest.raises(ValueError):
-        DSNet("attention", 1024, 128, [4], 8, pooling_type="roi")
+        DSNet("lstm", 1024, 128, [4], 8, pooling_type="roi")
     with pytest.raises(ValueError):
         DSNet("nystromformer", 1024, 128, [4], 8)                   # default pooling_type='fft'
     with pytest.raises(ValueError):
@@ -121,3 +121,11 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|oracle\.", src, re.M), f
+
+
+def test_attention_base_state_dict_matches_reference_layout():
+    p = orc.synth_params_mha(3, "default")
+    m = DSNet("attention", 1024, 128, [4, 8], 8, fc_depth=3, pooling_type="roi")
+    want = ref_state_dict(p, 3)
+    assert set(m.state_dict()) == set(want)
+    m.load_state_dict(want, strict=True)

@@ -45,9 +45,9 @@ def ref_state_dict(p, fc_depth):
     return sd
 
 
-def make_model(p, scales, fc_depth, precision, device=None):
+def make_model(p, scales, fc_depth, precision, device=None, base="nystromformer"):
     from edsnet_b200 import DSNet
-    m = DSNet("nystromformer", 1024, 128, list(scales), 8, fc_depth=fc_depth, orientation=None,
+    m = DSNet(base, 1024, 128, list(scales), 8, fc_depth=fc_depth, orientation=None,
               pooling_type="roi", precision=precision).eval()
     m.load_state_dict(ref_state_dict(p, fc_depth), strict=True)
     if device is not None:
