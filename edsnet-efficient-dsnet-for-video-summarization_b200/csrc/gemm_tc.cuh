@@ -10,8 +10,8 @@
 // accumulators in TMEM (4 x 128 columns = all 512): the hi.hi products rotate over three of them by K block (<= 24
 // steps each for K = 1024), the two small cross terms go to the fourth, and the epilogue adds the four in fp32 with
 // round-to-nearest.
-// Persistent CTAs, 128 x 128 output tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 =
-// epilogue (TMEM -> registers -> global).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
+// Persistent CTAs, 128 x 128 output tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..9 =
+// epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, 64 columns each).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
 // by full/empty mbarriers; operands land in shared memory in the 128B (BK=64) / 64B (BK=32) swizzled K-major
 // layout that both TMA and the UMMA shared-memory descriptor understand; the accumulator lives in TMEM.
 // Every mbarrier wait is bounded: on timeout a global flag is raised and the kernel drains instead of hanging.
@@ -134,11 +134,11 @@ struct TcCfg {
     static constexpr int kAccs = PASSES == 3 ? 4 : 1;      // TMEM accumulators per tile (see the header comment)
     static constexpr int kBufs = PASSES == 3 ? 1 : 2;      // tiles in flight in TMEM
     static constexpr int kTmemCols = kAccs * kBufs * BN;
-    static_assert(BN == 128, "one thread keeps a 128-column output row in registers");
+    static_assert(BN == 128, "an epilogue thread keeps half a 128-column output row in registers");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
     static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static constexpr int kThreads = 192;
+    static constexpr int kThreads = 320;                   // TMA warp, MMA warp, 8 epilogue warps
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); CTA b owns tiles b, b + grid, ...  (n fastest, so the CTAs that run
@@ -147,7 +147,7 @@ struct TcCfg {
 // whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
 // residual and stores -- the next tile's MMAs overlap those global accesses.
 template <int BN, int BK, int STAGES, int PASSES, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
     using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
@@ -175,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -248,8 +248,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else {
-        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> one output row ----
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> 64 columns of one output row ----
         const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;                       // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127
         const int n_main = PASSES == 3 ? (nk < 3 ? nk : 3) : 1;     // accumulators that received hi.hi products
         bool ok = true;
         int t = 0;
@@ -260,10 +261,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int row = m0 + quarter * 32 + lane;
             ok = mbar_wait(tfull_bar(buf), tph);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16);
-            float v[BN];
+            const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) +
+                                (uint32_t)(chalf * 64);
+            const int nc0 = n0 + chalf * 64;                         // first global column of this thread
+            float v[64];
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = 0; c0 < 64; c0 += 16) {
                 uint32_t r0[16];
                 tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
                 if (PASSES == 3) {
@@ -294,47 +297,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (row < M && EPI == EPI_QKV_PLANES) {
                 // q|k|v as operand planes: per (row, head) power-of-two scale, hi = fp16(x 2^s), lo = fp16(x 2^s - hi)
                 const float ra = __ldg(ep.a_scale + row);
-                __half* hi_row = reinterpret_cast<__half*>(C) + (size_t)row * N + n0;
+                __half* hi_row = reinterpret_cast<__half*>(C) + (size_t)row * N + nc0;
                 __half* lo_row = hi_row + (size_t)M * N;
+                float mx = 0.f;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float mx = 0.f;
+                for (int j = 0; j < 64; j += 4) {
+                    const float4 rb = ldg4(ep.b_scale + nc0 + j);
+                    v[j] *= ra * rb.x; v[j + 1] *= ra * rb.y; v[j + 2] *= ra * rb.z; v[j + 3] *= ra * rb.w;
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 1])), fmaxf(fabsf(v[j + 2]), fabsf(v[j + 3]))));
+                }
+                int e = 0;
+                if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+                e = max(-100, min(100, e));
+                const float sc = ldexpf(1.f, e);
+                const int slot = nc0 >> 6;                                  // part * 8 + head
+                ep.aux[(size_t)row * 24 + slot] = ldexpf(1.f, -e) * (slot < 8 ? 0.125f : 1.f);
 #pragma unroll
-                    for (int j = 0; j < 64; j += 4) {
-                        const float4 rb = ldg4(ep.b_scale + n0 + half * 64 + j);
-                        v[half * 64 + j] *= ra * rb.x; v[half * 64 + j + 1] *= ra * rb.y;
-                        v[half * 64 + j + 2] *= ra * rb.z; v[half * 64 + j + 3] *= ra * rb.w;
-                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[half * 64 + j]), fabsf(v[half * 64 + j + 1])),
-                                             fmaxf(fabsf(v[half * 64 + j + 2]), fabsf(v[half * 64 + j + 3]))));
+                for (int c = 0; c < 8; ++c) {
+                    __half2 hh[4], ll[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float v0 = v[c * 8 + 2 * q] * sc, v1 = v[c * 8 + 2 * q + 1] * sc;
+                        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                        hh[q] = __halves2half2(h0, h1);
+                        ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
+                                               __float2half_rn(v1 - __half2float(h1)));
                     }
-                    int e = 0;
-                    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
-                    e = max(-100, min(100, e));
-                    const float sc = ldexpf(1.f, e);
-                    const int slot = (n0 >> 6) + half;                      // part * 8 + head
-                    ep.aux[(size_t)row * 24 + slot] = ldexpf(1.f, -e) * (slot < 8 ? 0.125f : 1.f);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        __half2 hh[4], ll[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float v0 = v[half * 64 + c * 8 + 2 * q] * sc, v1 = v[half * 64 + c * 8 + 2 * q + 1] * sc;
-                            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-                            hh[q] = __halves2half2(h0, h1);
-                            ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
-                                                   __float2half_rn(v1 - __half2float(h1)));
-                        }
-                        *reinterpret_cast<uint4*>(hi_row + half * 64 + c * 8) = *reinterpret_cast<uint4*>(hh);
-                        *reinterpret_cast<uint4*>(lo_row + half * 64 + c * 8) = *reinterpret_cast<uint4*>(ll);
-                    }
+                    *reinterpret_cast<uint4*>(hi_row + c * 8) = *reinterpret_cast<uint4*>(hh);
+                    *reinterpret_cast<uint4*>(lo_row + c * 8) = *reinterpret_cast<uint4*>(ll);
                 }
             } else if (row < M) {
-                float* crow = C + (size_t)row * N + n0;
-                const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + n0 : nullptr;
+                float* crow = C + (size_t)row * N + nc0;
+                const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + nc0 : nullptr;
                 const float ra = __ldg(ep.a_scale + row);
 #pragma unroll
-                for (int j = 0; j < BN; j += 4) {
-                    const int c = n0 + j;
+                for (int j = 0; j < 64; j += 4) {
+                    const int c = nc0 + j;
                     const float4 rb = ldg4(ep.b_scale + c);
                     float4 o = make_float4(v[j] * (ra * rb.x), v[j + 1] * (ra * rb.y), v[j + 2] * (ra * rb.z),
                                            v[j + 3] * (ra * rb.w));
