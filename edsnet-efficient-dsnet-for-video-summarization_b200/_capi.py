@@ -39,7 +39,7 @@ class Weights(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_videos", C.c_int32), ("total_rows", C.c_int32), ("max_rows", C.c_int32),
                 ("cu_rows", C.c_void_p), ("tiles64", C.c_void_p), ("n_tiles64", C.c_int32),
-                ("tiles128", C.c_void_p), ("n_tiles128", C.c_int32)]
+                ("tiles128", C.c_void_p), ("n_tiles128", C.c_int32), ("cu_rows_host", C.c_void_p)]
 
 
 LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",

@@ -75,7 +75,8 @@ __device__ __forceinline__ bool nms_suppresses(int2 a, int2 b, double thresh, do
 
 __global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(const float* __restrict__ scores, const int* __restrict__ boxes_i32, const int* __restrict__ cu_rows,
-           int S, double thresh, int smem_cap, const long long* __restrict__ scratch_off, unsigned char* scratch,
+           int S, double thresh, int smem_cap, int skip_large, const long long* __restrict__ scratch_off,
+           unsigned char* scratch,
            int* keep_count, int* keep_idx, float* keep_scores, int* keep_boxes) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ int s_nvalid, s_kept;
@@ -89,6 +90,7 @@ nms_kernel(const float* __restrict__ scores, const int* __restrict__ boxes_i32, 
     unsigned long long* keys;
     int2* sbox;
     int2* kept;
+    if (P > smem_cap && skip_large) return;       // handled by the multi-CTA path (nms_large.cuh)
     if (P <= smem_cap) {
         keys = reinterpret_cast<unsigned long long*>(nms_smem);
         sbox = reinterpret_cast<int2*>(nms_smem + (size_t)smem_cap * 8);

@@ -15,6 +15,7 @@
 #include "nystrom.cuh"
 #include "tail.cuh"
 #include "decode_nms.cuh"
+#include "nms_large.cuh"
 
 namespace {
 
@@ -87,6 +88,8 @@ int check_batch(const edsnet_batch* b) {
     if (!b) return fail(EDSNET_E_ARG, "batch is NULL");
     if (b->n_videos < 1 || b->total_rows < 1 || b->max_rows < 1) return fail(EDSNET_E_ARG, "empty batch");
     if (!b->cu_rows || !b->tiles64 || !b->tiles128) return fail(EDSNET_E_ARG, "batch tables are NULL");
+    if (b->cu_rows_host && (b->cu_rows_host[0] != 0 || b->cu_rows_host[b->n_videos] != b->total_rows))
+        return fail(EDSNET_E_ARG, "cu_rows_host does not describe this batch");
     if (b->n_videos > 65535) return fail(EDSNET_E_ARG, "at most 65535 videos per call");
     return EDSNET_OK;
 }
@@ -532,8 +535,9 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     if (!pred_cls || !pred_loc || !boxes_i32 || !keep_count || !keep_idx || !keep_scores || !keep_boxes)
         return fail(EDSNET_E_ARG, "decode_nms: NULL operand");
     const long long max_n = (long long)batch->max_rows * cfg->n_scales;
-    if (max_n > kNmsSmemCap && (!nms_scratch_off || !nms_scratch))
+    if (max_n > kNmsSmemCap && (!nms_scratch || (!nms_scratch_off && !batch->cu_rows_host)))
         return fail(EDSNET_E_ARG, "decode_nms: a video has more than 4096 anchors, scratch is required");
+    const int skip_large = (max_n > kNmsSmemCap && batch->cu_rows_host) ? 1 : 0;
     if (max_n > (1ll << 30)) return fail(EDSNET_E_UNSUPPORTED, "decode_nms: video too long");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int halo = 0;
@@ -556,10 +560,27 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     {
         StageScope scope(ST_NMS, st);
         nms_kernel<<<batch->n_videos, kNmsThreads, nms_smem, st>>>(
-            pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh, cap,
+            pred_cls, boxes_i32, batch->cu_rows, cfg->n_scales, nms_thresh, cap, skip_large,
             reinterpret_cast<const long long*>(nms_scratch_off), static_cast<unsigned char*>(nms_scratch), keep_count,
             keep_idx, keep_scores, keep_boxes);
         CU_CHECK(cudaGetLastError(), "nms_kernel");
+        if (skip_large) {
+            // videos with more than 4096 anchors: multi-CTA sort + blocked suppression, one video after the other;
+            // scratch offsets follow the same rule as the caller's table (32 bytes per anchor, power of two)
+            size_t off = 0;
+            for (int v = 0; v < batch->n_videos; ++v) {
+                const long long row0 = batch->cu_rows_host[v];
+                const long long n = (long long)(batch->cu_rows_host[v + 1] - row0) * cfg->n_scales;
+                if (n <= kNmsSmemCap) continue;
+                size_t P = kNmsTile;
+                while ((long long)P < n) P <<= 1;
+                const size_t g0 = (size_t)row0 * cfg->n_scales;
+                CU_CHECK(launch_nms_large(pred_cls + g0, boxes_i32 + 2 * g0, (int)n, nms_thresh,
+                                          static_cast<unsigned char*>(nms_scratch) + off, keep_count + v, keep_idx + g0,
+                                          keep_scores + g0, keep_boxes + 2 * g0, st), "nms_large");
+                off += 32 * P;
+            }
+        }
     }
     return EDSNET_OK;
 }

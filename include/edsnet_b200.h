@@ -93,7 +93,7 @@ typedef struct {
     const void* mha_fc_w16;    /* planes of (1024, 1024) */
 } edsnet_weights;
 
-/* A packed batch of videos.  All arrays [dev], int32.  Tile tables are built by the host (see
+/* A packed batch of videos.  Arrays [dev] int32 unless noted.  Tile tables are built by the host (see
  * edsnet_b200/plan.py): one {video, first_row} pair per 64-row (attention) / 128-row (pooling) tile of a video. */
 typedef struct {
     int32_t n_videos;
@@ -104,6 +104,8 @@ typedef struct {
     int32_t n_tiles64;
     const int32_t* tiles128;   /* [n_tiles128][2] */
     int32_t n_tiles128;
+    const int32_t* cu_rows_host; /* optional HOST copy of cu_rows: lets edsnet_decode_nms spread videos with more than
+                                  * 4096 anchors over the whole GPU (without it they run on one CTA each) */
 } edsnet_batch;
 
 /* Byte offsets of the intermediates inside the forward workspace (for tests / profiling). */
@@ -146,8 +148,9 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
  *   keep_count [dev][n_videos]; keep_idx / keep_scores / keep_boxes are [dev] arrays of total_rows*S entries,
  *   the kept proposals of video v (descending score) start at entry cu_rows[v]*S; keep_idx is the flat
  *   anchor index t*S+s inside the video.
- *   Videos with more than 4096 anchors need scratch: nms_scratch_off [dev][n_videos] byte offsets into
- *   nms_scratch (24 bytes per anchor rounded up to a power of two); both may be NULL otherwise. */
+ *   Videos with more than 4096 anchors need scratch: 32 bytes per anchor, anchors rounded up to a power of two,
+ *   video after video in batch order; nms_scratch_off [dev][n_videos] are those byte offsets (only read when
+ *   batch->cu_rows_host is NULL).  Both may be NULL when no video is that long. */
 int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls,
                       const float* pred_loc, double nms_thresh, float* boxes_f32, int32_t* boxes_i32,
                       int32_t* keep_count, int32_t* keep_idx, float* keep_scores, int32_t* keep_boxes,
