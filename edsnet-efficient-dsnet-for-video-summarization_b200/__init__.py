@@ -11,5 +11,6 @@ from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
 from .dsnet import DSNet, NystromAttention, AttentionExtractor                      # noqa: F401
 from .pipeline import ScoringPipeline                            # noqa: F401
 from . import training                                           # noqa: F401
+from .summary import ShotPlan, keyshot_summaries, split_summaries  # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

@@ -50,6 +50,10 @@ class WorkspaceLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in LAYOUT_FIELDS]
 
 
+class Shots(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cu_seg", "cps", "nfps", "picks", "cu_frames", "capacity", "gcd", "dp_off")]
+
+
 # every symbol include/edsnet_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -60,6 +64,8 @@ SYMBOLS = {
                                  C.c_size_t, _P]),
     "edsnet_decode_nms": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, C.c_double, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P]),
+    "edsnet_keyshot_summary": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), C.POINTER(Shots), _P, _P, _P, _P, _P, _P,
+                                         _P, _P, _P, _P]),
     "edsnet_decode_boxes": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_forward_launches": (C.c_int, [C.POINTER(Config)]),
     "edsnet_split_f16_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

@@ -16,6 +16,7 @@
 #include "tail.cuh"
 #include "decode_nms.cuh"
 #include "nms_large.cuh"
+#include "summary.cuh"
 
 namespace {
 
@@ -498,6 +499,38 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     if (rc) return rc;
     // 6. ROI pooling + heads                                                    (dsnet.py:110-115)
     return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st);
+}
+
+int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, const edsnet_shots* shots,
+                           const int32_t* keep_count, const float* keep_scores, const int32_t* keep_boxes,
+                           float* pos_scores, float* frame_scores, int32_t* seg_scores, uint8_t* picked,
+                           uint8_t* summary, void* dp_scratch, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!shots || !shots->cu_seg || !shots->cps || !shots->nfps || !shots->picks || !shots->cu_frames ||
+        !shots->capacity || !shots->gcd || !shots->dp_off)
+        return fail(EDSNET_E_ARG, "keyshot_summary: shot tables are NULL");
+    if (!keep_count || !keep_scores || !keep_boxes || !pos_scores || !frame_scores || !seg_scores || !picked ||
+        !summary || !dp_scratch)
+        return fail(EDSNET_E_ARG, "keyshot_summary: NULL operand");
+    ShotTables sh{shots->cu_seg, shots->cps, shots->nfps, shots->picks,
+                  reinterpret_cast<const long long*>(shots->cu_frames), shots->capacity, shots->gcd,
+                  reinterpret_cast<const long long*>(shots->dp_off)};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool stack_set = false;
+    if (!stack_set) {                     // numpy_pairwise_sum recurses (depth <= log2(n / 128) + 1)
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < 4096)
+            CU_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 4096), "stack size");
+        stack_set = true;
+    }
+    keyshot_summary_kernel<<<batch->n_videos, 256, 0, st>>>(batch->cu_rows, cfg->n_scales, sh, keep_count, keep_scores,
+                                                           keep_boxes, pos_scores, frame_scores, seg_scores, picked,
+                                                           summary, static_cast<unsigned char*>(dp_scratch));
+    CU_CHECK(cudaGetLastError(), "keyshot_summary_kernel");
+    return EDSNET_OK;
 }
 
 int edsnet_forward_launches(const edsnet_config* cfg) {

@@ -156,6 +156,28 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
                       int32_t* keep_count, int32_t* keep_idx, float* keep_scores, int32_t* keep_boxes,
                       const int64_t* nms_scratch_off, void* nms_scratch, void* stream);
 
+/* Shot structure of the videos of a batch, for edsnet_keyshot_summary.  All arrays [dev].
+ * dp_scratch layout per video (byte offset dp_off[v]): two int32 rows of (capacity[v] + 1), then
+ * n_seg x ceil((capacity[v] + 1) / 32) uint32 decision words. */
+typedef struct {
+    const int32_t* cu_seg;      /* [n_videos + 1] first shot of every video                                   */
+    const int32_t* cps;         /* [total_seg][2] change points: first / last frame of the shot, inclusive     */
+    const int32_t* nfps;        /* [total_seg] frames per shot (the knapsack weights)                          */
+    const int32_t* picks;       /* [total_rows] frame index of every sub-sampled position, aligned with cu_rows */
+    const int64_t* cu_frames;   /* [n_videos + 1] prefix sum of n_frames                                       */
+    const int32_t* capacity;    /* [n_videos] int(n_frames * 0.15) / gcd[v]                                    */
+    const int32_t* gcd;         /* [n_videos] a common divisor of capacity and all shot weights (1 always works) */
+    const int64_t* dp_off;      /* [n_videos] byte offsets into dp_scratch                                     */
+} edsnet_shots;
+
+/* evaluate.py:29 / infer.py:35: vsumm_helper.bbox2summary (helpers/vsumm_helper.py:101-116, 53-98, 26-45) on the
+ * device, from the kept proposals edsnet_decode_nms wrote.  Outputs: pos_scores [total_rows], frame_scores
+ * [total_frames], seg_scores [total_seg], picked [total_seg] (0/1), summary [total_frames] (0/1). */
+int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, const edsnet_shots* shots,
+                           const int32_t* keep_count, const float* keep_scores, const int32_t* keep_boxes,
+                           float* pos_scores, float* frame_scores, int32_t* seg_scores, uint8_t* picked,
+                           uint8_t* summary, void* dp_scratch, void* stream);
+
 /* decode only (what DSNet.predict returns, dsnet.py:146-153, plus the evaluate.py:26 clip/round):
  * boxes_f32 [dev][total_rows*S][2] (may be NULL), boxes_i32 [dev][total_rows*S][2] (may be NULL). */
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

@@ -484,3 +484,73 @@ def test_mha_base_packed_and_gradients():
     cls, loc = model(xs[0][None].to(DEV))                      # eval + grad enabled: kernel values, torch-graph gradients
     (cls.sum() + loc.sum()).backward()
     assert model.base_model.Q.weight.grad is not None and torch.isfinite(model.base_model.Q.weight.grad).all()
+
+
+# ------------------------------------------------------------------------------------------------ keyshot summary (f-1)
+def _shots_for(T, rng, shot_lo=3, shot_hi=12, rate=15):
+    """Synthetic shot structure shaped like the reference's h5 records (tests/test_train.py:16-45): picks every
+    `rate` frames, contiguous shots covering all frames."""
+    n_frames = T * rate - int(rng.integers(0, rate))
+    bounds = [0]
+    while bounds[-1] < n_frames:
+        bounds.append(min(n_frames, bounds[-1] + int(rng.integers(shot_lo, shot_hi + 1)) * rate // 2))
+    cps = np.stack([bounds[:-1], np.asarray(bounds[1:]) - 1], 1).astype(np.int32)
+    nfps = (cps[:, 1] - cps[:, 0] + 1).astype(np.int32)
+    picks = (np.arange(T) * rate).astype(np.int32)
+    picks = picks[picks < n_frames]
+    assert len(picks) == T
+    return dict(cps=cps, nfps=nfps, picks=picks, n_frames=n_frames)
+
+
+@pytest.mark.parametrize("name", list(DN["cases"]))
+def test_keyshot_summary_matches_reference_golden(name):
+    """The reference's own bbox2summary output (knapsack = the exact DP both sides share) on the reference's kept boxes."""
+    from edsnet_b200 import BatchPlan, ShotPlan, keyshot_summaries, split_summaries
+    T = int(DN[f"{name}/T"])
+    scales = [int(s) for s in DN[f"{name}/scales"]]
+    S = len(scales)
+    model = make_model(orc.synth_params(1, "default"), scales, 5, "fp32", DEV)
+    batch = BatchPlan.build([T]).to(DEV)
+    ks, kb = DN[f"{name}/keep_scores"], DN[f"{name}/keep_boxes"]
+    n = T * S
+    nms = {"keep_count": torch.tensor([len(ks)], dtype=torch.int32, device=DEV),
+           "keep_scores": torch.zeros(n, device=DEV), "keep_boxes": torch.zeros((n, 2), dtype=torch.int32, device=DEV)}
+    nms["keep_scores"][:len(ks)] = torch.from_numpy(ks).to(DEV)
+    nms["keep_boxes"][:len(ks)] = torch.from_numpy(kb).to(DEV)
+    vd = dict(cps=DN[f"{name}/cps"], nfps=DN[f"{name}/nfps"], picks=DN[f"{name}/picks"], n_frames=T * 15)
+    shots = ShotPlan([vd], DEV)
+    out = keyshot_summaries(model, nms, batch, shots)
+    got = split_summaries(out["summary"], shots)[0]
+    assert np.array_equal(np.packbits(got), DN[f"{name}/summary"])
+
+
+def test_keyshot_summary_packed_vs_oracle():
+    """features -> proposals -> summaries for a packed batch, every stage on the device, against the oracle's host
+    restatement fed with the same kept proposals (bit-exact: integer shot scores, same exact knapsack)."""
+    from edsnet_b200 import BatchPlan, ShotPlan, keyshot_summaries, split_summaries
+    rng = np.random.default_rng(5)
+    p = orc.synth_params(71, "xavier")
+    scales = [4, 8, 16, 32]
+    model = make_model(p, scales, 5, "fp16x3", DEV)
+    lengths = [int(t) for t in rng.integers(20, 700, size=12)] + [1, 64]
+    xs = [orc.synth_features(t, 3000 + i) for i, t in enumerate(lengths)]
+    vds = [_shots_for(t, rng) for t in lengths]
+    batch = BatchPlan.build(lengths).to(DEV)
+    shots = ShotPlan(vds, DEV)
+    with torch.no_grad():
+        cls, loc = model.forward_packed(torch.cat(xs).to(DEV), batch)
+        nms = model.nms_packed(cls, loc, batch, 0.5)
+    out = keyshot_summaries(model, nms, batch, shots)
+    torch.cuda.synchronize()
+    got = split_summaries(out["summary"], shots)
+    counts = nms["keep_count"].cpu().numpy()
+    ks, kb = nms["keep_scores"].cpu().numpy(), nms["keep_boxes"].cpu().numpy()
+    seg = out["seg_scores"].cpu().numpy()
+    o = 0
+    for v, (t, vd) in enumerate(zip(lengths, vds)):
+        a, c = o * 4, int(counts[v])
+        want = orc.bbox_summary(t, ks[a:a + c], kb[a:a + c], vd["cps"], vd["n_frames"], vd["nfps"], vd["picks"])
+        assert np.array_equal(got[v], want), v
+        assert 0 < got[v].sum() <= int(vd["n_frames"] * 0.15) or got[v].sum() == 0
+        o += t
+    assert seg.max() <= 1000 and seg.min() >= 0
