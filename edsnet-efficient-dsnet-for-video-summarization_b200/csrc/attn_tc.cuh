@@ -58,12 +58,49 @@ __device__ __forceinline__ float absmax64(const float (&v)[64]) {
     for (int j = 0; j < 64; ++j) mx = fmaxf(mx, fabsf(v[j]));
     return mx;
 }
+// half a row (32 values, columns c0..c0+31 of the head's 64) -> 4 chunks of the hi and lo planes of row r
+__device__ __forceinline__ void store_row32(unsigned char* hi, unsigned char* lo, int r, int chunk0, const float (&v)[32],
+                                            float mul) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        __half2 hh[4], ll[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float v0 = v[c * 8 + 2 * q] * mul, v1 = v[c * 8 + 2 * q + 1] * mul;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            hh[q] = __halves2half2(h0, h1);
+            ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+        }
+        const uint32_t off = sw128_off(r, chunk0 + c);
+        *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(hh);
+        *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(ll);
+    }
+}
+__device__ __forceinline__ float absmax32(const float (&v)[32]) {
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
+    return mx;
+}
+
 // MN-major right operand stored as [k rows][128 B = 64 n values], SWIZZLE_128B: 8-row atoms of 1024 B along K
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | (64ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
 
+// sum of the hi.hi and cross-term accumulators for 32 columns of this thread's row
+__device__ __forceinline__ void tmem_read32_sum(uint32_t t_main, uint32_t t_lo, float (&v)[32]) {
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(t_main + (uint32_t)c0, r0);
+        tmem_ld16_nowait(t_lo + (uint32_t)c0, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+    }
+}
 // sum of the hi.hi and cross-term accumulators for 64 columns of this thread's row
 __device__ __forceinline__ void tmem_read64_sum(uint32_t t_main, uint32_t t_lo, float (&v)[64]) {
 #pragma unroll
@@ -133,12 +170,15 @@ landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict_
 // half of each product is never read).  Keys stream in 64-row tiles through a 2-stage TMA ring; the running
 // max / sum / output row live in registers (flash-attention style), the zero pad keys of the reference are folded
 // into the start state (logit 0, value 0).
-// 160 threads: warps 0..3 = rows, warp 4 = TMA producer.  TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
+// TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kA3Stage = 8 * 8192;                                          // k_h0 k_h1 v_h0 v_h1, hi and lo
-constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + 2 * 4 * 64 * 4 + 128 + 1024;
+constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4;                   // key scales [2 stages][4][64] + pair exchange
+constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
-__global__ void __launch_bounds__(160, 1)
+// 288 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
+// 32..63), warp 8 = TMA producer.
+__global__ void __launch_bounds__(288, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
               float* __restrict__ a3v) {
@@ -147,8 +187,9 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
     constexpr int oQl = 0, oKV = 32768, oP = 32768 + 2 * kA3Stage, oVec = oP + 32768;
     float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
-    const uint32_t bars = base + oVec + 2 * 4 * 64 * 4;                       // full[2] empty[2] mma
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 2 * 4 * 64 * 4 + 64);
+    float* s_pair = sc_vec + 2 * 4 * 64;                                    // [2 halves][128 rows]
+    const uint32_t bars = base + oVec + kA3VecBytes;                          // full[2] empty[2] mma
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kA3VecBytes + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pair = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
@@ -161,7 +202,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         mbar_init(bars + 32, 1);                                            // mma
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(bars + 64, 512);
+    if (warp == 8) tmem_alloc(bars + 64, 512);
     float inv_ql = 1.f;
     if (tid < 128) {
         // landmark queries of both heads -> A operand planes (row t), per-row scale
@@ -169,6 +210,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         load_row64(q, q_land + (((size_t)v * kHeads + h0 + (tid >> 6)) * kLandmark + (tid & 63)) * kDimHead);
         const int e = scale_exp(absmax64(q));
         inv_ql = ldexpf(1.f, -e);
+        s_pair[tid] = inv_ql;
         store_row64(g + oQl, g + oQl + 16384, tid, q, ldexpf(1.f, e));
         // scales of tile 0: thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
         const int key = tid & 63, part = 1 + (tid >> 6);
@@ -183,7 +225,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             // ---- TMA producer: 8 boxes of 64 rows x 64 columns per tile ----
             for (int i = 0; i < n_tiles; ++i) {
@@ -201,20 +243,24 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             }
         }
     } else {
-        const int hh = tid >> 6;                                            // which head of the pair this row belongs to
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(hh * 128), tO = tS + 256u;
-        float o[64];
+        const int row = tid & 127, half = tid >> 7;
+        const int hh = row >> 6;                                            // which head of the pair this row belongs to
+        inv_ql = s_pair[row];
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(hh * 128 + half * 32), tO = tS + 256u;
+        float o[32];
 #pragma unroll
-        for (int d = 0; d < 64; ++d) o[d] = 0.f;
-        float run_max = vi.pad > 0 ? 0.f : -INFINITY, run_sum = (float)vi.pad;
+        for (int d = 0; d < 32; ++d) o[d] = 0.f;
+        // running max is shared by the two threads of a row; the running sum is per thread (its keys) and merged at the end
+        float run_max = vi.pad > 0 ? 0.f : -INFINITY, run_sum = half == 0 ? (float)vi.pad : 0.f;
         uint32_t mma_phase = 0;
         bool ok = true;
+        named_bar_sync(1, 256);                                             // everyone has read inv_ql out of s_pair
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
             // prefetch the next tile's scales (written to the other stage's slot at the end of this iteration)
             float nsc0 = 0.f, nsc1 = 0.f;
-            {
+            if (tid < 128) {
                 const int key = (i + 1) * 64 + (tid & 63), part = 1 + (tid >> 6);
                 if (key < vi.T) {
                     const float* ip = inv + (size_t)(vi.row0 + key) * 24 + part * 8 + h0;
@@ -233,35 +279,40 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             ok = ok && mbar_wait(bars + 32, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
-            // ---- this row's logits against the 64 keys of the tile ----
-            float p[64];
-            tmem_read64_sum(tS, tS + 64u, p);
-            const float* isk = sc_vec + (s * 4 + hh) * 64;
-            const float* isv = sc_vec + (s * 4 + 2 + hh) * 64;
-            const int kvalid = vi.T - i * 64;
-            float mx = -INFINITY;
+            // ---- this thread's 32 logits of its row ----
+            float p[32];
+            tmem_read32_sum(tS, tS + 64u, p);
+            const float* isk = sc_vec + (s * 4 + hh) * 64 + half * 32;
+            const float* isv = sc_vec + (s * 4 + 2 + hh) * 64 + half * 32;
+            const int kvalid = vi.T - i * 64 - half * 32;
+            float mx = -INFINITY, vmx = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
+            for (int j = 0; j < 32; ++j) {
                 p[j] = j < kvalid ? p[j] * (inv_ql * isk[j]) : -INFINITY;
                 mx = fmaxf(mx, p[j]);
             }
-            const float new_max = fmaxf(run_max, mx);
-            const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
-            float ps = 0.f, pmx = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
+            for (int j = 0; j < 64; ++j) vmx = fmaxf(vmx, sc_vec[(s * 4 + 2 + hh) * 64 + j]);   // same for both halves
+            s_pair[half * 128 + row] = mx;
+            tc_fence_before();
+            named_bar_sync(1, 256);
+            const float new_max = fmaxf(run_max, fmaxf(mx, s_pair[(half ^ 1) * 128 + row]));
+            const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
+            float ps = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
                 const float e = expf(p[j] - new_max);                       // 0 for masked keys
                 ps += e;
                 p[j] = e * isv[j];                                          // fold v's per-key scale into P
-                pmx = fmaxf(pmx, p[j]);
             }
             run_sum = run_sum * alpha + ps;
             run_max = new_max;
-            const int ep = scale_exp(pmx);
-            store_row64(g + oP, g + oP + 16384, tid, p, ldexpf(1.f, ep));
+            // P' <= max_j isv[j]: one row scale for both halves without another exchange
+            const int ep = scale_exp(vmx);
+            store_row32(g + oP, g + oP + 16384, row, half * 4, p, ldexpf(1.f, ep));
             fence_proxy_async();
             tc_fence_before();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             if (tid == 0) {
                 tc_fence_after();
                 issue_split_mma64<true>(tmem_base + 256u, tmem_base + 320u, base + oP, base + oP + 16384,
@@ -272,29 +323,34 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 umma_commit(bars + 16 + 8 * s);                             // K/V stage free once these MMAs are done
             }
             // next tile's scales into the other stage's slot (its previous readers finished before the barrier above)
-            sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
-            sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
+            if (tid < 128) {
+                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
+                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
+            }
             ok = ok && mbar_wait(bars + 32, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
-            float pv[64];
-            tmem_read64_sum(tO, tO + 64u, pv);
+            float pv[32];
+            tmem_read32_sum(tO, tO + 64u, pv);
             const float inv_p = ldexpf(1.f, -ep);
 #pragma unroll
-            for (int d = 0; d < 64; ++d) o[d] = fmaf(o[d], alpha, pv[d] * inv_p);
+            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha, pv[d] * inv_p);
             tc_fence_before();
-            named_bar_sync(1, 128);          // scales visible; everyone is done with S / O before the next tile's MMAs
+            named_bar_sync(1, 256);          // scales visible; everyone is done with S / O before the next tile's MMAs
         }
+        // merge the two partial sums of the row
+        s_pair[half * 128 + row] = run_sum;
+        named_bar_sync(1, 256);
+        const float rs = 1.f / (run_sum + s_pair[(half ^ 1) * 128 + row]);
         if (ok) {
-            float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (tid & 63)) * kDimHead;
-            const float rs = 1.f / run_sum;
+            float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kDimHead + half * 32;
 #pragma unroll
-            for (int d = 0; d < 64; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
+            for (int d = 0; d < 32; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -302,11 +358,14 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 // tiles through a 2-stage TMA ring.  k_land and W are converted to operand planes once per CTA.  The probabilities
 // overwrite the q stage they were computed from (q is dead once S is in TMEM), so a CTA needs 96 KB: two per SM.
 // Writes attn[R][512] (head-merged columns h*64..); value_conv_kernel adds the convolution afterwards.
-// 160 threads: warps 0..3 = rows, warp 4 = TMA producer.  TMEM 256 columns: S main | S cross | O main | O cross.
+// TMEM 256 columns: S main | S cross | O main | O cross.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + 64 * 4 + 128 + 1024;
+constexpr int kAoVecBytes = 64 * 4 + 4 * 128 * 4;                            // inv_kl [64] + pair exchange max / sum [2][128] each
+constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + kAoVecBytes + 128 + 1024;
 
-__global__ void __launch_bounds__(160, 2)
+// 288 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: landmarks / output columns
+// 0..31 and 32..63), warp 8 = TMA producer.
+__global__ void __launch_bounds__(288, 2)
 attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ k_land,
                    const float* __restrict__ w_mat, float* __restrict__ attn) {
@@ -315,9 +374,11 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
     constexpr int oK = 0, oW = 16384, oQ = 32768, oVec = 32768 + 65536;
     float* inv_kl = reinterpret_cast<float*>(g + oVec);                     // [64]
-    unsigned* s_wmax = reinterpret_cast<unsigned*>(g + oVec + 256);
-    const uint32_t bars = base + oVec + 256 + 16;                             // full[2] empty[2] mma
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 256 + 16 + 48);
+    float* s_pmax = inv_kl + 64;                                            // [2][128]
+    float* s_psum = s_pmax + 256;                                           // [2][128]
+    unsigned* s_wmax = reinterpret_cast<unsigned*>(g + oVec + kAoVecBytes);
+    const uint32_t bars = base + oVec + kAoVecBytes + 16;                     // full[2] empty[2] mma
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kAoVecBytes + 16 + 48);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
@@ -331,7 +392,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_wmax = 0u;
     }
-    if (warp == 4) tmem_alloc(bars + 48, 256);
+    if (warp == 8) tmem_alloc(bars + 48, 256);
     __syncthreads();
     float wrow[64];
     if (tid < 64) {
@@ -353,7 +414,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i & 1;
@@ -368,15 +429,16 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
         }
     } else {
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr, tO = tS + 128u;
+        const int trow = tid & 127, half = tid >> 7;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(half * 32), tO = tS + 128u;
         const float o_scale = ldexpf(1.f, -ew) * (1.f / 16384.f);
         uint32_t mma_phase = 0;
         bool ok = true;
-        float inv_q = tid < vi.T ? __ldg(inv + (size_t)(vi.row0 + tid) * 24 + h) : 0.f;
+        float inv_q = trow < vi.T ? __ldg(inv + (size_t)(vi.row0 + trow) * 24 + h) : 0.f;
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
-            const int row = i * 128 + tid;
+            const int row = i * 128 + trow;
             const float inv_q_next = (row + 128 < vi.T) ? __ldg(inv + (size_t)(vi.row0 + row + 128) * 24 + h) : 0.f;
             ok = mbar_wait(bars + 8 * s, (uint32_t)(i >> 1) & 1u);
             const uint32_t st = base + oQ + s * 32768;
@@ -389,46 +451,50 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             ok = ok && mbar_wait(bars + 32, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
-            float p[64];
-            tmem_read64_sum(tS, tS + 64u, p);
+            float p[32];
+            tmem_read32_sum(tS, tS + 64u, p);
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { p[j] *= inv_q * inv_kl[j]; mx = fmaxf(mx, p[j]); }
+            for (int j = 0; j < 32; ++j) { p[j] *= inv_q * inv_kl[half * 32 + j]; mx = fmaxf(mx, p[j]); }
+            s_pmax[half * 128 + trow] = mx;
+            tc_fence_before();
+            named_bar_sync(1, 256);
+            mx = fmaxf(mx, s_pmax[(half ^ 1) * 128 + trow]);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
-            const float rs = 1.f / sum;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) p[j] *= rs;
-            store_row64(stp, stp + 16384, tid, p, 16384.f);                 // probabilities <= 1: fixed scale 2^14
+            for (int j = 0; j < 32; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
+            s_psum[half * 128 + trow] = sum;
+            // un-normalised probabilities (<= 1, fixed scale 2^14); the row sum divides the output instead
+            store_row32(stp, stp + 16384, trow, half * 4, p, 16384.f);
             fence_proxy_async();
             tc_fence_before();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             if (tid == 0) {
                 tc_fence_after();
                 issue_split_mma64<true>(tmem_base + 128u, tmem_base + 192u, st, st + 16384, base + oW, base + oW + 8192);
                 umma_commit(bars + 32);
                 umma_commit(bars + 16 + 8 * s);                             // stage free once P has been consumed
             }
+            const float rs = o_scale / (sum + s_psum[(half ^ 1) * 128 + trow]);
             ok = ok && mbar_wait(bars + 32, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
-            float ov[64];
-            tmem_read64_sum(tO, tO + 64u, ov);
+            float ov[32];
+            tmem_read32_sum(tO, tO + 64u, ov);
             if (row < vi.T) {
-                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead;
+                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32;
 #pragma unroll
-                for (int j = 0; j < 64; j += 4)
-                    st4(dst + j, make_float4(ov[j] * o_scale, ov[j + 1] * o_scale, ov[j + 2] * o_scale, ov[j + 3] * o_scale));
+                for (int j = 0; j < 32; j += 4)
+                    st4(dst + j, make_float4(ov[j] * rs, ov[j + 1] * rs, ov[j + 2] * rs, ov[j + 3] * rs));
             }
             inv_q = inv_q_next;
             tc_fence_before();
-            named_bar_sync(1, 128);          // all rows done with S / O before the next tile's MMAs overwrite them
+            named_bar_sync(1, 256);          // all rows done with S / O before the next tile's MMAs overwrite them
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -438,7 +504,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 // heads stacked along M) and as right operand (MN-major, the two heads side by side along N, LBO = 8 KB): each
 // 128 x 128 product holds the two wanted 64 x 64 products on its block diagonal, thread t reads row t of its own block.
 // Per product: row -> registers -> (7I - ., 15I - ., ...) -> matrix max (shuffle + one barrier) -> planes -> MMA.
-// grid (4 head pairs, V), 128 threads, 5 tiles = 160 KB shared memory, TMEM 256 columns (main | cross).
+// grid (4 head pairs, V), 256 threads, 5 tiles = 160 KB shared memory, TMEM 256 columns (main | cross).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPinvTile = 32768;
 constexpr int kPinvTcSmemBytes = 5 * kPinvTile + 256 + 1024;
@@ -459,18 +525,22 @@ __device__ __forceinline__ void issue_pinv_product(uint32_t tmem_base, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(128, 1)
+// 256 threads: thread t and t + 128 share accumulator row (t & 127); the first owns columns 0..31 of its head's block,
+// the second columns 32..63 (warps w and w + 4 may touch the same TMEM lane quarter).  Two warps per scheduler keep
+// the dependent chain's ALU latency covered.
+__global__ void __launch_bounds__(256, 1)
 pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
                  float* __restrict__ w_out, float* __restrict__ z_out, int iters) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
     constexpr int oA = 0, oZ = kPinvTile, oXZ = 2 * kPinvTile, oT = 3 * kPinvTile, oU = 4 * kPinvTile, oVec = 5 * kPinvTile;
-    float* s_mx = reinterpret_cast<float*>(g + oVec);                       // [2 parities][2 slots][4 warps]
+    float* s_mx = reinterpret_cast<float*>(g + oVec);                       // [2 parities][2 slots][8 warps]
     const uint32_t bar = base + oVec + 128;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 144);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int hh = tid >> 6, i = tid & 63;
+    const int row = tid & 127, half = tid >> 7;                            // tile row, column half
+    const int hh = row >> 6, i = row & 63, c0 = half * 32;
     const int v = blockIdx.y, h = blockIdx.x * 2 + hh;
     const size_t off = ((size_t)v * kHeads + h) * 4096;
 
@@ -483,31 +553,33 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(hh * 64), t_lo = t_main + 128u;
+    const uint32_t t_main = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * 64 + c0), t_lo = t_main + 128u;
     uint32_t phase = 0, par = 0;
     bool ok = true;
 
-    // head-wide maximum of up to two per-row values (one shuffle reduction + one barrier)
+    // head-wide maximum of up to two per-thread values (one shuffle reduction + one barrier)
     auto head_max2 = [&](float m0, float m1, float& o0, float& o1) {
         m0 = warp_max(m0); m1 = warp_max(m1);
-        float* slot = s_mx + par * 8;
-        if (lane == 0) { slot[warp] = m0; slot[4 + warp] = m1; }
+        float* slot = s_mx + par * 16;
+        if (lane == 0) { slot[warp] = m0; slot[8 + warp] = m1; }
         tc_fence_before();
-        named_bar_sync(1, 128);
-        o0 = fmaxf(slot[2 * hh], slot[2 * hh + 1]);
-        o1 = fmaxf(slot[4 + 2 * hh], slot[4 + 2 * hh + 1]);
+        __syncthreads();
+        // rows of head hh live in warps 2hh, 2hh+1 (columns 0..31) and 4+2hh, 5+2hh (columns 32..63)
+        o0 = fmaxf(fmaxf(slot[2 * hh], slot[2 * hh + 1]), fmaxf(slot[4 + 2 * hh], slot[5 + 2 * hh]));
+        o1 = fmaxf(fmaxf(slot[8 + 2 * hh], slot[9 + 2 * hh]), fmaxf(slot[12 + 2 * hh], slot[13 + 2 * hh]));
         par ^= 1u;
     };
-    // store this thread's row of a matrix into tile `o` with the head-wide scale 2^e; returns 2^-e
-    auto put = [&](int o, const float (&row)[64], float head_mx) -> float {
-        const int e = scale_exp(head_mx);
-        store_row64(g + o, g + o + 16384, tid, row, ldexpf(1.f, e));
+    // store this thread's half row (raw accumulator units, true value = raw * unscale) into tile `o` with the head-wide
+    // scale 2^e chosen from the true maximum; returns 2^-e
+    auto put = [&](int o, const float (&r)[32], float unscale, float head_mx_raw) -> float {
+        const int e = scale_exp(head_mx_raw * fabsf(unscale));
+        store_row32(g + o, g + o + 16384, row, half * 4, r, unscale * ldexpf(1.f, e));
         return ldexpf(1.f, -e);
     };
-    auto product = [&](int left, int right, float (&out)[64], float scale) {
+    auto product = [&](int left, int right, float (&out)[32]) {
         fence_proxy_async();
         tc_fence_before();
-        named_bar_sync(1, 128);
+        __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             issue_pinv_product(tmem_base, base + left, base + right);
@@ -516,9 +588,21 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
         ok = mbar_wait(bar, phase) && ok;
         phase ^= 1u;
         tc_fence_after();
-        tmem_read64_sum(t_main, t_lo, out);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) out[j] *= scale;
+        for (int q = 0; q < 32; q += 16) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16_nowait(t_main + (uint32_t)q, r0);
+            tmem_ld16_nowait(t_lo + (uint32_t)q, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out[q + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+        }
+    };
+    const bool has_diag = (i >= c0) && (i < c0 + 32);
+    // t = d * I - t * s  for this thread's columns (s and d / s are powers of two times small integers: exact)
+    auto diag_minus = [&](float (&t)[32], float s, float d) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = (has_diag && j == i - c0 ? d : 0.f) - t[j] * s;
     };
 
     // ---- start: A = attn2, Z0 = A^T / (max row sum * max column sum over ALL 8 heads of the video) ----
@@ -529,56 +613,68 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
         mcol = fmaxf(mcol, __ldg(stats + ((size_t)v * kHeads + q) * 2 + 1));
     }
     const float denom = mrow * mcol;
-    float z[64], t[64];
-    load_row64(t, attn2 + off + i * 64);                                   // row i of A
+    float z[32], t[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) z[j] = __ldg(attn2 + off + j * 64 + i) / denom;    // row i of A^T
+    for (int j = 0; j < 32; j += 4) {
+        const float4 x = ldg4(attn2 + off + i * 64 + c0 + j);               // row i of A
+        t[j] = x.x; t[j + 1] = x.y; t[j + 2] = x.z; t[j + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = __ldg(attn2 + off + (c0 + j) * 64 + i) / denom;    // row i of A^T
     float mA, mZ;
-    head_max2(absmax64(t), absmax64(z), mA, mZ);
-    const float invA = put(oA, t, mA);
-    float invZ = put(oZ, z, mZ);
+    head_max2(absmax32(t), absmax32(z), mA, mZ);
+    const float invA = put(oA, t, 1.f, mA);
+    float invZ = put(oZ, z, 1.f, mZ);
 
     for (int it = 0; it < iters && ok; ++it) {
         // XZ = A Z ; T1 = 7I - XZ
-        float xz[64];
-        product(oA, oZ, xz, invA * invZ);
+        float xz[32];
+        product(oA, oZ, xz);
+        const float sXZ = invA * invZ;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 7.f : 0.f) - xz[j];
+        for (int j = 0; j < 32; ++j) { xz[j] *= sXZ; t[j] = (has_diag && j == i - c0 ? 7.f : 0.f) - xz[j]; }
         float mXZ, mT;
-        head_max2(absmax64(xz), absmax64(t), mXZ, mT);
-        const float invXZ = put(oXZ, xz, mXZ);
-        float invT = put(oT, t, mT);
+        head_max2(absmax32(xz), absmax32(t), mXZ, mT);
+        const float invXZ = put(oXZ, xz, 1.f, mXZ);
+        float invT = put(oT, t, 1.f, mT);
         // U = 15I - XZ T1
-        product(oXZ, oT, t, invXZ * invT);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 15.f : 0.f) - t[j];
+        product(oXZ, oT, t);
+        diag_minus(t, invXZ * invT, 15.f);
         float mU, dummy;
-        head_max2(absmax64(t), 0.f, mU, dummy);
-        const float invU = put(oU, t, mU);
+        head_max2(absmax32(t), 0.f, mU, dummy);
+        const float invU = put(oU, t, 1.f, mU);
         // T2 = 13I - XZ U
-        product(oXZ, oU, t, invXZ * invU);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) t[j] = (j == i ? 13.f : 0.f) - t[j];
-        head_max2(absmax64(t), 0.f, mT, dummy);
-        invT = put(oT, t, mT);
+        product(oXZ, oU, t);
+        diag_minus(t, invXZ * invU, 13.f);
+        head_max2(absmax32(t), 0.f, mT, dummy);
+        invT = put(oT, t, 1.f, mT);
         // Z' = 0.25 Z T2
-        product(oZ, oT, z, 0.25f * invZ * invT);
-        head_max2(absmax64(z), 0.f, mZ, dummy);
-        invZ = put(oZ, z, mZ);
+        product(oZ, oT, z);
+        const float sZ = 0.25f * invZ * invT;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] *= sZ;
+        head_max2(absmax32(z), 0.f, mZ, dummy);
+        invZ = put(oZ, z, 1.f, mZ);
     }
     if (z_out != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) st4(z_out + off + i * 64 + j, make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]));
+        for (int j = 0; j < 32; j += 4) st4(z_out + off + i * 64 + c0 + j, make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]));
     }
     // ---- W = Z a3v ----
-    load_row64(t, a3v + off + i * 64);
-    float mV, dummy2;
-    head_max2(absmax64(t), 0.f, mV, dummy2);
-    const float invV = put(oU, t, mV);
-    product(oZ, oU, t, invZ * invV);
-    if (ok) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) st4(w_out + off + i * 64 + j, make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]));
+    for (int j = 0; j < 32; j += 4) {
+        const float4 x = ldg4(a3v + off + i * 64 + c0 + j);
+        t[j] = x.x; t[j + 1] = x.y; t[j + 2] = x.z; t[j + 3] = x.w;
+    }
+    float mV, dummy2;
+    head_max2(absmax32(t), 0.f, mV, dummy2);
+    const float invV = put(oU, t, 1.f, mV);
+    product(oZ, oU, t);
+    if (ok) {
+        const float sW = invZ * invV;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            st4(w_out + off + i * 64 + c0 + j, make_float4(t[j] * sW, t[j + 1] * sW, t[j + 2] * sW, t[j + 3] * sW));
     }
     tc_fence_before();
     __syncthreads();

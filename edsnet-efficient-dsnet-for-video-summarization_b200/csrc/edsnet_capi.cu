@@ -194,20 +194,20 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     }
     {
         StageScope scope(ST_A3V, st);
-        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 160, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
+        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 288, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
         else a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
         CU_CHECK(cudaGetLastError(), "a3v_kernel");
     }
     {
         StageScope scope(ST_PINV, st);
-        if (tcp) tc::pinv_w_tc_kernel<<<dim3(kHeads / 2, V), 128, tc::kPinvTcSmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        if (tcp) tc::pinv_w_tc_kernel<<<dim3(kHeads / 2, V), 256, tc::kPinvTcSmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         else pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
     }
     if (tcp) {
         {
             StageScope scope(ST_ATTN_OUT, st);
-            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 160, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 288, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
                                                                                   k_land, wmat, merged);
             CU_CHECK(cudaGetLastError(), "attn_out_tc_kernel");
         }
