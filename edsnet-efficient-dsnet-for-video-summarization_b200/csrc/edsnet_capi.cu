@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "fc_stack_tc.cuh"
 #include "attn_tc.cuh"
 #include "mha.cuh"
@@ -357,7 +358,7 @@ int edsnet_debug_stage_times(double* ms_sum, int32_t* launches, int32_t n) {
 }
 
 int edsnet_debug_set_tc_variant(int32_t variant) {
-    if (variant < 0 || variant > 1) return fail(EDSNET_E_ARG, "tc variant must be 0 or 1");
+    if (variant < 0 || variant > 4) return fail(EDSNET_E_ARG, "tc variant must be 0..4");
     tc::variant_ref() = variant;
     return EDSNET_OK;
 }

@@ -17,6 +17,7 @@
 // Every mbarrier wait is bounded: on timeout a global flag is raised and the kernel drains instead of hanging.
 #pragma once
 #include <cuda.h>
+#include <cstdlib>
 #include <string>
 #include "common.cuh"
 #include "gemm_f32.cuh"   // GemmEpi / GemmEpiArgs
@@ -125,20 +126,138 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int BK, int STAGES, int PASSES>
+
+// ---- epilogue stores, shared by the one-CTA and the CTA-pair kernels ----
+// A thread holds 64 consecutive columns (nc0 ..) of output row `row` as raw accumulator sums.
+constexpr int kEpiScratchLd = 20;                                    // floats per row of the 32 x 16 transposition tile
+constexpr int kEpiScratchWarp = 32 * kEpiScratchLd * 4;              // bytes per epilogue warp
+
+// q|k|v as operand planes: per (row, head) power-of-two scale, hi = fp16(x 2^s), lo = fp16(x 2^s - hi).
+// A thread owns one (row, head) = 128 bytes of each plane; stored directly a warp instruction would touch 32 rows x 16
+// bytes, so every 32-column half of a plane goes through the warp-private smem tile (row stride 80 bytes) and leaves
+// as 8 rows x 64 contiguous bytes per instruction.
+__device__ __forceinline__ void epi_store_planes(float (&v)[64], int row0, int lane, int nc0, int M, int N, float* C,
+                                                 const GemmEpiArgs& ep, float* scratch) {
+    const int row = row0 + lane;
+    const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+        const float4 rb = ldg4(ep.b_scale + nc0 + j);
+        v[j] *= ra * rb.x; v[j + 1] *= ra * rb.y; v[j + 2] *= ra * rb.z; v[j + 3] *= ra * rb.w;
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 1])), fmaxf(fabsf(v[j + 2]), fabsf(v[j + 3]))));
+    }
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+    e = max(-100, min(100, e));
+    const float sc = ldexpf(1.f, e);
+    const int slot = nc0 >> 6;                                  // part * 8 + head
+    if (row < M) ep.aux[(size_t)row * 24 + slot] = ldexpf(1.f, -e) * (slot < 8 ? 0.125f : 1.f);
+    unsigned char* sbytes = reinterpret_cast<unsigned char*>(scratch);
+    __half* hi_base = reinterpret_cast<__half*>(C);
+    __half* lo_base = hi_base + (size_t)M * N;
+    const int rr = lane >> 2, cc = lane & 3;                    // read-back: row rr + 8 i, 16-byte chunk cc
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                               // 32 columns at a time
+        uint4 hi4[4], lo4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            __half2 hh[4], ll[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float v0 = v[h * 32 + c * 8 + 2 * q] * sc, v1 = v[h * 32 + c * 8 + 2 * q + 1] * sc;
+                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                hh[q] = __halves2half2(h0, h1);
+                ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
+                                       __float2half_rn(v1 - __half2float(h1)));
+            }
+            hi4[c] = *reinterpret_cast<uint4*>(hh);
+            lo4[c] = *reinterpret_cast<uint4*>(ll);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(sbytes + lane * 80 + c * 16) = pl == 0 ? hi4[c] : lo4[c];
+            __syncwarp();
+            __half* base = pl == 0 ? hi_base : lo_base;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rr + 8 * i;
+                const uint4 o = *reinterpret_cast<const uint4*>(sbytes + r * 80 + cc * 16);
+                if (row0 + r < M)
+                    *reinterpret_cast<uint4*>(base + (size_t)(row0 + r) * N + nc0 + h * 32 + cc * 8) = o;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// fp32 output (+ 1/8 on the q columns, + bias, + residual).  In the accumulator layout a warp instruction would touch 32
+// rows x 16 bytes; every 16-column slab therefore goes through a warp-private 32 x 16 smem tile (row stride 20 floats:
+// conflict-free float4 writes) and leaves as 8 rows x 64 contiguous bytes per instruction, the residual read likewise.
+template <int EPI>
+__device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, int lane, int nc0, int M, int N, float* C,
+                                              const GemmEpiArgs& ep, float* scratch) {
+    const int row = row0 + lane;
+    const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
+    const int rr = lane >> 2, cc = (lane & 3) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const int c = nc0 + q * 16 + j;
+            const float4 rb = ldg4(ep.b_scale + c);
+            float4 o = make_float4(v[q * 16 + j] * (ra * rb.x), v[q * 16 + j + 1] * (ra * rb.y),
+                                   v[q * 16 + j + 2] * (ra * rb.z), v[q * 16 + j + 3] * (ra * rb.w));
+            if (EPI == EPI_QSCALE) {
+                if (c < ep.qcols) { o.x *= 0.125f; o.y *= 0.125f; o.z *= 0.125f; o.w *= 0.125f; }
+            }
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RES) {
+                const float4 b = ldg4(ep.bias + c);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            st4(scratch + lane * kEpiScratchLd + j, o);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rr + 8 * i;
+            const int grow = row0 + r;
+            float4 o = lds4(scratch + r * kEpiScratchLd + cc);
+            if (grow < M) {
+                const int c = nc0 + q * 16 + cc;
+                if (EPI == EPI_BIAS_RES) {
+                    const float4 x = ldg4(ep.res + (size_t)grow * ep.ldr + c);
+                    o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                }
+                st4(C + (size_t)grow * N + c, o);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (hi.hi rotating over three + cross terms) or 2 (hi.hi | cross terms);
+// PASSES == 1: 1.  Whatever fits twice into the 512 TMEM columns is double-buffered (MMAs of tile t+1 overlap the
+// drain of tile t).
+template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES == 3 ? 4 : 1)>
 struct TcCfg {
     static constexpr int BM = 128;
     static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
     static constexpr int kBTile = BN * BK * 2;
     static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
-    static constexpr int kAccs = PASSES == 3 ? 4 : 1;      // TMEM accumulators per tile (see the header comment)
-    static constexpr int kBufs = PASSES == 3 ? 1 : 2;      // tiles in flight in TMEM
+    static constexpr int kAccs = ACCS;
+    static constexpr int kBufs = (2 * ACCS * BN <= 512) ? 2 : 1;      // tiles in flight in TMEM
     static constexpr int kTmemCols = kAccs * kBufs * BN;
-    static_assert(BN == 128, "an epilogue thread keeps half a 128-column output row in registers");
+    static_assert(BN == 128 || BN == 64, "an epilogue thread keeps 64 columns of an output row in registers");
+    static_assert(PASSES == 3 ? (ACCS == 4 || ACCS == 2) : ACCS == 1, "accumulator scheme");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
-    static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    static constexpr int kThreads = 320;                   // TMA warp, MMA warp, 8 epilogue warps
+    static constexpr int kEpiWarps = BN / 16;              // 8 (two per TMEM lane quarter) or 4
+    static constexpr int kScratchOff = STAGES * kStageBytes + 256;    // after the barriers
+    static constexpr int kSmemBytes = kScratchOff + kEpiWarps * kEpiScratchWarp + 1024 /*alignment slack*/;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); CTA b owns tiles b, b + grid, ...  (n fastest, so the CTAs that run
@@ -146,11 +265,11 @@ struct TcCfg {
 // boundaries, so the smem ring is full again by the time the epilogue has drained TMEM.  The epilogue pulls the
 // whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
 // residual and stores -- the next tile's MMAs overlap those global accesses.
-template <int BN, int BK, int STAGES, int PASSES, int EPI>
-__global__ void __launch_bounds__(320, 1)
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES == 3 ? 4 : 1)>
+__global__ void __launch_bounds__(64 + 2 * BN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
-    using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
@@ -175,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+        for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), Cfg::kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -228,13 +347,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
                     const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
                     // PASSES == 3: hi.hi of K block kb -> accumulator kb % 3, both cross terms -> accumulator 3
-                    const uint32_t acc_main = tmem_acc + (PASSES == 3 ? (uint32_t)((kb % 3) * BN) : 0u);
-                    const uint32_t acc_lo = tmem_acc + 3u * BN;
+                    const uint32_t acc_main = tmem_acc + (ACCS == 4 ? (uint32_t)((kb % 3) * BN) : 0u);
+                    const uint32_t acc_lo = tmem_acc + (uint32_t)((ACCS - 1) * BN);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint32_t koff = k * 32;       // 16 fp16 = 32 bytes further along K inside the atom
                         const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
-                        const bool first_main = PASSES == 3 ? (kb < 3 && k == 0) : ((kb | k) == 0);
+                        const bool first_main = ACCS == 4 ? (kb < 3 && k == 0) : ((kb | k) == 0);
                         umma_f16(acc_main, dah, dbh, idesc, first_main ? 0u : 1u);
                         if (PASSES == 3) {
                             const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
@@ -250,15 +369,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> 64 columns of one output row ----
         const int quarter = warp & 3;
-        const int chalf = (warp - 2) >> 2;                       // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127
-        const int n_main = PASSES == 3 ? (nk < 3 ? nk : 3) : 1;     // accumulators that received hi.hi products
+        const int chalf = (warp - 2) >> 2;                       // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127 (BN 128)
+        const int n_main = ACCS == 4 ? (nk < 3 ? nk : 3) : 1;       // accumulators that received hi.hi products
         bool ok = true;
         int t = 0;
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
             const int m0 = (tile / tiles_n) * Cfg::BM, n0 = (tile % tiles_n) * BN;
             const int buf = t % Cfg::kBufs;
             const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
-            const int row = m0 + quarter * 32 + lane;
             ok = mbar_wait(tfull_bar(buf), tph);
             tc_fence_after();
             const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) +
@@ -269,7 +387,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 uint32_t r0[16];
                 tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
-                if (PASSES == 3) {
+                if (ACCS == 2) {
+                    uint32_t r1[16];
+                    tmem_ld16_nowait(t0 + (uint32_t)BN + (uint32_t)c0, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                } else if (ACCS == 4) {
                     // (acc0 + acc1) + (acc2 + acc3), every add rounded to nearest
                     uint32_t r1[16], r2[16], r3[16];
                     tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
@@ -294,61 +418,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
-            if (row < M && EPI == EPI_QKV_PLANES) {
-                // q|k|v as operand planes: per (row, head) power-of-two scale, hi = fp16(x 2^s), lo = fp16(x 2^s - hi)
-                const float ra = __ldg(ep.a_scale + row);
-                __half* hi_row = reinterpret_cast<__half*>(C) + (size_t)row * N + nc0;
-                __half* lo_row = hi_row + (size_t)M * N;
-                float mx = 0.f;
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    const float4 rb = ldg4(ep.b_scale + nc0 + j);
-                    v[j] *= ra * rb.x; v[j + 1] *= ra * rb.y; v[j + 2] *= ra * rb.z; v[j + 3] *= ra * rb.w;
-                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 1])), fmaxf(fabsf(v[j + 2]), fabsf(v[j + 3]))));
-                }
-                int e = 0;
-                if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
-                e = max(-100, min(100, e));
-                const float sc = ldexpf(1.f, e);
-                const int slot = nc0 >> 6;                                  // part * 8 + head
-                ep.aux[(size_t)row * 24 + slot] = ldexpf(1.f, -e) * (slot < 8 ? 0.125f : 1.f);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    __half2 hh[4], ll[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float v0 = v[c * 8 + 2 * q] * sc, v1 = v[c * 8 + 2 * q + 1] * sc;
-                        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-                        hh[q] = __halves2half2(h0, h1);
-                        ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
-                                               __float2half_rn(v1 - __half2float(h1)));
-                    }
-                    *reinterpret_cast<uint4*>(hi_row + c * 8) = *reinterpret_cast<uint4*>(hh);
-                    *reinterpret_cast<uint4*>(lo_row + c * 8) = *reinterpret_cast<uint4*>(ll);
-                }
-            } else if (row < M) {
-                float* crow = C + (size_t)row * N + nc0;
-                const float* rrow = (EPI == EPI_BIAS_RES) ? ep.res + (size_t)row * ep.ldr + nc0 : nullptr;
-                const float ra = __ldg(ep.a_scale + row);
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    const int c = nc0 + j;
-                    const float4 rb = ldg4(ep.b_scale + c);
-                    float4 o = make_float4(v[j] * (ra * rb.x), v[j + 1] * (ra * rb.y), v[j + 2] * (ra * rb.z),
-                                           v[j + 3] * (ra * rb.w));
-                    if (EPI == EPI_QSCALE) {
-                        if (c < ep.qcols) { o.x *= 0.125f; o.y *= 0.125f; o.z *= 0.125f; o.w *= 0.125f; }
-                    }
-                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_RES) {
-                        const float4 b = ldg4(ep.bias + c);
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (EPI == EPI_BIAS_RES) {
-                        const float4 x = ldg4(rrow + j);
-                        o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                    }
-                    st4(crow + j, o);
-                }
+            if (EPI == EPI_QKV_PLANES) {
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
+                epi_store_planes(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+            } else {
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
+                epi_store_f32<EPI>(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
             }
         }
     }
@@ -446,14 +521,14 @@ inline int num_sms() {
     return n;
 }
 
-template <int BN, int BK, int STAGES, int PASSES, int EPI>
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES == 3 ? 4 : 1)>
 cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                            cudaStream_t st, std::string* msg) {
-    using Cfg = TcCfg<BN, BK, STAGES, PASSES>;
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS>;
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A16, 2ull * M, K, BK, Cfg::BM, msg)) return cudaErrorUnknown;
     if (!make_map(&mapB, B16, 2ull * N, K, BK, BN, msg)) return cudaErrorUnknown;
-    auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI>;
+    auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI, ACCS>;
     static bool opted = false;
     if (!opted) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -466,8 +541,17 @@ cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M
     return cudaGetLastError();
 }
 
-// variant: 0 = BK64 / 128B swizzle (default), 1 = BK32 / 64B swizzle (two CTAs per SM)
-inline int& variant_ref() { static int v = 0; return v; }
+// CTA-pair kernel (gemm_tc2.cuh)
+template <int STAGES, int EPI>
+cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
+                        cudaStream_t st, std::string* msg);
+
+// variant: 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh), 0 = BK64 / 128B swizzle (default), 1 = BK32 / 64B swizzle, 2 = 128 x 64 tiles (4 accumulators, double-
+// buffered TMEM), 3 = 128 x 128 tiles with 2 accumulators (double-buffered TMEM)
+inline int& variant_ref() {
+    static int v = [] { const char* e = getenv("EDSNET_TC_VARIANT"); return e ? atoi(e) : 0; }();   // profiling knob
+    return v;
+}
 
 template <int PASSES, int EPI>
 cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
@@ -476,7 +560,10 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
     if (N % 128 == 0) {
         if (PASSES == 3) {
             // four 128-column accumulators fill TMEM
+            if (variant == 4) return launch_pair<4, EPI>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 1) return launch_variant<128, 32, 4, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            if (variant == 2) return launch_variant<64, 64, 4, 3, EPI, 4>(A16, B16, C, M, N, K, ep, st, msg);
+            if (variant == 3) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 3, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         } else {
             if (variant == 1) return launch_variant<128, 32, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
