@@ -49,16 +49,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok;
 }
 // bounded wait: returns false (and raises g_timeout_flag) after ~2^31 cycles
+// (the clock / flag check touches global memory, so it runs only every 256 failed probes: the wake-up after the barrier
+// flips must not wait for an L2 round trip)
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 31) || *((volatile int*)&g_timeout_flag) != 0) {
-            atomicExch(&g_timeout_flag, 1);
-            return false;
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((spins & 255u) == 0u) {
+            if (clock64() - t0 > (1ll << 31) || *((volatile int*)&g_timeout_flag) != 0) {
+                atomicExch(&g_timeout_flag, 1);
+                return false;
+            }
         }
     }
-    return true;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
