@@ -5,6 +5,8 @@ Public surface:
   BatchPlan        packed variable-length batch tables
   shard_videos     video-wise partition across ranks (no collective on the data path)
   ScoringPipeline  host-buffer -> proposals throughput path (pinned H2D / compute / D2H overlapped)
+  ShotPlan / keyshot_summaries   kept proposals -> keyshot summaries on the device (bbox2summary)
+  TruthPlan / eval_metrics / evaluate   F-score and diversity of the summaries on the device (evaluate.py)
   training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
 from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
@@ -12,5 +14,6 @@ from .dsnet import DSNet, NystromAttention, AttentionExtractor                  
 from .pipeline import ScoringPipeline                            # noqa: F401
 from . import training                                           # noqa: F401
 from .summary import ShotPlan, keyshot_summaries, split_summaries  # noqa: F401
+from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

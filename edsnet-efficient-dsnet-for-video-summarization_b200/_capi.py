@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 3
+EDSNET_ABI_VERSION = 4
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -54,6 +54,10 @@ class Shots(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("cu_seg", "cps", "nfps", "picks", "cu_frames", "capacity", "gcd", "dp_off")]
 
 
+class EvalTruth(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cu_users", "user_off", "user_frames", "user_summ", "metric")]
+
+
 # every symbol include/edsnet_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -66,6 +70,7 @@ SYMBOLS = {
                                     _P, _P, _P]),
     "edsnet_keyshot_summary": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), C.POINTER(Shots), _P, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _P]),
+    "edsnet_eval_metrics": (C.c_int, [C.POINTER(Batch), _P, _P, C.POINTER(EvalTruth), _P, _P, _P, _P, _P, _P]),
     "edsnet_decode_boxes": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_forward_launches": (C.c_int, [C.POINTER(Config)]),
     "edsnet_split_f16_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

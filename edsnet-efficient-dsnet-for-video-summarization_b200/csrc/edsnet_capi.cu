@@ -18,6 +18,7 @@
 #include "decode_nms.cuh"
 #include "nms_large.cuh"
 #include "summary.cuh"
+#include "eval.cuh"
 
 namespace {
 
@@ -500,6 +501,24 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     if (rc) return rc;
     // 6. ROI pooling + heads                                                    (dsnet.py:110-115)
     return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st);
+}
+
+int edsnet_eval_metrics(const edsnet_batch* batch, const int64_t* cu_frames, const uint8_t* summary,
+                        const edsnet_eval_truth* truth, const float* x, double* fscore, double* diversity,
+                        double* user_f1, int32_t* counts, void* stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (!truth || !truth->cu_users || !truth->user_off || !truth->user_frames || !truth->user_summ || !truth->metric)
+        return fail(EDSNET_E_ARG, "eval_metrics: truth tables are NULL");
+    if (!cu_frames || !summary || !x || !fscore || !diversity || !user_f1 || !counts)
+        return fail(EDSNET_E_ARG, "eval_metrics: NULL operand");
+    EvalTruth tr{truth->cu_users, reinterpret_cast<const long long*>(truth->user_off), truth->user_frames,
+                 truth->user_summ, truth->metric};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    eval_metrics_kernel<<<batch->n_videos, 256, 0, st>>>(batch->cu_rows, reinterpret_cast<const long long*>(cu_frames),
+                                                        summary, tr, x, fscore, diversity, user_f1, counts);
+    CU_CHECK(cudaGetLastError(), "eval_metrics_kernel");
+    return EDSNET_OK;
 }
 
 int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, const edsnet_shots* shots,

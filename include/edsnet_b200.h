@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 3
+#define EDSNET_ABI_VERSION 4
 
 enum {
     EDSNET_OK = 0,
@@ -177,6 +177,26 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
                            const int32_t* keep_count, const float* keep_scores, const int32_t* keep_boxes,
                            float* pos_scores, float* frame_scores, int32_t* seg_scores, uint8_t* picked,
                            uint8_t* summary, void* dp_scratch, void* stream);
+
+/* Ground-truth user summaries of the videos of a batch, for edsnet_eval_metrics.  All arrays [dev]. */
+typedef struct {
+    const int32_t* cu_users;    /* [n_videos + 1] first user row of every video                                  */
+    const int64_t* user_off;    /* [total_users] byte offset of the user's 0/1 row inside user_summ, multiple of 4 */
+    const int32_t* user_frames; /* [n_videos] frames per user row (user_summary.shape[1])                         */
+    const uint8_t* user_summ;   /* 0/1 bytes, rows padded to a multiple of 4 bytes                                */
+    const int32_t* metric;      /* [n_videos] 0 = 'avg' (TVSum keys), 1 = 'max' (evaluate.py:31)                  */
+} edsnet_eval_truth;
+
+/* evaluate.py:31-37: vsumm_helper.get_summ_f1score (helpers/vsumm_helper.py:142-172, f1_score :8-23) and
+ * get_summ_diversity (:119-139) of downsample_summ (:48-50), per video, on the device.
+ *   summary [total_frames] 0/1 and cu_frames [n_videos + 1] as written by / given to edsnet_keyshot_summary;
+ *   x [total_rows][1024] the batch's features.  Outputs: fscore [n_videos] float64 (bit-exact: integer counts +
+ *   the reference's float64 operations), diversity [n_videos] float64 (float64 accumulation; the reference sums
+ *   float32 products: equal to ~1e-6 relative), user_f1 [total_users] float64, counts [n_videos][2] =
+ *   {frames selected within the users' frame count, selected feature rows}. */
+int edsnet_eval_metrics(const edsnet_batch* batch, const int64_t* cu_frames, const uint8_t* summary,
+                        const edsnet_eval_truth* truth, const float* x, double* fscore, double* diversity,
+                        double* user_f1, int32_t* counts, void* stream);
 
 /* decode only (what DSNet.predict returns, dsnet.py:146-153, plus the evaluate.py:26 clip/round):
  * boxes_f32 [dev][total_rows*S][2] (may be NULL), boxes_i32 [dev][total_rows*S][2] (may be NULL). */

@@ -433,6 +433,57 @@ def bbox_summary(T: int, keep_scores: np.ndarray, keep_boxes: np.ndarray, cps, n
 
 
 # --------------------------------------------------------------------------
+# evaluation metrics (evaluate.py:31-37; helpers/vsumm_helper.py:8-23, 48-50, 119-172)
+# --------------------------------------------------------------------------
+
+def f1_score(pred: np.ndarray, test: np.ndarray) -> float:
+    """helpers/vsumm_helper.py:8-23: integer counts, float64 precision / recall / harmonic mean."""
+    pred = np.asarray(pred, dtype=bool)
+    test = np.asarray(test, dtype=bool)
+    overlap = (pred & test).sum()
+    if overlap == 0:
+        return 0.0
+    precision = overlap / pred.sum()
+    recall = overlap / test.sum()
+    return float(2 * precision * recall / (precision + recall))
+
+
+def summ_f1score(pred_summ: np.ndarray, test_summ: np.ndarray, eval_metric: str = "avg") -> float:
+    """helpers/vsumm_helper.py:142-172: the prediction is cut / zero-padded to the users' frame count, then the
+    mean ('avg', TVSum) or the maximum ('max', SumMe) of the per-user F1 scores."""
+    pred_summ = np.asarray(pred_summ, dtype=bool)
+    test_summ = np.asarray(test_summ, dtype=bool)
+    n = test_summ.shape[1]
+    if pred_summ.size > n:
+        pred_summ = pred_summ[:n]
+    elif pred_summ.size < n:
+        pred_summ = np.pad(pred_summ, (0, n - pred_summ.size))
+    f1s = [f1_score(u, pred_summ) for u in test_summ]
+    if eval_metric == "avg":
+        return float(np.mean(f1s))
+    if eval_metric == "max":
+        return float(np.max(f1s))
+    raise ValueError(f"Invalid eval metric {eval_metric}")
+
+
+def downsample_summ(summ: np.ndarray) -> np.ndarray:
+    """helpers/vsumm_helper.py:48-50."""
+    return summ[::15]
+
+
+def summ_diversity(pred_summ: np.ndarray, features: np.ndarray) -> float:
+    """helpers/vsumm_helper.py:119-139: mean over ordered pairs i != j of the selected rows of f_i . f_j."""
+    assert len(pred_summ) == len(features)
+    pos = np.asarray(features)[np.asarray(pred_summ, dtype=bool)]
+    if len(pos) < 2:
+        return 0.0
+    div = 0.0
+    for f in pos:
+        div += (f * pos).sum() - (f * f).sum()
+    return float(div / (len(pos) * (len(pos) - 1)))
+
+
+# --------------------------------------------------------------------------
 # error metrics used by every parity test
 # --------------------------------------------------------------------------
 

@@ -554,3 +554,80 @@ def test_keyshot_summary_packed_vs_oracle():
         assert 0 < got[v].sum() <= int(vd["n_frames"] * 0.15) or got[v].sum() == 0
         o += t
     assert seg.max() <= 1000 and seg.min() >= 0
+
+
+# ------------------------------------------------------------------------------------------------ evaluation metrics
+EV = load_npz("eval_golden.npz")
+
+
+def _eval_case(name):
+    n_frames, nu = int(EV[f"{name}/n_frames"]), int(EV[f"{name}/users_frames"])
+    pred = np.unpackbits(EV[f"{name}/pred"])[:n_frames]
+    users = np.unpackbits(EV[f"{name}/users"], axis=1)[:, :nu]
+    return int(EV[f"{name}/T"]), n_frames, pred, users, str(EV[f"{name}/metric"]), int(EV[f"{name}/x_seed"])
+
+
+def test_eval_metrics_match_reference_golden():
+    """F-score (bit-exact float64) and diversity of the reference's get_summ_f1score / get_summ_diversity, all golden
+    cases in ONE packed launch (cut and zero-padded predictions, avg and max, empty and single-row selections)."""
+    from edsnet_b200 import BatchPlan, ShotPlan, TruthPlan, eval_metrics
+    names = [str(n) for n in EV["cases"]]
+    cases = [_eval_case(n) for n in names]
+    lengths = [c[0] for c in cases]
+    x = torch.cat([orc.synth_features(c[0], c[5]) for c in cases]).to(DEV)
+    batch = BatchPlan.build(lengths).to(DEV)
+    vds = [dict(cps=np.array([[0, c[1] - 1]]), nfps=np.array([c[1]]), picks=np.arange(c[0]) * 15, n_frames=c[1]) for c in cases]
+    shots = ShotPlan(vds, DEV)
+    truth = TruthPlan([c[3] for c in cases], [c[4] for c in cases], DEV)
+    summary = torch.from_numpy(np.concatenate([c[2] for c in cases]).astype(np.uint8)).to(DEV)
+    out = eval_metrics(x, batch, shots, truth, summary)
+    torch.cuda.synchronize()
+    f, d = out["fscore"].cpu().numpy(), out["diversity"].cpu().numpy()
+    uf = out["user_f1"].cpu().numpy()
+    o = 0
+    for i, n in enumerate(names):
+        assert f[i] == float(EV[f"{n}/fscore"]), (n, f[i], float(EV[f"{n}/fscore"]))
+        want_u = EV[f"{n}/user_f1"]
+        assert np.array_equal(uf[o:o + len(want_u)], want_u), n
+        o += len(want_u)
+        want_d = float(EV[f"{n}/diversity"])
+        assert abs(d[i] - want_d) <= 1e-5 * max(abs(want_d), 1e-12), (n, d[i], want_d)
+
+
+def test_evaluate_loop_vs_oracle():
+    """edsnet_b200.evaluate (the reference's evaluate() over a loader of 8-tuples) against the oracle's host chain fed
+    with the device's kept proposals: F-scores identical, diversity to 1e-5."""
+    from edsnet_b200 import evaluate
+    from edsnet_b200 import BatchPlan, ShotPlan, TruthPlan, eval_metrics, keyshot_summaries, split_summaries
+    rng = np.random.default_rng(11)
+    p = orc.synth_params(5, "xavier")
+    scales = [4, 8, 16, 32]
+    model = make_model(p, scales, 5, "fp16x3", DEV)
+    lengths = [int(t) for t in rng.integers(40, 500, size=9)]
+    items = []
+    for i, t in enumerate(lengths):
+        vd = _shots_for(t, rng)
+        nf = int(vd["n_frames"])
+        users = (rng.random((int(rng.integers(3, 21)), nf)) < 0.2).astype(np.uint8)
+        key = f"../datasets/eccv16_dataset_{'tvsum' if i % 2 == 0 else 'summe'}_google_pool5.h5/video_{i}"
+        items.append((key, orc.synth_features(t, 6000 + i).numpy(), None, vd["cps"], nf, vd["nfps"], vd["picks"], users))
+    fs, dv = evaluate(model, items, 0.5, DEV)
+    # oracle chain on the device's proposals
+    batch = BatchPlan.build(lengths).to(DEV)
+    x = torch.from_numpy(np.concatenate([it[1] for it in items])).to(DEV)
+    with torch.no_grad():
+        cls, loc = model.forward_packed(x, batch)
+        nms = model.nms_packed(cls, loc, batch, 0.5)
+    counts = nms["keep_count"].cpu().numpy()
+    ks, kb = nms["keep_scores"].cpu().numpy(), nms["keep_boxes"].cpu().numpy()
+    o, want_f, want_d = 0, [], []
+    for v, it in enumerate(items):
+        t = lengths[v]
+        a, c = o * 4, int(counts[v])
+        summ = orc.bbox_summary(t, ks[a:a + c], kb[a:a + c], it[3], it[4], it[5], it[6])
+        want_f.append(orc.summ_f1score(summ, it[7], "avg" if "tvsum" in it[0] else "max"))
+        want_d.append(orc.summ_diversity(orc.downsample_summ(summ), it[1]))
+        o += t
+    assert fs == float(sum(want_f) / len(want_f)), (fs, want_f)
+    assert abs(dv - sum(want_d) / len(want_d)) < 1e-5
+    assert 0.0 < fs < 1.0
