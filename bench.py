@@ -217,7 +217,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from edsnet_b200 import BatchPlan, ScoringPipeline, _capi
+    from edsnet_b200.pipeline import bind_host_to_gpu_numa_node
     lib = _capi.lib()
+    # host threads and the pinned staging buffers of this rank on the socket its GPU hangs off
+    orig_affinity = os.sched_getaffinity(0)
+    numa_cpus = bind_host_to_gpu_numa_node(local_rank)
+    log(f"[rank {rank}] bound to {len(numa_cpus)} GPU-local cores" if numa_cpus else f"[rank {rank}] no NUMA binding")
 
     lengths = workload_lengths(rank, args.videos)
     R = int(sum(lengths))
@@ -277,6 +282,10 @@ def main():
     ms_e2e = timed(lambda: pipe.run(x_host, lengths, dev), args.steps)
     clocks = sampler.stop()
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    if world > 1:                      # bytes per step of the whole job, like `value`
+        t = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
     kept_total = int(res[0].sum())
 
     # instrumented steps: per-stage CUDA events on the launching stream (not part of `value`)
@@ -327,6 +336,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, orig_affinity)          # the CPU leg gets every host core again
         score, cores = cpu_reference_setup(model.state_dict(), scales)
         n, frames, dt = run_cpu_sample(score, x_host, lengths, args.cpu_budget, 2048)
         cpu_base = {"value": n / dt, "unit": "videos/s", "cores": cores, "kind": "port",
@@ -341,7 +351,7 @@ def main():
             "frames_per_sec": frames_all * args.steps / (ms_dev * 1e-3),
             "config": {"workload": workload, "videos_per_gpu": args.videos, "frames_per_gpu": R,
                        "device_chunk_rows": args.device_chunk_rows, "chunks_per_step": len(chunks),
-                       "e2e_chunk_rows": args.chunk_rows, "parallelism": f"video-wise x{world}",
+                       "e2e_chunk_rows": args.chunk_rows, "parallelism": f"video-wise x{world}", "host_numa_binding": bool(numa_cpus),
                        "l2": "inputs (7.5 GB/GPU) exceed L2; no flush needed", "weights": "xavier random init",
                        "kept_proposals": kept_total},
             "e2e": {"value": e2e_v, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

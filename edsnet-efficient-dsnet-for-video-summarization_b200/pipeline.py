@@ -16,6 +16,31 @@ import torch
 from .plan import BatchPlan
 
 
+def bind_host_to_gpu_numa_node(device_index: int) -> List[int]:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (same socket / PCIe root).
+    Pinned host buffers allocated afterwards land in that socket's memory, so the host->device stream of every rank of
+    a multi-GPU box stays off the inter-socket link.  Returns the core list ([] if NVML or the affinity call is
+    unavailable: the pipeline then runs unbound, as before)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in range(n_cpu) if (int(words[c // 64]) >> (c % 64)) & 1 and c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
+
+
 class ScoringPipeline:
     def __init__(self, model, chunk_rows: int = 32768, nms_thresh: float = 0.5, depth: int = 2):
         self.model = model
