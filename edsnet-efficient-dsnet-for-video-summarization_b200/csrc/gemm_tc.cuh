@@ -206,6 +206,18 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
     const int row = row0 + lane;
     const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
     const int rr = lane >> 2, cc = (lane & 3) * 4;
+    // residual: all 16 loads of this thread (post-transposition layout) in flight at once, one exposed latency per tile
+    float4 resv[EPI == EPI_BIAS_RES ? 16 : 1];
+    if (EPI == EPI_BIAS_RES) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int grow = row0 + rr + 8 * i;
+                resv[q * 4 + i] = grow < M ? ldg4(ep.res + (size_t)grow * ep.ldr + nc0 + q * 16 + cc)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -232,7 +244,7 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
             if (grow < M) {
                 const int c = nc0 + q * 16 + cc;
                 if (EPI == EPI_BIAS_RES) {
-                    const float4 x = ldg4(ep.res + (size_t)grow * ep.ldr + c);
+                    const float4 x = resv[q * 4 + i];
                     o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
                 }
                 st4(C + (size_t)grow * N + c, o);
@@ -568,6 +580,10 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
             if (variant == 1) return launch_variant<128, 32, 4, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 2) return launch_variant<64, 64, 4, 3, EPI, 4>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 3) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
+            // K <= 512: the hi.hi products of one tile are <= 32 accumulation steps, so ONE main accumulator stays
+            // inside the truncation budget of the K = 1024 case (3 x <= 24 steps) and the tile fits twice into TMEM:
+            // the next tile's MMAs overlap the drain
+            if (variant == 0 && K <= 512) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 3, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         } else {
             if (variant == 1) return launch_variant<128, 32, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
