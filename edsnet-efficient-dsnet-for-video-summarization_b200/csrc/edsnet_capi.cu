@@ -252,14 +252,9 @@ int roi_impl(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_bat
              float* pred_cls, float* pred_loc, cudaStream_t st) {
     int halo = 0;
     ScaleList sl = make_scales(cfg, &halo);
-    const int smem = (128 + 2 * halo) * kHidden * (int)sizeof(float);
-    static int opted = 0;
-    if (smem > opted) {
-        CU_CHECK(opt_in_smem(roi_pool_heads_kernel, smem), "smem opt-in roi_pool_heads");
-        opted = smem;
-    }
+    if (halo > kRoiMaxHalo) return fail(EDSNET_E_UNSUPPORTED, "roi_pool_heads: anchor scale above 128");
     StageScope scope(ST_ROI, st);
-    roi_pool_heads_kernel<<<b->n_tiles128, 256, smem, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
+    roi_pool_heads_kernel<<<b->n_tiles128, 256, 0, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
                                                              sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
                                                              pred_cls, pred_loc);
     CU_CHECK(cudaGetLastError(), "roi_pool_heads_kernel");

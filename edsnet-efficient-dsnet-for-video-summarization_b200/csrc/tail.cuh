@@ -191,58 +191,82 @@ fc_stack_kernel(const float* __restrict__ u_in, const float* __restrict__ w, con
 //   pooled[t][s] = (1/scale_s) * sum_{j = t - scale_s/2}^{t + scale_s/2 - 1} u[j]   (u[j] = 0 outside the video;
 //   AvgPool1d(scale, 1, scale//2) with count_include_pad, last of the T+1 outputs dropped)
 //   pred_cls = sigmoid(pooled . w_cls + b_cls),  pred_loc = pooled . W_loc + b_loc
-// One CTA per 128-row tile of one video (tiles[] = {video, first row}); the tile plus a max_scale/2 halo is
-// staged in smem once (128-bit loads), one warp per output row, every lane owns 4 of the 128 channels.
+// Pooling and the heads are both linear, so the three head projections are taken FIRST, once per feature row
+// (d[t] = u[t] . {w_cls, w_loc0, w_loc1}), and the windows then run over 3 channels instead of 128:
+// pooled . w = (1/s) sum_j d[j].  The kernel is a pure stream over u (512 B per row in, 12 S bytes per row out):
+// one CTA per 128-row tile of one video (tiles[] = {video, first row}) plus a max_scale/2 halo; a warp takes four rows
+// at a time (four independent 128-bit loads per lane in flight), the 12 partial dots are reduced with a packed
+// butterfly (18 shuffles per 4 rows), then one thread per (row, scale) sums its window out of shared memory.
 // ---------------------------------------------------------------------------------------------------------
 struct ScaleList { int n; int s[kMaxScales]; };
+constexpr int kRoiMaxHalo = 64;                                   // scales <= 128
 
 __global__ void __launch_bounds__(256)
 roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
                       ScaleList scales, int halo, const float* __restrict__ w_cls, const float* __restrict__ b_cls,
                       const float* __restrict__ w_loc, const float* __restrict__ b_loc,
                       float* __restrict__ pred_cls, float* __restrict__ pred_loc) {
-    extern __shared__ __align__(16) float smem[];      // [(128 + 2*halo)][128]
+    __shared__ float sd[3][128 + 2 * kRoiMaxHalo + 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 tile = tiles[blockIdx.x];
     const int v = tile.x, t0 = tile.y;
     const VidInfo vi = vid_info(cu_rows, v);
     const int nrows = 128 + 2 * halo;
-    for (int idx = tid; idx < nrows * 32; idx += 256) {
-        int r = idx >> 5, c4 = (idx & 31) * 4;
-        int t = t0 - halo + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < vi.T) x = ldg4(u + (size_t)(vi.row0 + t) * kHidden + c4);
-        st4(smem + r * kHidden + c4, x);
-    }
     const float4 wc = ldg4(w_cls + lane * 4);
     const float4 w0 = ldg4(w_loc + lane * 4);
     const float4 w1 = ldg4(w_loc + kHidden + lane * 4);
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    const int grp = (lane >> 3) & 3;                               // which of the 4 rows this lane ends up holding
+    for (int r4 = warp * 4; r4 < nrows; r4 += 32) {
+        float p[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = t0 - halo + r4 + k;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < vi.T && r4 + k < nrows) x = ldg4(u + (size_t)(vi.row0 + t) * kHidden + lane * 4);
+            p[k * 3 + 0] = fmaf(x.x, wc.x, fmaf(x.y, wc.y, fmaf(x.z, wc.z, x.w * wc.w)));
+            p[k * 3 + 1] = fmaf(x.x, w0.x, fmaf(x.y, w0.y, fmaf(x.z, w0.z, x.w * w0.w)));
+            p[k * 3 + 2] = fmaf(x.x, w1.x, fmaf(x.y, w1.y, fmaf(x.z, w1.z, x.w * w1.w)));
+        }
+        // packed butterfly: 12 -> 6 values (lanes 16 apart), 6 -> 3 (8 apart), then plain butterflies over 4, 2, 1;
+        // lanes 8 g .. 8 g + 7 end up with the three sums of row r4 + g
+        float q[6], r[3];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float mine = b4 ? p[6 + i] : p[i], other = b4 ? p[i] : p[6 + i];
+            q[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float mine = b3 ? q[3 + i] : q[i], other = b3 ? q[i] : q[3 + i];
+            r[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
+        }
+        if ((lane & 7) == 0 && r4 + grp < nrows) {
+            sd[0][r4 + grp] = r[0];
+            sd[1][r4 + grp] = r[1];
+            sd[2][r4 + grp] = r[2];
+        }
+    }
     const float bc = __ldg(b_cls), bl0 = __ldg(b_loc), bl1 = __ldg(b_loc + 1);
     __syncthreads();
     const int S = scales.n;
-    for (int i = warp; i < 128; i += 8) {
+    for (int idx = tid; idx < 128 * S; idx += 256) {
+        const int i = idx / S, si = idx - i * S;
         const int t = t0 + i;
         if (t >= vi.T) break;
-        for (int si = 0; si < S; ++si) {
-            const int sc = scales.s[si];
-            const float* p = smem + (i + halo - sc / 2) * kHidden + lane * 4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = 0; j < sc; ++j) {
-                const float4 x = lds4(p + j * kHidden);
-                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-            }
-            const float div = (float)sc;
-            a.x /= div; a.y /= div; a.z /= div; a.w /= div;
-            float dc = fmaf(a.x, wc.x, fmaf(a.y, wc.y, fmaf(a.z, wc.z, a.w * wc.w)));
-            float d0 = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w0.z, a.w * w0.w)));
-            float d1 = fmaf(a.x, w1.x, fmaf(a.y, w1.y, fmaf(a.z, w1.z, a.w * w1.w)));
-            dc = warp_sum(dc); d0 = warp_sum(d0); d1 = warp_sum(d1);
-            if (lane == 0) {
-                const size_t o = (size_t)(vi.row0 + t) * S + si;
-                pred_cls[o] = 1.f / (1.f + expf(-(dc + bc)));
-                pred_loc[o * 2 + 0] = d0 + bl0;
-                pred_loc[o * 2 + 1] = d1 + bl1;
-            }
-        }
+        const int sc = scales.s[si];
+        const int base = i + halo - sc / 2;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int j = 0; j < sc; ++j) { a0 += sd[0][base + j]; a1 += sd[1][base + j]; a2 += sd[2][base + j]; }
+        const float div = (float)sc;
+        const size_t o = (size_t)(vi.row0 + t) * S + si;
+        pred_cls[o] = 1.f / (1.f + expf(-(a0 / div + bc)));
+        pred_loc[o * 2 + 0] = a1 / div + bl0;
+        pred_loc[o * 2 + 1] = a2 / div + bl1;
     }
 }
