@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--scales", type=int, nargs="+", default=[12])
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--chunk-rows", type=int, default=32768, help="rows per chunk of the host->device pipeline (e2e)")
-    ap.add_argument("--device-chunk-rows", type=int, default=262144, help="rows per launch sequence, device-resident arm")
+    ap.add_argument("--device-chunk-rows", type=int, default=524288, help="rows per launch sequence, device-resident arm")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
