@@ -176,9 +176,10 @@ constexpr int kA3Stage = 8 * 8192;                                          // k
 constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4;                   // key scales [2 stages][4][64] + pair exchange
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
-// 288 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
-// 32..63), warp 8 = TMA producer.
-__global__ void __launch_bounds__(288, 1)
+// 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
+// 32..63), warp 8 = TMA producer, warp 9 = MMA issuer (told by mbarriers when S has been read out / P is in place, so
+// the row warps never wait for an issue loop).
+__global__ void __launch_bounds__(320, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
               float* __restrict__ a3v) {
@@ -188,8 +189,10 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     constexpr int oQl = 0, oKV = 32768, oP = 32768 + 2 * kA3Stage, oVec = oP + 32768;
     float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
     float* s_pair = sc_vec + 2 * 4 * 64;                                    // [2 halves][128 rows]
-    const uint32_t bars = base + oVec + kA3VecBytes;                          // full[2] empty[2] mma
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kA3VecBytes + 64);
+    // barriers: K full[2] +0, K empty[2] +16, S done +32, P.V done +40, V full[2] +48, V empty[2] +64, S read out +80,
+    // P in place +88; TMEM slot +96
+    const uint32_t bars = base + oVec + kA3VecBytes;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kA3VecBytes + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pair = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
@@ -197,12 +200,17 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int h0 = pair * 2;
 
     if (tid == 0) {
-        mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // full
-        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // empty
-        mbar_init(bars + 32, 1);                                            // mma
+        mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
+        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // K empty
+        mbar_init(bars + 32, 1);                                            // S products done
+        mbar_init(bars + 40, 1);                                            // P.V products done
+        mbar_init(bars + 48, 1); mbar_init(bars + 56, 1);                   // V full
+        mbar_init(bars + 64, 1); mbar_init(bars + 72, 1);                   // V empty
+        mbar_init(bars + 80, 256);                                          // every row thread has read S
+        mbar_init(bars + 88, 256);                                          // every row thread has stored P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(bars + 64, 512);
+    if (warp == 8) tmem_alloc(bars + 96, 512);
     float inv_ql = 1.f;
     if (tid < 128) {
         // landmark queries of both heads -> A operand planes (row t), per-row scale
@@ -227,19 +235,60 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 
     if (warp == 8) {
         if (lane == 0) {
-            // ---- TMA producer: 8 boxes of 64 rows x 64 columns per tile ----
-            for (int i = 0; i < n_tiles; ++i) {
+            // ---- TMA producer: 8 boxes of 64 rows x 64 columns per tile.  The K half of a stage is released by the
+            // S products, the V half by the P.V products, so the K tiles run one tile further ahead than the V tiles ----
+            bool pok = true;
+            for (int i = 0; i < n_tiles && pok; ++i) {
                 const int s = i & 1;
-                if (!mbar_wait(bars + 16 + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u)) break;
+                const uint32_t ph = ((uint32_t)(i >> 1) & 1u) ^ 1u;
                 const uint32_t st = base + oKV + s * kA3Stage;
-                mbar_expect_tx(bars + 8 * s, kA3Stage);
                 const int row = vi.row0 + i * 64;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {                               // k_h0 k_h1 v_h0 v_h1
-                    const int col = (1 + (b >> 1)) * kInner + (h0 + (b & 1)) * kDimHead;
-                    tma_load_2d(st + b * 16384, &map_hi, bars + 8 * s, col, row);
-                    tma_load_2d(st + b * 16384 + 8192, &map_lo, bars + 8 * s, col, row);
+                for (int kv = 0; kv < 2; ++kv) {                            // 0: k_h0 k_h1, 1: v_h0 v_h1
+                    const uint32_t full = bars + (kv ? 48 : 0) + 8 * s, empty = bars + (kv ? 64 : 16) + 8 * s;
+                    if (!pok || !mbar_wait(empty, ph)) { pok = false; continue; }
+                    mbar_expect_tx(full, kA3Stage / 2);
+#pragma unroll
+                    for (int b = 2 * kv; b < 2 * kv + 2; ++b) {
+                        const int col = (1 + (b >> 1)) * kInner + (h0 + (b & 1)) * kDimHead;
+                        tma_load_2d(st + b * 16384, &map_hi, full, col, row);
+                        tma_load_2d(st + b * 16384 + 8192, &map_lo, full, col, row);
+                    }
                 }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ---- MMA issuer: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
+            bool mok = true;
+            auto issue_s = [&](int i) {
+                const int s1 = i & 1;
+                mok = mbar_wait(bars + 8 * s1, (uint32_t)(i >> 1) & 1u) && mok;         // K of that tile has landed
+                tc_fence_after();
+                const uint32_t st1 = base + oKV + s1 * kA3Stage;
+                issue_split_mma64<false>(tmem_base, tmem_base + 64u, base + oQl, base + oQl + 16384, st1, st1 + 8192);
+                issue_split_mma64<false>(tmem_base + 128u, tmem_base + 192u, base + oQl, base + oQl + 16384,
+                                         st1 + 16384, st1 + 16384 + 8192);
+                umma_commit(bars + 32);
+                umma_commit(bars + 16 + 8 * s1);                            // K half of the stage free after the S products
+            };
+            if (n_tiles > 0) issue_s(0);
+            for (int i = 0; i < n_tiles && mok; ++i) {
+                const int s = i & 1;
+                const uint32_t st = base + oKV + s * kA3Stage;
+                if (i + 1 < n_tiles) {
+                    mok = mbar_wait(bars + 80, (uint32_t)i & 1u) && mok;    // S(i) is in registers everywhere
+                    issue_s(i + 1);
+                }
+                mok = mbar_wait(bars + 48 + 8 * s, (uint32_t)(i >> 1) & 1u) && mok;     // V of this tile has landed
+                mok = mbar_wait(bars + 88, (uint32_t)i & 1u) && mok;        // P(i) stored, O(i-1) read by everyone
+                tc_fence_after();
+                issue_split_mma64<true>(tmem_base + 256u, tmem_base + 320u, base + oP, base + oP + 16384,
+                                        st + 32768, st + 32768 + 8192);
+                issue_split_mma64<true>(tmem_base + 384u, tmem_base + 448u, base + oP, base + oP + 16384,
+                                        st + 49152, st + 49152 + 8192);
+                umma_commit(bars + 40);
+                umma_commit(bars + 64 + 8 * s);                             // V half of the stage free after P.V
             }
         }
     } else {
@@ -253,12 +302,25 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int d = 0; d < 32; ++d) o[d] = 0.f;
         // running max is shared by the two threads of a row; the running sum is per thread (its keys) and merged at the end
         float run_max = vi.pad > 0 ? 0.f : -INFINITY, run_sum = half == 0 ? (float)vi.pad : 0.f;
-        uint32_t mma_phase = 0;
+        // Software pipeline over the key tiles: S(i+1) is issued as soon as every thread has pulled S(i) out of TMEM,
+        // so it runs under the softmax of tile i; the P.V product of tile i is only collected in iteration i+1, after
+        // that tile's softmax arithmetic, so it runs under the S read-out and the exponentials of tile i+1.
+        uint32_t s_phase = 0, pv_phase = 0;
+        float alpha_prev = 1.f, inv_p_prev = 1.f;
         bool ok = true;
         named_bar_sync(1, 256);                                             // everyone has read inv_ql out of s_pair
+        auto collect_pv = [&]() {
+            ok = mbar_wait(bars + 40, pv_phase) && ok;
+            pv_phase ^= 1u;
+            tc_fence_after();
+            float pv[32];
+            tmem_read32_sum(tO, tO + 64u, pv);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha_prev, pv[d] * inv_p_prev);
+        };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
-            // prefetch the next tile's scales (written to the other stage's slot at the end of this iteration)
+            // prefetch the next tile's scales (written to the other stage's slot below)
             float nsc0 = 0.f, nsc1 = 0.f;
             if (tid < 128) {
                 const int key = (i + 1) * 64 + (tid & 63), part = 1 + (tid >> 6);
@@ -267,17 +329,9 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                     nsc0 = __ldg(ip); nsc1 = __ldg(ip + 1);
                 }
             }
-            ok = mbar_wait(bars + 8 * s, (uint32_t)(i >> 1) & 1u);
             const uint32_t st = base + oKV + s * kA3Stage;
-            if (tid == 0) {
-                tc_fence_after();
-                issue_split_mma64<false>(tmem_base, tmem_base + 64u, base + oQl, base + oQl + 16384, st, st + 8192);
-                issue_split_mma64<false>(tmem_base + 128u, tmem_base + 192u, base + oQl, base + oQl + 16384,
-                                         st + 16384, st + 16384 + 8192);
-                umma_commit(bars + 32);
-            }
-            ok = ok && mbar_wait(bars + 32, mma_phase);
-            mma_phase ^= 1u;
+            ok = mbar_wait(bars + 32, s_phase) && ok;
+            s_phase ^= 1u;
             tc_fence_after();
             // ---- this thread's 32 logits of its row ----
             float p[32];
@@ -295,7 +349,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             for (int j = 0; j < 64; ++j) vmx = fmaxf(vmx, sc_vec[(s * 4 + 2 + hh) * 64 + j]);   // same for both halves
             s_pair[half * 128 + row] = mx;
             tc_fence_before();
+            mbar_arrive(bars + 80);                                         // this thread holds its S(i) values
             named_bar_sync(1, 256);
+            // next tile's scales into the other stage's slot: its previous readers (tile i-1) are past their last barrier
+            if (tid < 128) {
+                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
+                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
+            }
             const float new_max = fmaxf(run_max, fmaxf(mx, s_pair[(half ^ 1) * 128 + row]));
             const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
             float ps = 0.f;
@@ -307,37 +367,19 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             }
             run_sum = run_sum * alpha + ps;
             run_max = new_max;
+            // the previous tile's P.V product: its P tile and O accumulator are about to be reused
+            if (i > 0) collect_pv();
             // P' <= max_j isv[j]: one row scale for both halves without another exchange
             const int ep = scale_exp(vmx);
             store_row32(g + oP, g + oP + 16384, row, half * 4, p, ldexpf(1.f, ep));
             fence_proxy_async();
             tc_fence_before();
-            named_bar_sync(1, 256);
-            if (tid == 0) {
-                tc_fence_after();
-                issue_split_mma64<true>(tmem_base + 256u, tmem_base + 320u, base + oP, base + oP + 16384,
-                                        st + 32768, st + 32768 + 8192);
-                issue_split_mma64<true>(tmem_base + 384u, tmem_base + 448u, base + oP, base + oP + 16384,
-                                        st + 49152, st + 49152 + 8192);
-                umma_commit(bars + 32);
-                umma_commit(bars + 16 + 8 * s);                             // K/V stage free once these MMAs are done
-            }
-            // next tile's scales into the other stage's slot (its previous readers finished before the barrier above)
-            if (tid < 128) {
-                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
-                sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
-            }
-            ok = ok && mbar_wait(bars + 32, mma_phase);
-            mma_phase ^= 1u;
-            tc_fence_after();
-            float pv[32];
-            tmem_read32_sum(tO, tO + 64u, pv);
-            const float inv_p = ldexpf(1.f, -ep);
-#pragma unroll
-            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha, pv[d] * inv_p);
-            tc_fence_before();
-            named_bar_sync(1, 256);          // scales visible; everyone is done with S / O before the next tile's MMAs
+            mbar_arrive(bars + 88);                                         // P(i) stored, O(i-1) read
+            named_bar_sync(1, 256);                                         // scale slots / s_pair reusable
+            alpha_prev = alpha;
+            inv_p_prev = ldexpf(1.f, -ep);
         }
+        if (n_tiles > 0 && ok) collect_pv();
         // merge the two partial sums of the row
         s_pair[half * 128 + row] = run_sum;
         named_bar_sync(1, 256);

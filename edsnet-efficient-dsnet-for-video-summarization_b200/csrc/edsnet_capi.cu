@@ -196,7 +196,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     }
     {
         StageScope scope(ST_A3V, st);
-        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 288, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
+        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 320, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
         else a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
         CU_CHECK(cudaGetLastError(), "a3v_kernel");
     }
