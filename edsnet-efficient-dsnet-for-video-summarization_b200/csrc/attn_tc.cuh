@@ -405,9 +405,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 constexpr int kAoVecBytes = 64 * 4 + 4 * 128 * 4;                            // inv_kl [64] + pair exchange max / sum [2][128] each
 constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + kAoVecBytes + 128 + 1024;
 
-// 288 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: landmarks / output columns
-// 0..31 and 32..63), warp 8 = TMA producer.
-__global__ void __launch_bounds__(288, 2)
+// 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: landmarks / output columns
+// 0..31 and 32..63), warp 8 = TMA producer, warp 9 = MMA issuer.  The row tiles are independent, so S(i+1) is issued as
+// soon as S(i) has been read out (if its q tile has landed, else right after P.V(i)), and the P.V product of tile i is
+// collected and stored one iteration later, under the softmax of tile i+1.
+__global__ void __launch_bounds__(320, 2)
 attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ k_land,
                    const float* __restrict__ w_mat, float* __restrict__ attn) {
@@ -419,8 +421,9 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     float* s_pmax = inv_kl + 64;                                            // [2][128]
     float* s_psum = s_pmax + 256;                                           // [2][128]
     unsigned* s_wmax = reinterpret_cast<unsigned*>(g + oVec + kAoVecBytes);
-    const uint32_t bars = base + oVec + kAoVecBytes + 16;                     // full[2] empty[2] mma
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kAoVecBytes + 16 + 48);
+    // barriers: full[2] +0, empty[2] +16, S done +32, P.V done +40, S read out +48, P in place +56; TMEM slot +64
+    const uint32_t bars = base + oVec + kAoVecBytes + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kAoVecBytes + 16 + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
@@ -430,11 +433,12 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     if (tid == 0) {
         mbar_init(bars, 1); mbar_init(bars + 8, 1);
         mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);
-        mbar_init(bars + 32, 1);
+        mbar_init(bars + 32, 1); mbar_init(bars + 40, 1);
+        mbar_init(bars + 48, 256); mbar_init(bars + 56, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *s_wmax = 0u;
     }
-    if (warp == 8) tmem_alloc(bars + 48, 256);
+    if (warp == 8) tmem_alloc(bars + 64, 256);
     __syncthreads();
     float wrow[64];
     if (tid < 64) {
@@ -470,69 +474,99 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 tma_load_2d(st + 24576, &map_lo, bars + 8 * s, col, row + 64);
             }
         }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            bool mok = true;
+            auto issue_s = [&](int i) {
+                const uint32_t st = base + oQ + (i & 1) * 32768;
+                tc_fence_after();
+                issue_split_mma64<false>(tmem_base, tmem_base + 64u, st, st + 16384, base + oK, base + oK + 8192);
+                umma_commit(bars + 32);
+            };
+            if (n_tiles > 0) {
+                mok = mbar_wait(bars, 0u);
+                issue_s(0);
+            }
+            for (int i = 0; i < n_tiles && mok; ++i) {
+                const int s = i & 1;
+                const uint32_t st = base + oQ + s * 32768;
+                bool next_issued = i + 1 >= n_tiles;
+                const uint32_t full_next = bars + 8 * ((i + 1) & 1), ph_next = (uint32_t)((i + 1) >> 1) & 1u;
+                mok = mbar_wait(bars + 48, (uint32_t)i & 1u) && mok;        // S(i) is in registers everywhere
+                if (!next_issued && mbar_try_wait(full_next, ph_next)) {
+                    issue_s(i + 1);
+                    next_issued = true;
+                }
+                mok = mbar_wait(bars + 56, (uint32_t)i & 1u) && mok;        // P(i) in its q stage, O(i-1) read out
+                tc_fence_after();
+                issue_split_mma64<true>(tmem_base + 128u, tmem_base + 192u, st, st + 16384, base + oW, base + oW + 8192);
+                umma_commit(bars + 40);
+                umma_commit(bars + 16 + 8 * s);                             // stage free once P has been consumed
+                if (!next_issued) {
+                    mok = mbar_wait(full_next, ph_next) && mok;
+                    issue_s(i + 1);
+                }
+            }
+        }
     } else {
         const int trow = tid & 127, half = tid >> 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_addr + (uint32_t)(half * 32), tO = tS + 128u;
         const float o_scale = ldexpf(1.f, -ew) * (1.f / 16384.f);
-        uint32_t mma_phase = 0;
+        uint32_t s_phase = 0, pv_phase = 0;
         bool ok = true;
         float inv_q = trow < vi.T ? __ldg(inv + (size_t)(vi.row0 + trow) * 24 + h) : 0.f;
+        float rs_prev = 0.f;
+        // P.V product of tile j: read out, scale by the row's 1 / sum, store
+        auto collect = [&](int j, float rs) {
+            ok = mbar_wait(bars + 40, pv_phase) && ok;
+            pv_phase ^= 1u;
+            tc_fence_after();
+            float ov[32];
+            tmem_read32_sum(tO, tO + 64u, ov);
+            const int row = j * 128 + trow;
+            if (row < vi.T) {
+                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    st4(dst + c, make_float4(ov[c] * rs, ov[c + 1] * rs, ov[c + 2] * rs, ov[c + 3] * rs));
+            }
+        };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
             const int row = i * 128 + trow;
             const float inv_q_next = (row + 128 < vi.T) ? __ldg(inv + (size_t)(vi.row0 + row + 128) * 24 + h) : 0.f;
-            ok = mbar_wait(bars + 8 * s, (uint32_t)(i >> 1) & 1u);
-            const uint32_t st = base + oQ + s * 32768;
             unsigned char* stp = g + oQ + s * 32768;
-            if (tid == 0) {
-                tc_fence_after();
-                issue_split_mma64<false>(tmem_base, tmem_base + 64u, st, st + 16384, base + oK, base + oK + 8192);
-                umma_commit(bars + 32);
-            }
-            ok = ok && mbar_wait(bars + 32, mma_phase);
-            mma_phase ^= 1u;
+            ok = mbar_wait(bars + 32, s_phase) && ok;
+            s_phase ^= 1u;
             tc_fence_after();
             float p[32];
             tmem_read32_sum(tS, tS + 64u, p);
+            tc_fence_before();
+            mbar_arrive(bars + 48);                                         // this thread holds its S(i) values
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { p[j] *= inv_q * inv_kl[half * 32 + j]; mx = fmaxf(mx, p[j]); }
             s_pmax[half * 128 + trow] = mx;
-            tc_fence_before();
             named_bar_sync(1, 256);
             mx = fmaxf(mx, s_pmax[(half ^ 1) * 128 + trow]);
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
             s_psum[half * 128 + trow] = sum;
+            // the previous tile's output: its accumulator is about to be overwritten by P.V(i)
+            if (i > 0) collect(i - 1, rs_prev);
             // un-normalised probabilities (<= 1, fixed scale 2^14); the row sum divides the output instead
             store_row32(stp, stp + 16384, trow, half * 4, p, 16384.f);
             fence_proxy_async();
             tc_fence_before();
-            named_bar_sync(1, 256);
-            if (tid == 0) {
-                tc_fence_after();
-                issue_split_mma64<true>(tmem_base + 128u, tmem_base + 192u, st, st + 16384, base + oW, base + oW + 8192);
-                umma_commit(bars + 32);
-                umma_commit(bars + 16 + 8 * s);                             // stage free once P has been consumed
-            }
-            const float rs = o_scale / (sum + s_psum[(half ^ 1) * 128 + trow]);
-            ok = ok && mbar_wait(bars + 32, mma_phase);
-            mma_phase ^= 1u;
-            tc_fence_after();
-            float ov[32];
-            tmem_read32_sum(tO, tO + 64u, ov);
-            if (row < vi.T) {
-                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    st4(dst + j, make_float4(ov[j] * rs, ov[j + 1] * rs, ov[j + 2] * rs, ov[j + 3] * rs));
-            }
+            mbar_arrive(bars + 56);                                         // P(i) stored, O(i-1) read out
+            named_bar_sync(1, 256);                                         // partner's row sum visible
+            rs_prev = o_scale / (sum + s_psum[(half ^ 1) * 128 + trow]);
             inv_q = inv_q_next;
-            tc_fence_before();
-            named_bar_sync(1, 256);          // all rows done with S / O before the next tile's MMAs overwrite them
         }
+        if (n_tiles > 0 && ok) collect(n_tiles - 1, rs_prev);
     }
     tc_fence_before();
     __syncthreads();

@@ -209,7 +209,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     if (tcp) {
         {
             StageScope scope(ST_ATTN_OUT, st);
-            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 288, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 320, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
                                                                                   k_land, wmat, merged);
             CU_CHECK(cudaGetLastError(), "attn_out_tc_kernel");
         }
