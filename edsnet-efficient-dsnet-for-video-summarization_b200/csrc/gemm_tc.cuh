@@ -294,7 +294,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + Cfg::kBufs + b); };
-    constexpr int kSlotOff = 8 * (2 * STAGES + 2 * Cfg::kBufs);
+    // four single-buffered accumulators: accumulators 0 and 3 (first K block: hi.hi and the cross terms) are handed
+    // back to the MMA warp half way through the drain, 1 and 2 at its end (tempty2)
+    constexpr bool kPhased = ACCS == 4 && Cfg::kBufs == 1;
+    const uint32_t tempty2_bar = bar_base + 8u * (2 * STAGES + 2 * Cfg::kBufs);
+    constexpr int kSlotOff = 8 * (2 * STAGES + 2 * Cfg::kBufs + 1);
     const uint32_t tmem_slot = bar_base + kSlotOff;
     unsigned char* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * Cfg::kStageBytes + kSlotOff);
@@ -311,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < Cfg::kBufs; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), Cfg::kEpiWarps); }
+        mbar_init(tempty2_bar, Cfg::kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -358,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int s = it % STAGES;
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     ok = mbar_wait(full_bar(s), ph);
+                    if (kPhased && kb == 1) ok = mbar_wait(tempty2_bar, tph ^ 1u) && ok;   // accumulators 1, 2 drained
                     tc_fence_after();
                     const uint32_t st = smem_base + s * Cfg::kStageBytes;
                     const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
@@ -399,6 +405,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 (uint32_t)(chalf * 64);
             const int nc0 = n0 + chalf * 64;                         // first global column of this thread
             float v[64];
+            if (kPhased) {
+                // (acc0 + acc3) first, hand those two back, then + (acc1 + acc2); every add rounded to nearest
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t r0[16], r3[16];
+                    tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
+                    tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r3[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                if (n_main > 1) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        uint32_t r1[16], r2[16];
+                        tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
+                        if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a12 = n_main > 2 ? __fadd_rn(__uint_as_float(r1[j]), __uint_as_float(r2[j]))
+                                                         : __uint_as_float(r1[j]);
+                            v[c0 + j] = __fadd_rn(v[c0 + j], a12);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty2_bar);
+            } else {
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 uint32_t r0[16];
@@ -434,6 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+            }
             if (EPI == EPI_QKV_PLANES) {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 epi_store_planes(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
