@@ -143,6 +143,11 @@ class DSNet(nn.Module):
         return _capi.make_config(self.anchor_scales, self.fc_depth, _capi.PRECISIONS[self.precision],
                                  _capi.BASE_MODELS[self.base_model_type])
 
+    def invalidate_weight_cache(self):
+        """Forget the cached fp16 operand planes.  Needed after parameter updates that do not bump the tensors'
+        version counters (CUDA-graph replays of an optimiser step)."""
+        self._wkey = None
+
     def _weights(self, device, stream: int) -> _capi.Weights:
         named = self._named_weights()
         key = (self.precision, str(device)) + tuple((n, p.data_ptr(), p._version) for n, p in named.items())

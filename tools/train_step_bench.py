@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--videos-per-rank", type=int, default=1)
     ap.add_argument("--scales", type=int, nargs="+", default=[4, 8, 16, 32])
     ap.add_argument("--cpu", action="store_true", help="also time the same step on the host cores")
+    ap.add_argument("--graphs", action="store_true", help="replay the step as CUDA graphs (GraphedDataParallelStep)")
     args = ap.parse_args()
     rank, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -58,7 +59,7 @@ def main():
     rng = np.random.default_rng(bench.SEED + rank)
     vids = synth_split(40, rng)
     feats = [bench.synth_features_device(T, dev, 7000 + 100 * rank + i) for i, (T, _) in enumerate(vids)]
-    stepper = tr.DataParallelStep(model, world_size=world)
+    stepper = (tr.GraphedDataParallelStep if args.graphs else tr.DataParallelStep)(model, world_size=world)
     k = args.videos_per_rank
     label_s = [0.0]
 
@@ -71,7 +72,7 @@ def main():
         loc_l = [torch.from_numpy(l).float().to(dev, non_blocking=True) for _, l in labs]
         return stepper.step([feats[s] for s in sel], cls_l, loc_l)
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 2 * len(vids) // k + 2 if args.graphs else 0)):     # graphs: every video seen twice
         one_step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -95,7 +96,8 @@ def main():
             "videos_per_sec": world * k * args.steps / (ms * 1e-3),
             "host_label_ms_per_step": 1e3 * label_s[0] / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
             "loss_first": float(np.mean(losses[:5])), "loss_last": float(np.mean(losses[-5:])),
-            "grad_allreduce": "one flat fp32 bucket (NCCL)" if world > 1 else "none (1 GPU)"}
+            "grad_allreduce": "one flat fp32 bucket (NCCL)" if world > 1 else "none (1 GPU)",
+            "cuda_graphs": bool(args.graphs)}
     if args.cpu and rank == 0 and world == 1:
         cpu_model = bench.xavier_state(args.scales)
         cpu_model.train()
