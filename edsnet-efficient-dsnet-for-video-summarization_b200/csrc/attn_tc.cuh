@@ -580,10 +580,15 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 // heads stacked along M) and as right operand (MN-major, the two heads side by side along N, LBO = 8 KB): each
 // 128 x 128 product holds the two wanted 64 x 64 products on its block diagonal, thread t reads row t of its own block.
 // Per product: row -> registers -> (7I - ., 15I - ., ...) -> matrix max (shuffle + one barrier) -> planes -> MMA.
-// grid (4 head pairs, V), 256 threads, 5 tiles = 160 KB shared memory, TMEM 256 columns (main | cross).
+// grid (4 head pairs, V), 256 threads, TMEM 256 columns (main | cross).  Only THREE tiles live in shared memory: Z, a
+// tile Q that is A during the first product of an iteration and XZ afterwards, and a tile P that is in turn T1, U, T2
+// and a3v (a product's result may overwrite an operand once the MMAs have completed).  A's planes are parked in
+// global memory by the prologue (in the video's zmat slot, 32 KB per head pair, overwritten by Z at the end) and
+// copied back into Q under the third product of every iteration.  96 KB per CTA: TWO CTAs share an SM, and one
+// chain's MMA / barrier latencies are covered by the other's.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPinvTile = 32768;
-constexpr int kPinvTcSmemBytes = 5 * kPinvTile + 256 + 1024;
+constexpr int kPinvTcSmemBytes = 3 * kPinvTile + 256 + 1024;
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn2(uint32_t addr) {      // two MN atoms, 8 KB apart
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -604,13 +609,13 @@ __device__ __forceinline__ void issue_pinv_product(uint32_t tmem_base, uint32_t 
 // 256 threads: thread t and t + 128 share accumulator row (t & 127); the first owns columns 0..31 of its head's block,
 // the second columns 32..63 (warps w and w + 4 may touch the same TMEM lane quarter).  Two warps per scheduler keep
 // the dependent chain's ALU latency covered.
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
                  float* __restrict__ w_out, float* __restrict__ z_out, int iters) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
-    constexpr int oA = 0, oZ = kPinvTile, oXZ = 2 * kPinvTile, oT = 3 * kPinvTile, oU = 4 * kPinvTile, oVec = 5 * kPinvTile;
+    constexpr int oZ = 0, oQ = kPinvTile, oP = 2 * kPinvTile, oVec = 3 * kPinvTile;
     float* s_mx = reinterpret_cast<float*>(g + oVec);                       // [2 parities][2 slots][8 warps]
     const uint32_t bar = base + oVec + 128;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + 144);
@@ -652,7 +657,9 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
         store_row32(g + o, g + o + 16384, row, half * 4, r, unscale * ldexpf(1.f, e));
         return ldexpf(1.f, -e);
     };
-    auto product = [&](int left, int right, float (&out)[32]) {
+    // A's planes parked in global memory: this CTA's 32 KB slot, same byte layout as the shared-memory tile
+    uint4* a_park = reinterpret_cast<uint4*>(z_out + ((size_t)v * kHeads + blockIdx.x * 2) * 4096);
+    auto product = [&](int left, int right, float (&out)[32], bool reload_a) {
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -661,9 +668,19 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
             issue_pinv_product(tmem_base, base + left, base + right);
             umma_commit(bar);
         }
+        uint4 a_copy[8];
+        if (reload_a) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a_copy[k] = a_park[k * 256 + tid];       // in flight under the MMAs
+        }
         ok = mbar_wait(bar, phase) && ok;
         phase ^= 1u;
         tc_fence_after();
+        if (reload_a) {
+            // the product that just completed was the last reader of XZ: tile Q takes A again for the next iteration
+#pragma unroll
+            for (int k = 0; k < 8; ++k) reinterpret_cast<uint4*>(g + oQ)[k * 256 + tid] = a_copy[k];
+        }
 #pragma unroll
         for (int q = 0; q < 32; q += 16) {
             uint32_t r0[16], r1[16];
@@ -699,33 +716,37 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
     for (int j = 0; j < 32; ++j) z[j] = __ldg(attn2 + off + (c0 + j) * 64 + i) / denom;    // row i of A^T
     float mA, mZ;
     head_max2(absmax32(t), absmax32(z), mA, mZ);
-    const float invA = put(oA, t, 1.f, mA);
+    const float invA = put(oQ, t, 1.f, mA);
     float invZ = put(oZ, z, 1.f, mZ);
+    __syncthreads();
+    // park A's planes (the attn2 rows above were the last reads of anything this slot could alias)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a_park[k * 256 + tid] = reinterpret_cast<const uint4*>(g + oQ)[k * 256 + tid];
 
     for (int it = 0; it < iters && ok; ++it) {
         // XZ = A Z ; T1 = 7I - XZ
         float xz[32];
-        product(oA, oZ, xz);
+        product(oQ, oZ, xz, false);
         const float sXZ = invA * invZ;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { xz[j] *= sXZ; t[j] = (has_diag && j == i - c0 ? 7.f : 0.f) - xz[j]; }
         float mXZ, mT;
         head_max2(absmax32(xz), absmax32(t), mXZ, mT);
-        const float invXZ = put(oXZ, xz, 1.f, mXZ);
-        float invT = put(oT, t, 1.f, mT);
+        const float invXZ = put(oQ, xz, 1.f, mXZ);
+        float invT = put(oP, t, 1.f, mT);
         // U = 15I - XZ T1
-        product(oXZ, oT, t);
+        product(oQ, oP, t, false);
         diag_minus(t, invXZ * invT, 15.f);
         float mU, dummy;
         head_max2(absmax32(t), 0.f, mU, dummy);
-        const float invU = put(oU, t, 1.f, mU);
-        // T2 = 13I - XZ U
-        product(oXZ, oU, t);
+        const float invU = put(oP, t, 1.f, mU);
+        // T2 = 13I - XZ U   (XZ's last use: A comes back into its tile)
+        product(oQ, oP, t, it + 1 < iters);
         diag_minus(t, invXZ * invU, 13.f);
         head_max2(absmax32(t), 0.f, mT, dummy);
-        invT = put(oT, t, 1.f, mT);
+        invT = put(oP, t, 1.f, mT);
         // Z' = 0.25 Z T2
-        product(oZ, oT, z);
+        product(oZ, oP, z, false);
         const float sZ = 0.25f * invZ * invT;
 #pragma unroll
         for (int j = 0; j < 32; ++j) z[j] *= sZ;
@@ -744,8 +765,8 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
     }
     float mV, dummy2;
     head_max2(absmax32(t), 0.f, mV, dummy2);
-    const float invV = put(oU, t, 1.f, mV);
-    product(oZ, oU, t);
+    const float invV = put(oP, t, 1.f, mV);
+    product(oZ, oP, t, false);
     if (ok) {
         const float sW = invZ * invV;
 #pragma unroll
