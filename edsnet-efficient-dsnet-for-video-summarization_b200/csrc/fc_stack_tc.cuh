@@ -17,7 +17,8 @@ namespace tc {
 constexpr int kFcTile = 128;                                  // rows per warpgroup tile
 constexpr int kFcPlane = 128 * 128 * 2;                       // bytes of one fp16 128x128 plane
 // W hi | W lo | A hi (wg0) | A lo (wg0) | A hi (wg1) | A lo (wg1) | vectors | barriers
-constexpr int kFcSmemBytes = 6 * kFcPlane + 4 * 128 * 4 + 64 + 1024;
+constexpr int kFcXchBytes = 2 * 3 * 2 * 128 * 2 * 4;           // [group][slot][half][row][2] floats
+constexpr int kFcSmemBytes = 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes + 64 + 1024;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -30,7 +31,14 @@ __device__ __forceinline__ uint32_t fc_plane_off(int r, int c16) {
     return (uint32_t)((c16 >> 3) * 16384 + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// 512 threads = two groups of 256; a group owns a stream of 128-row tiles.  Thread t and t + 128 of a group share tile
+// row (t & 127): the first holds columns 0..63 of the 128-value row, the second 64..127 (warps w and w + 4 touch the
+// same TMEM lane quarter).  What the two halves of a row must agree on goes through a small exchange buffer and the
+// group's named barrier: the row maximum that picks the plane scale of the first layer (the later layers' inputs are
+// LayerNorm outputs, bounded by sqrt(127) max|gamma| + max|beta|: one fixed scale, no exchange) and the row sum /
+// sum of squares of every LayerNorm.  Sixteen warps instead of eight keep the per-layer register arithmetic of one
+// group under the other group's MMAs and barriers.
+__global__ void __launch_bounds__(512, 1)
 fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_planes, const float* __restrict__ w_inv_scale,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ u_out, int rows, int depth) {
@@ -39,14 +47,17 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t w_hi = base, w_lo = base + kFcPlane;
     float* vec = reinterpret_cast<float*>(gbase + 6 * kFcPlane);          // wscale[128] bias[128] gamma[128] beta[128]
-    const uint32_t bar0 = base + 6 * kFcPlane + 4 * 128 * 4;               // mbarrier per warpgroup, then the TMEM slot
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 6 * kFcPlane + 4 * 128 * 4 + 16);
+    float* xch = vec + 4 * 128;                                             // [group][slot 0..2][half][row][2]
+    const uint32_t bar0 = base + 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes;  // mbarrier per group, then the TMEM slot
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gbase + 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes + 16);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wg = tid >> 7, wtid = tid & 127;                             // warpgroup, thread within it (= row)
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int grp = tid >> 8, gt = tid & 255;                              // group, thread within it
+    const int trow = gt & 127, half = gt >> 7, cb = half * 64;             // tile row, column half, first column
 
     // ---- one-time setup: weight planes -> swizzled smem, vectors, barriers, TMEM ----
-    for (int idx = tid; idx < 2 * 128 * 16; idx += 256) {
+    for (int idx = tid; idx < 2 * 128 * 16; idx += 512) {
         const int plane = idx >> 11, r = (idx >> 4) & 127, c16 = idx & 15;
         const uint4 val = __ldg(reinterpret_cast<const uint4*>(w_planes + (size_t)plane * 128 * 128 + r * 128 + c16 * 8));
         *reinterpret_cast<uint4*>(gbase + plane * kFcPlane + fc_plane_off(r, c16)) = val;
@@ -68,59 +79,73 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t acc_main = tmem_base + (uint32_t)(wg * 256), acc_lo = acc_main + 128u;
-    const uint32_t a_hi = base + (2 + 2 * wg) * kFcPlane, a_lo = a_hi + kFcPlane;
-    unsigned char* a_hi_ptr = gbase + (2 + 2 * wg) * kFcPlane;
+    const uint32_t acc_main = tmem_base + (uint32_t)(grp * 256), acc_lo = acc_main + 128u;
+    const uint32_t a_hi = base + (2 + 2 * grp) * kFcPlane, a_lo = a_hi + kFcPlane;
+    unsigned char* a_hi_ptr = gbase + (2 + 2 * grp) * kFcPlane;
     unsigned char* a_lo_ptr = a_hi_ptr + kFcPlane;
-    const uint32_t my_bar = bar0 + 8u * wg;
+    const uint32_t my_bar = bar0 + 8u * grp;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     constexpr uint32_t idesc = make_idesc(128, 128);
     const int n_tiles = (rows + kFcTile - 1) / kFcTile;
+    // plane scale of every LayerNorm output: |LN(x)| <= sqrt(127) max|gamma| + max|beta|
+    float gmax = 0.f, bmax = 0.f;
+    for (int j = 0; j < 128; ++j) { gmax = fmaxf(gmax, fabsf(vec[256 + j])); bmax = fmaxf(bmax, fabsf(vec[384 + j])); }
+    const float ln_bound = 11.27f * gmax + bmax;
+    int e_ln = 0;
+    if (ln_bound > 0.f && ln_bound < INFINITY) e_ln = 14 - ilogbf(ln_bound);
+    e_ln = max(-100, min(100, e_ln));
+    float* xg = xch + grp * (3 * 2 * 128 * 2);
     uint32_t phase = 0;
     bool ok = true;
 
-    for (int tile = blockIdx.x * 2 + wg; tile < n_tiles && ok; tile += gridDim.x * 2) {
-        const int row = tile * kFcTile + wtid;
-        float u[128];
+    for (int tile = blockIdx.x * 2 + grp; tile < n_tiles && ok; tile += gridDim.x * 2) {
+        const int row = tile * kFcTile + trow;
+        float u[64];
         if (row < rows) {
-            const float* src = u_in + (size_t)row * kHidden;
+            const float* src = u_in + (size_t)row * kHidden + cb;
 #pragma unroll
-            for (int j = 0; j < 128; j += 4) {
+            for (int j = 0; j < 64; j += 4) {
                 const float4 x = ldg4(src + j);
                 u[j] = x.x; u[j + 1] = x.y; u[j + 2] = x.z; u[j + 3] = x.w;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 128; ++j) u[j] = 0.f;
+            for (int j = 0; j < 64; ++j) u[j] = 0.f;
         }
         for (int layer = 0; layer < depth && ok; ++layer) {
-            // ---- A operand: row -> scaled fp16 hi / lo planes ----
-            float mx = 0.f;
+            // ---- A operand: half row -> scaled fp16 hi / lo planes ----
+            int e = e_ln;
+            if (layer == 0) {
+                float mx = 0.f;
 #pragma unroll
-            for (int j = 0; j < 128; ++j) mx = fmaxf(mx, fabsf(u[j]));
-            int e = 0;
-            if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
-            e = max(-100, min(100, e));
+                for (int j = 0; j < 64; ++j) mx = fmaxf(mx, fabsf(u[j]));
+                xg[(2 * 2 + half) * 256 + trow * 2] = mx;                   // slot 2: row maximum
+                named_bar_sync(1 + grp, 256);
+                mx = fmaxf(mx, xg[(2 * 2 + (half ^ 1)) * 256 + trow * 2]);
+                e = 0;
+                if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+                e = max(-100, min(100, e));
+            }
             const float sc = ldexpf(1.f, e), inv_a = ldexpf(1.f, -e);
 #pragma unroll
-            for (int c16 = 0; c16 < 16; ++c16) {
+            for (int c = 0; c < 8; ++c) {
                 __half2 hh[4], ll[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float v0 = u[c16 * 8 + 2 * q] * sc, v1 = u[c16 * 8 + 2 * q + 1] * sc;
+                    const float v0 = u[c * 8 + 2 * q] * sc, v1 = u[c * 8 + 2 * q + 1] * sc;
                     const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
                     hh[q] = __halves2half2(h0, h1);
                     ll[q] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
                 }
-                const uint32_t off = fc_plane_off(wtid, c16);
+                const uint32_t off = fc_plane_off(trow, half * 8 + c);
                 *reinterpret_cast<uint4*>(a_hi_ptr + off) = *reinterpret_cast<uint4*>(hh);
                 *reinterpret_cast<uint4*>(a_lo_ptr + off) = *reinterpret_cast<uint4*>(ll);
             }
             fence_proxy_async();               // generic-proxy smem writes -> visible to the async (tensor core) proxy
             tc_fence_before();                 // orders this thread's earlier tcgen05.ld before the barrier
-            named_bar_sync(1 + wg, 128);
-            // ---- MMA: one elected thread of the warpgroup ----
-            if (wtid == 0) {
+            named_bar_sync(1 + grp, 256);
+            // ---- MMA: one elected thread of the group ----
+            if (gt == 0) {
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -137,33 +162,38 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
             phase ^= 1u;
             tc_fence_after();
             // ---- epilogue in registers: (main + lo) * scales + bias, ReLU, LayerNorm(128) ----
-            float sum = 0.f;
+            float sum = 0.f, sq = 0.f;
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 16) {
+            for (int c0 = 0; c0 < 64; c0 += 16) {
                 uint32_t r0[16], r1[16];
-                tmem_ld16_nowait(acc_main + lane_addr + (uint32_t)c0, r0);
-                tmem_ld16_nowait(acc_lo + lane_addr + (uint32_t)c0, r1);
+                tmem_ld16_nowait(acc_main + lane_addr + (uint32_t)(cb + c0), r0);
+                tmem_ld16_nowait(acc_lo + lane_addr + (uint32_t)(cb + c0), r1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float acc = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
-                    const float lin = fmaf(acc, inv_a * vec[c0 + j], vec[128 + c0 + j]);
+                    const float lin = fmaf(acc, inv_a * vec[cb + c0 + j], vec[128 + cb + c0 + j]);
                     u[c0 + j] = fmaxf(lin, 0.f);
                     sum += u[c0 + j];
                 }
             }
-            const float mean = sum * (1.f / 128.f);
-            float q = 0.f;
+            // mean over the whole row first, then the centred sum of squares (two exchanges, two-pass variance)
+            float* slot = xg + ((layer & 1) * 2) * 256;
+            slot[half * 256 + trow * 2] = sum;
+            named_bar_sync(1 + grp, 256);
+            const float mean = (sum + slot[(half ^ 1) * 256 + trow * 2]) * (1.f / 128.f);
 #pragma unroll
-            for (int j = 0; j < 128; ++j) { u[j] -= mean; q = fmaf(u[j], u[j], q); }
-            const float rstd = 1.f / sqrtf(q * (1.f / 128.f) + 1e-5f);
+            for (int j = 0; j < 64; ++j) { u[j] -= mean; sq = fmaf(u[j], u[j], sq); }
+            slot[half * 256 + trow * 2 + 1] = sq;
+            named_bar_sync(1 + grp, 256);
+            const float rstd = 1.f / sqrtf((sq + slot[(half ^ 1) * 256 + trow * 2 + 1]) * (1.f / 128.f) + 1e-5f);
 #pragma unroll
-            for (int j = 0; j < 128; ++j) u[j] = fmaf(u[j] * rstd, vec[256 + j], vec[384 + j]);
+            for (int j = 0; j < 64; ++j) u[j] = fmaf(u[j] * rstd, vec[256 + cb + j], vec[384 + cb + j]);
         }
         if (row < rows) {
-            float* dst = u_out + (size_t)row * kHidden;
+            float* dst = u_out + (size_t)row * kHidden + cb;
 #pragma unroll
-            for (int j = 0; j < 128; j += 4) st4(dst + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
+            for (int j = 0; j < 64; j += 4) st4(dst + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
         }
     }
     tc_fence_before();
@@ -184,7 +214,7 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
     }
     const int n_pairs = ((rows + tc::kFcTile - 1) / tc::kFcTile + 1) / 2;
     const int grid = n_pairs < tc::num_sms() ? n_pairs : tc::num_sms();
-    tc::fc_stack_tc_kernel<<<grid, 256, tc::kFcSmemBytes, st>>>(
+    tc::fc_stack_tc_kernel<<<grid, 512, tc::kFcSmemBytes, st>>>(
         u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
         depth);
     return cudaGetLastError();
