@@ -155,7 +155,9 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
 // plane, with qkv_inv [R][24] (gemm_tc.cuh EPI_QKV_PLANES).
 int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, const float* qkv_inv,
                       const float* conv_w, float* q_land, float* k_land, float* attn2, float* stats, float* a3v,
-                      float* zmat, float* wmat, float* merged, cudaStream_t st) {
+                      float* zmat, float* wmat, float* merged, cudaStream_t st, void* merged16 = nullptr) {
+    // merged16 != nullptr (tcgen05 precisions, edsnet_forward): `merged` only carries the attention part and the sum
+    // with the value convolution leaves as the to_out operand planes in merged16 (edsnet_split_f16 layout, 512 columns)
     const bool tcp = precision != EDSNET_PREC_FP32;
     const __half* p_hi = reinterpret_cast<const __half*>(qkv);
     const __half* p_lo = p_hi + (size_t)b->total_rows * kQkvCols;
@@ -170,7 +172,8 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (!tc_attr) {
             CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
-            CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
+            CU_CHECK(opt_in_smem(tc::value_conv_kernel<false>, tc::kConvSmemBytes), "smem opt-in value_conv");
+            CU_CHECK(opt_in_smem(tc::value_conv_kernel<true>, tc::kConvSmemBytes), "smem opt-in value_conv planes");
             CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
             tc_attr = true;
         }
@@ -210,12 +213,24 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         {
             StageScope scope(ST_ATTN_OUT, st);
             tc::attn_out_tc_kernel<<<dim3(kHeads, V), 320, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
-                                                                                  k_land, wmat, merged);
+                                                                                  k_land, wmat, merged,
+                                                                                  merged16 ? stats : nullptr);
             CU_CHECK(cudaGetLastError(), "attn_out_tc_kernel");
         }
         StageScope scope(ST_CONV, st);
-        tc::value_conv_kernel<<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
-            p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged);
+        if (merged16) {
+            // stats [V][8][2] is dead after the pinv kernel: slot 0 of every (video, head) now holds max|W|
+            __half* m_hi = static_cast<__half*>(merged16);
+            __half* m_lo = m_hi + (size_t)b->total_rows * kInner;
+            float* m_inv = reinterpret_cast<float*>(m_lo + (size_t)b->total_rows * kInner);
+            tc::value_conv_kernel<true><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
+                p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, stats,
+                m_hi, m_lo, m_inv);
+        } else {
+            tc::value_conv_kernel<false><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
+                p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, nullptr,
+                nullptr, nullptr, nullptr);
+        }
         CU_CHECK(cudaGetLastError(), "value_conv_kernel");
     } else {
         StageScope scope(ST_ATTN_OUT, st);
@@ -457,17 +472,13 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
                            F(L.qkv), R, kQkvCols, kFeat, nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
         if (rc) return rc;
         // 2. landmark attention core -> merged heads                                (nystroformer.py:95-142)
+        // (tcgen05: the x16 planes are dead after step 1; the front of that region takes merged (R x 512) as planes)
+        void* merged16_out = prec != EDSNET_PREC_FP32 ? static_cast<void*>(ws + L.x16) : nullptr;
         rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
-                               F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st);
+                               F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, merged16_out);
         if (rc) return rc;
         // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
-        const void* merged16 = nullptr;
-        if (prec != EDSNET_PREC_FP32) {
-            // the x16 planes are dead after step 1: reuse the front of that region for merged (R x 512)
-            rc = edsnet_split_f16(F(L.merged), ws + L.x16, R, kInner, stream);
-            if (rc) return rc;
-            merged16 = ws + L.x16;
-        }
+        const void* merged16 = merged16_out;
         rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
                            kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
         if (rc) return rc;
@@ -550,10 +561,10 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
 
 int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
-    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add two operand splits (x,
-    // merged) and run the value convolution as its own kernel
+    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add the operand split of x
+    // (and of merged for the attention base) and run the value convolution as its own kernel
     if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 9;
-    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 14;
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 13;
 }
 
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

@@ -117,8 +117,11 @@ def test_forward_stages_match_oracle(precision):
         print(name, err)
         # the Newton-Schulz chain amplifies rounding differences of an ill-conditioned attn2 (cond ~1e3..1e4)
         assert err < (2e-3 if name == "zmat" else 2e-5), (name, err)
-    merged = view(L.merged, (T, 512))
-    assert orc.rel_l2(merged.numpy(), stages["merged"][pad:].numpy()) < 2e-5
+    if precision == "fp32":
+        # (tcgen05 precisions: merged leaves the value-convolution kernel as the to_out operand planes in a region
+        # the LayerNorm planes overwrite later in the same forward; the stages below depend on it)
+        merged = view(L.merged, (T, 512))
+        assert orc.rel_l2(merged.numpy(), stages["merged"][pad:].numpy()) < 2e-5
     u1 = view(L.u1, (T, 128))
     assert orc.rel_l2(u1.numpy(), stages["hidden"].numpy()) < 2e-5
 
