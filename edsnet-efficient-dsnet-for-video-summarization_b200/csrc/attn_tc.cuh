@@ -893,4 +893,242 @@ value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same value convolution + merge on the tensor cores (tcgen05 precisions, to_out operand planes out).
+// A 33-tap FIR along the rows is a banded Toeplitz product:  conv[r][c] = sum_j Band[r][j] V[j][c] with
+// Band[r][j] = taps[j - r] for 0 <= j - r <= 32 over the 160-row window (rows r0-16 .. r0+143) of a 128-row tile.
+//   * B operand = the v planes themselves: three 64-row TMA boxes per plane straight out of the q|k|v planes
+//     (MN-major, 128-byte swizzle).  Window rows outside the video arrive as whatever neighbours them in the packed
+//     buffer (or as TMA zero fill) and are switched off through the band.
+//   * A operand = Band' = taps[j - r] * 2^-sv[j] * 2^c in shared memory (K-major, 3 K blocks of 64, hi / lo planes):
+//     v's per-row plane scale 2^sv[j] varies along K, where a B operand cannot carry it, so its inverse is folded into
+//     the band column j (a power of two: exact), together with the row mask (0 outside the video).  The band positions
+//     are the same for every tile and head; only the 33 values per row are rewritten (the rest stays zero).
+//   * 12 K steps x {hi.hi -> main; hi.lo, lo.hi -> cross} per head, accumulators double-buffered in TMEM: the MMAs of
+//     head h+1 run under the epilogue of head h (TMEM -> + attention part -> plane scale -> hi / lo planes).
+// One CTA per 128-row tile, all 8 heads; 320 threads: warps 0..7 = rows (two threads per row, 32 columns each),
+// warp 8 = TMA producer, warp 9 = MMA issuer.  The output plane scale is the tile-wide bound of value_conv_kernel<true>.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCvBandBytes = 3 * 32768;                                    // [kb][hi | lo][128 rows][128 B]
+constexpr int kCvVPlane = kConvRowsIn * 128;                                // 160 window rows x 128 B = 20 KB
+constexpr int kCvVStage = 2 * kCvVPlane;                                   // hi | lo
+constexpr int kCvStages = 2;
+constexpr int kCvScratch = 8 * 32 * 20 * 4;                                // per row warp: 32 rows x 16 columns (+4 pad) fp32
+constexpr int kCvVecFloats = kHeads * 192 + kHeads * kTaps + 3 * kHeads + 4;   // inv window, taps, e_c / f-scale, scale
+constexpr int kCvSmemBytes = kCvBandBytes + kCvStages * kCvVStage + kCvScratch + kCvVecFloats * 4 + 128 + 1024;
+
+__global__ void __launch_bounds__(320, 1)
+value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                     const float* __restrict__ inv, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
+                     const float* __restrict__ conv_w, const float* __restrict__ attn, const float* __restrict__ w_max,
+                     __half* __restrict__ m_hi, __half* __restrict__ m_lo, float* __restrict__ m_inv) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
+    constexpr int oBand = 0, oV = kCvBandBytes, oScr = oV + kCvStages * kCvVStage, oVec = oScr + kCvScratch;
+    float* s_inv = reinterpret_cast<float*>(g + oVec);                     // [8 heads][192 window rows], 0 = row masked
+    float* s_w = s_inv + kHeads * 192;                                      // [8][33]
+    float* s_fc = s_w + kHeads * kTaps;                                     // [8] 2^e_c per head
+    float* s_ic = s_fc + kHeads;                                            // [8] 2^-e_c
+    unsigned* s_vmax = reinterpret_cast<unsigned*>(s_ic + kHeads);         // [8] max inverse v scale over the window
+    float* s_scale = reinterpret_cast<float*>(s_vmax + kHeads);            // output plane scale
+    // barriers: V full[kCvStages] +0, V empty[kCvStages] +24, band ready +48, MMA done +56; TMEM slot +64
+    const uint32_t bars = base + oVec + kCvVecFloats * 4;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kCvVecFloats * 4 + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int2 tile = tiles[blockIdx.x];
+    const VidInfo vi = vid_info(cu_rows, tile.x);
+    const int r0 = tile.y;
+    const int win0 = vi.row0 + r0 - 16;                                     // packed row of window row 0 (may be < 0)
+
+    if (tid == 0) {
+        for (int q = 0; q < kCvStages; ++q) { mbar_init(bars + 8 * q, 1); mbar_init(bars + 24 + 8 * q, 1); }
+        mbar_init(bars + 48, 256);
+        mbar_init(bars + 56, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < kHeads) s_vmax[tid] = 0u;
+    if (warp == 8) tmem_alloc(bars + 64, 256);
+    // zero the band once (only its 33 diagonals are ever rewritten), stage the taps
+    for (int i = tid; i < kCvBandBytes / 16; i += 320) reinterpret_cast<uint4*>(g + oBand)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kHeads * kTaps; i += 320) s_w[i] = __ldg(conv_w + i);
+    __syncthreads();
+    // inverse v plane scales of the window rows, all heads (0 outside the video: masks the band column)
+    for (int i = tid; i < kHeads * 192; i += 320) {
+        const int hd = i / 192, j = i - hd * 192;
+        const int r = r0 - 16 + j;
+        float f = 0.f;
+        if (r >= 0 && r < vi.T && j < kConvRowsIn) {
+            f = __ldg(inv + (size_t)(vi.row0 + r) * 24 + 16 + hd);
+            atomicMax(&s_vmax[hd], __float_as_uint(f));
+        }
+        s_inv[i] = f;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int hd = tid >> 2, q = tid & 3;
+        float l1 = 0.f, wm = 0.f;
+        for (int t = q; t < kTaps; t += 4) { const float a = fabsf(s_w[hd * kTaps + t]); l1 += a; wm = fmaxf(wm, a); }
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, 1));
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, 2));
+        const float vmi = __uint_as_float(s_vmax[hd]);
+        if (q == 0) {
+            const int ec = scale_exp(wm * vmi);                             // largest band entry into [2^14, 2^15)
+            s_fc[hd] = ldexpf(1.f, ec);
+            s_ic[hd] = ldexpf(1.f, -ec);
+        }
+        float bound = __ldg(w_max + ((size_t)tile.x * kHeads + hd) * 2) + l1 * (32768.f * vmi);
+        bound = warp_max(bound);
+        if (tid == 0) *s_scale = ldexpf(1.f, scale_exp(bound));
+    }
+    __syncthreads();
+    for (int i = tid; i < kHeads * 192; i += 320) s_inv[i] *= s_fc[i / 192];        // band column factors 2^(e_c - sv[j])
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const float sc = *s_scale;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ---- TMA producer: the v planes of head hd, 192 window rows ----
+            for (int hd = 0; hd < kHeads; ++hd) {
+                const int s = hd % kCvStages;
+                if (!mbar_wait(bars + 24 + 8 * s, ((uint32_t)(hd / kCvStages) & 1u) ^ 1u)) break;
+                const uint32_t st = base + oV + s * kCvVStage;
+                mbar_expect_tx(bars + 8 * s, kCvVStage);
+                const int col = 2 * kInner + hd * kDimHead;
+#pragma unroll
+                for (int q = 0; q < kConvRowsIn / 32; ++q) {                // boxes of 32 rows x 64 columns
+                    tma_load_2d(st + q * 4096, &map_hi, bars + 8 * s, col, win0 + q * 32);
+                    tma_load_2d(st + kCvVPlane + q * 4096, &map_lo, bars + 8 * s, col, win0 + q * 32);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc = make_idesc_bmn(128, 64);
+            bool mok = true;
+            for (int hd = 0; hd < kHeads && mok; ++hd) {
+                const int s = hd % kCvStages;
+                const uint32_t st = base + oV + s * kCvVStage;
+                mok = mbar_wait(bars + 8 * s, (uint32_t)(hd / kCvStages) & 1u) && mok;     // v planes have landed
+                mok = mbar_wait(bars + 48, (uint32_t)hd & 1u) && mok;                      // band of this head in place
+                tc_fence_after();
+                const uint32_t acc_main = tmem_base + (uint32_t)((hd & 1) * 128), acc_lo = acc_main + 64u;
+#pragma unroll
+                for (int ks = 0; ks < kConvRowsIn / 16; ++ks) {             // 10 K steps of 16 window rows
+                    const uint32_t a0 = base + oBand + (ks >> 2) * 32768 + (ks & 3) * 32;
+                    const uint32_t b0 = st + ks * 2048;
+                    const uint64_t dah = make_smem_desc<64>(a0), dal = make_smem_desc<64>(a0 + 16384);
+                    const uint64_t dbh = make_smem_desc_mn(b0), dbl = make_smem_desc_mn(b0 + kCvVPlane);
+                    const uint32_t accum = ks != 0 ? 1u : 0u;
+                    umma_f16(acc_main, dah, dbh, idesc, accum);
+                    umma_f16(acc_lo, dah, dbl, idesc, accum);
+                    umma_f16(acc_lo, dal, dbh, idesc, 1u);
+                }
+                umma_commit(bars + 56);
+                umma_commit(bars + 24 + 8 * s);                             // v stage free once these MMAs are done
+            }
+        }
+    } else {
+        const int r = tid & 127, half = tid >> 7;
+        const int row = r0 + r;
+        const bool live = row < vi.T;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        // this thread's part of band row r: taps t0 .. t1-1 (columns r + t)
+        const int t0 = half * 17, t1 = half ? kTaps : 17;
+        auto build_band = [&](int hd) {
+            const float* f = s_inv + hd * 192 + r + t0;                     // already times 2^e_c of the head
+            const float* wv = s_w + hd * kTaps + t0;
+#pragma unroll
+            for (int t = 0; t < 17; ++t) {
+                if (t0 + t < t1) {
+                    const int j = r + t0 + t;
+                    const float x = wv[t] * f[t];
+                    const __half h = __float2half_rn(x);
+                    const __half l = __float2half_rn(x - __half2float(h));
+                    const uint32_t off = (uint32_t)((j >> 6) * 32768) + sw128_off(r, (j & 63) >> 3) + (uint32_t)((j & 7) * 2);
+                    *reinterpret_cast<__half*>(g + oBand + off) = h;
+                    *reinterpret_cast<__half*>(g + oBand + 16384 + off) = l;
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bars + 48);
+        };
+        if (live && half == 0) m_inv[vi.row0 + row] = 1.f / sc;
+        build_band(0);
+        uint32_t phase = 0;
+        bool ok = true;
+        // Epilogue layout: in TMEM a thread owns one row (32 of its columns), and stored that way a warp instruction
+        // would touch 32 rows x 16 bytes.  Every 16-column slab goes through a warp-private 32 x 16 smem tile and comes
+        // back as (row rr + 8 i, columns 4 cc .. 4 cc + 3): 8 rows x 64 B (attention part in) / 8 rows x 32 B (a plane
+        // out) per instruction.
+        float* scr = reinterpret_cast<float*>(g + oScr) + warp * (32 * 20);
+        const int wrow0 = r0 + (warp & 3) * 32;                             // first tile row of this warp's TMEM lanes
+        const int rr = lane >> 2, cc = lane & 3;
+        auto attn_off = [&](int hd, int q, int i) -> size_t {
+            const int rw = min(wrow0 + rr + 8 * i, vi.T - 1);
+            return (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + half * 32 + q * 16 + cc * 4;
+        };
+        float4 an[8];                                                       // attention part, one head ahead
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) an[q * 4 + i] = ldg4(attn + attn_off(0, q, i));
+        for (int hd = 0; hd < kHeads && ok; ++hd) {
+            float4 a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = an[j];
+            if (hd + 1 < kHeads) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) an[q * 4 + i] = ldg4(attn + attn_off(hd + 1, q, i));
+            }
+            ok = mbar_wait(bars + 56, phase) && ok;
+            phase ^= 1u;
+            tc_fence_after();
+            if (hd + 1 < kHeads) build_band(hd + 1);                        // the band is free again: next head's MMAs
+            const uint32_t t_main = tmem_base + lane_addr + (uint32_t)((hd & 1) * 128 + half * 32);
+            float cv[32];
+            tmem_read32_sum(t_main, t_main + 64u, cv);
+            tc_fence_before();
+            const float ic = s_ic[hd];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    st4(scr + lane * 20 + j, make_float4(cv[q * 16 + j], cv[q * 16 + j + 1], cv[q * 16 + j + 2], cv[q * 16 + j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rw = wrow0 + rr + 8 * i;
+                    const float4 c4 = lds4(scr + (rr + 8 * i) * 20 + cc * 4);
+                    const float4 at = a[q * 4 + i];
+                    const float v0 = fmaf(c4.x, ic, at.x) * sc, v1 = fmaf(c4.y, ic, at.y) * sc;
+                    const float v2 = fmaf(c4.z, ic, at.z) * sc, v3 = fmaf(c4.w, ic, at.w) * sc;
+                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1), h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+                    __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    __half2 ll[2] = {__halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
+                                     __halves2half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3)))};
+                    if (rw < vi.T) {
+                        const size_t oo = (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + half * 32 + q * 16 + cc * 4;
+                        *reinterpret_cast<uint2*>(m_hi + oo) = *reinterpret_cast<uint2*>(hh);
+                        *reinterpret_cast<uint2*>(m_lo + oo) = *reinterpret_cast<uint2*>(ll);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace tc

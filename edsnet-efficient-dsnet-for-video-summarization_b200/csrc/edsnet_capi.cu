@@ -174,6 +174,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
             CU_CHECK(opt_in_smem(tc::value_conv_kernel<false>, tc::kConvSmemBytes), "smem opt-in value_conv");
             CU_CHECK(opt_in_smem(tc::value_conv_kernel<true>, tc::kConvSmemBytes), "smem opt-in value_conv planes");
+            CU_CHECK(opt_in_smem(tc::value_conv_tc_kernel, tc::kCvSmemBytes), "smem opt-in value_conv_tc");
             CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
             tc_attr = true;
         }
@@ -223,9 +224,22 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             __half* m_hi = static_cast<__half*>(merged16);
             __half* m_lo = m_hi + (size_t)b->total_rows * kInner;
             float* m_inv = reinterpret_cast<float*>(m_lo + (size_t)b->total_rows * kInner);
-            tc::value_conv_kernel<true><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
-                p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, stats,
-                m_hi, m_lo, m_inv);
+            static const bool ffma_conv = getenv("EDSNET_CONV_FFMA") != nullptr;      // A/B knob: CUDA-core version
+            if (ffma_conv)
+                tc::value_conv_kernel<true><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
+                    p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, stats,
+                    m_hi, m_lo, m_inv);
+            else {
+                // v planes in boxes of 32 rows: the 160-row window is 5 boxes
+                CUtensorMap map32_hi, map32_lo;
+                std::string msg;
+                if (!tc::make_map(&map32_hi, p_hi, (uint64_t)b->total_rows, kQkvCols, 64, 32, &msg) ||
+                    !tc::make_map(&map32_lo, p_lo, (uint64_t)b->total_rows, kQkvCols, 64, 32, &msg))
+                    return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
+                tc::value_conv_tc_kernel<<<b->n_tiles128, 320, tc::kCvSmemBytes, st>>>(
+                    map32_hi, map32_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged,
+                    stats, m_hi, m_lo, m_inv);
+            }
         } else {
             tc::value_conv_kernel<false><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
                 p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, nullptr,
