@@ -403,7 +403,8 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 // TMEM 256 columns: S main | S cross | O main | O cross.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAoVecBytes = 64 * 4 + 4 * 128 * 4;                            // inv_kl [64] + pair exchange max / sum [2][128] each
-constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + kAoVecBytes + 128 + 1024;
+constexpr int kAoScratch = 8 * 32 * 12 * 4;                                 // per row warp: 32 rows x 8 columns (+4 pad) fp32
+constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + kAoVecBytes + 128 + kAoScratch + 1024;
 
 // 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: landmarks / output columns
 // 0..31 and 32..63), warp 8 = TMA producer, warp 9 = MMA issuer.  The row tiles are independent, so S(i+1) is issued as
@@ -522,18 +523,29 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         float inv_q = trow < vi.T ? __ldg(inv + (size_t)(vi.row0 + trow) * 24 + h) : 0.f;
         float rs_prev = 0.f;
         // P.V product of tile j: read out, scale by the row's 1 / sum, store
+        // Stored straight from the accumulator layout a warp instruction would touch 32 rows x 16 bytes (32 L1 tag
+        // look-ups); every 8-column slab goes through a warp-private 32 x 8 smem tile and leaves as 16 rows x 32 B.
+        float* scr = reinterpret_cast<float*>(g + oVec + kAoVecBytes + 128) + warp * (32 * 12);
+        const int wrow0 = (warp & 3) * 32, rr = lane >> 1, cc = lane & 1;
         auto collect = [&](int j, float rs) {
             ok = mbar_wait(bars + 40, pv_phase) && ok;
             pv_phase ^= 1u;
             tc_fence_after();
             float ov[32];
             tmem_read32_sum(tO, tO + 64u, ov);
-            const int row = j * 128 + trow;
-            if (row < vi.T) {
-                float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32;
 #pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                    st4(dst + c, make_float4(ov[c] * rs, ov[c + 1] * rs, ov[c + 2] * rs, ov[c + 3] * rs));
+            for (int q = 0; q < 4; ++q) {
+                st4(scr + lane * 12, make_float4(ov[q * 8] * rs, ov[q * 8 + 1] * rs, ov[q * 8 + 2] * rs, ov[q * 8 + 3] * rs));
+                st4(scr + lane * 12 + 4, make_float4(ov[q * 8 + 4] * rs, ov[q * 8 + 5] * rs, ov[q * 8 + 6] * rs, ov[q * 8 + 7] * rs));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int row = j * 128 + wrow0 + rr + 16 * i;
+                    const float4 o4 = lds4(scr + (rr + 16 * i) * 12 + cc * 4);
+                    if (row < vi.T)
+                        st4(attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32 + q * 8 + cc * 4, o4);
+                }
+                __syncwarp();
             }
         };
         for (int i = 0; i < n_tiles && ok; ++i) {
