@@ -65,8 +65,9 @@ constexpr int kNmsSmemCap = 4096;
 // half an ulp of it -- only then (never seen in practice) the real division is evaluated.
 __device__ __forceinline__ bool nms_suppresses(int2 a, int2 b, double thresh, double slack) {
     const int inter = min(a.y, b.y) - max(a.x, b.x);
+    if (inter <= 0) return !(0.0 < thresh);          // disjoint boxes: quotient exactly 0, no float64 work (the common case)
     const int hull = max(a.y, b.y) - min(a.x, b.x);
-    const double di = (double)(inter > 0 ? inter : 0), dh = (double)hull;
+    const double di = (double)inter, dh = (double)hull;
     const double d = fma(-thresh, dh, di);
     if (d >= 0.0) return true;
     if (-d > slack * dh) return false;

@@ -224,7 +224,7 @@ static cudaError_t launch_nms_large(const float* scores_v, const int* boxes_v, i
     const int n_blocks = (N + kNmsBlock - 1) / kNmsBlock;     // dropped boxes sort last; blocks beyond N hold only key 0
     for (int b = 0; b < n_blocks; ++b) {
         if (b > 0)
-            nmsl_filter_kernel<<<dim3(kNmsBlock / 256, 8), 256, 0, st>>>(sbox, b * kNmsBlock, P, kept, counters, thresh,
+            nmsl_filter_kernel<<<dim3(kNmsBlock / 256, 32), 256, 0, st>>>(sbox, b * kNmsBlock, P, kept, counters, thresh,
                                                                         dead);
         nmsl_resolve_kernel<<<1, 512, kNmsResolveSmem, st>>>(keys, sbox, b * kNmsBlock, P, dead, scores_v, thresh, counters, kept,
                                                keep_idx_v, keep_scores_v, keep_boxes_v);
