@@ -13,7 +13,7 @@ from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
 from .dsnet import DSNet, NystromAttention, AttentionExtractor                      # noqa: F401
 from .pipeline import ScoringPipeline                            # noqa: F401
 from . import training                                           # noqa: F401
-from .summary import ShotPlan, keyshot_summaries, split_summaries  # noqa: F401
+from .summary import ShotPlan, keyshot_summaries, keyshot_from_scores, training_targets, split_summaries  # noqa: F401
 from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

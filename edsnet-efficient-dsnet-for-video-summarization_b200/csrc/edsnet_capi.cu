@@ -552,7 +552,8 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
     if (!shots || !shots->cu_seg || !shots->cps || !shots->nfps || !shots->picks || !shots->cu_frames ||
         !shots->capacity || !shots->gcd || !shots->dp_off)
         return fail(EDSNET_E_ARG, "keyshot_summary: shot tables are NULL");
-    if (!keep_count || !keep_scores || !keep_boxes || !pos_scores || !frame_scores || !seg_scores || !picked ||
+    // keep_count == NULL: pos_scores is the input (per-position scores), keep_scores / keep_boxes are not read
+    if ((keep_count && (!keep_scores || !keep_boxes)) || !pos_scores || !frame_scores || !seg_scores || !picked ||
         !summary || !dp_scratch)
         return fail(EDSNET_E_ARG, "keyshot_summary: NULL operand");
     ShotTables sh{shots->cu_seg, shots->cps, shots->nfps, shots->picks,

@@ -63,7 +63,7 @@ keyshot_summary_kernel(const int* __restrict__ cu_rows, int S, ShotTables sh, co
     const VidInfo vi = vid_info(cu_rows, v);
     const int T = vi.T;
     const size_t g0 = (size_t)vi.row0 * S;
-    const int K = keep_count[v];
+    const int K = keep_count != nullptr ? keep_count[v] : 0;
     const int seg0 = sh.cu_seg[v], n_seg = sh.cu_seg[v + 1] - seg0;
     const long long f0 = sh.cu_frames[v];
     const int n_frames = (int)(sh.cu_frames[v + 1] - f0);
@@ -72,8 +72,9 @@ keyshot_summary_kernel(const int* __restrict__ cu_rows, int S, ShotTables sh, co
     float* fscore = frame_score + f0;
     unsigned char* summ = summary + f0;
 
-    // 1. per-position score: running max over the kept boxes
-    for (int t0 = 0; t0 < T; t0 += 256) {
+    // 1. per-position score: running max over the kept boxes (keep_count == nullptr: pos_score is an INPUT, e.g. the
+    //    ground-truth importance scores of anchor_based/train.py:79, and this step is skipped)
+    for (int t0 = 0; keep_count != nullptr && t0 < T; t0 += 256) {
         const int t = t0 + tid;
         float best = 0.f;
         for (int k0 = 0; k0 < K; k0 += 256) {

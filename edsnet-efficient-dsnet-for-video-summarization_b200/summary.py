@@ -90,6 +90,45 @@ def keyshot_summaries(model, nms_out: dict, batch: DeviceBatch, shots: ShotPlan)
     return out
 
 
+def keyshot_from_scores(model, scores: torch.Tensor, batch: DeviceBatch, shots: ShotPlan) -> dict:
+    """vsumm_helper.get_keyshot_summ (helpers/vsumm_helper.py:53-98) on given per-position scores, packed over the
+    videos of `batch` (e.g. the ground-truth importance scores the training loop turns into targets,
+    anchor_based/train.py:79).  scores: float32 [total_rows] on the device.  Same outputs as keyshot_summaries."""
+    if not scores.is_cuda:
+        raise RuntimeError("keyshot_from_scores needs CUDA tensors (there is no CPU fallback)")
+    if shots.lengths != [int(t) for t in batch.plan.lengths]:
+        raise ValueError("picks do not match the batch's video lengths")
+    dev = scores.device
+    out = {
+        "pos_scores": scores.to(torch.float32).contiguous().clone(),
+        "frame_scores": torch.empty(max(shots.total_frames, 1), dtype=torch.float32, device=dev),
+        "seg_scores": torch.empty(max(shots.total_seg, 1), dtype=torch.int32, device=dev),
+        "picked": torch.empty(max(shots.total_seg, 1), dtype=torch.uint8, device=dev),
+        "summary": torch.empty(max(shots.total_frames, 1), dtype=torch.uint8, device=dev),
+    }
+    scratch = torch.empty(shots.dp_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(_capi.lib().edsnet_keyshot_summary(
+            model._config(), batch.struct, shots.struct, None, None, None, out["pos_scores"].data_ptr(),
+            out["frame_scores"].data_ptr(), out["seg_scores"].data_ptr(), out["picked"].data_ptr(),
+            out["summary"].data_ptr(), scratch.data_ptr(), stream))
+    out["_scratch"] = scratch
+    return out
+
+
+def training_targets(model, gtscores: Sequence[np.ndarray], shots: ShotPlan, device) -> List[np.ndarray]:
+    """The per-video target masks of anchor_based/train.py:79-84 (get_keyshot_summ on the ground-truth scores, then
+    downsample_summ) for a whole split in one launch.  The reference recomputes them (ortools knapsack included)
+    every step of every epoch although they only depend on the dataset: compute once, cache."""
+    from .plan import BatchPlan
+    lengths = [len(g) for g in gtscores]
+    batch = BatchPlan.build(lengths).to(device)
+    s = torch.from_numpy(np.concatenate([np.asarray(g, dtype=np.float32) for g in gtscores])).to(device)
+    out = keyshot_from_scores(model, s, batch, shots)
+    return [m[::15] for m in split_summaries(out["summary"], shots)]
+
+
 def split_summaries(summary: torch.Tensor, shots: ShotPlan) -> List[np.ndarray]:
     s = summary.cpu().numpy().astype(bool)
     cf = shots.cu_frames_host

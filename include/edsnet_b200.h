@@ -171,7 +171,9 @@ typedef struct {
 } edsnet_shots;
 
 /* evaluate.py:29 / infer.py:35: vsumm_helper.bbox2summary (helpers/vsumm_helper.py:101-116, 53-98, 26-45) on the
- * device, from the kept proposals edsnet_decode_nms wrote.  Outputs: pos_scores [total_rows], frame_scores
+ * device, from the kept proposals edsnet_decode_nms wrote.  With keep_count == NULL the per-position scores are taken
+ * from pos_scores as an INPUT instead (vsumm_helper.get_keyshot_summ on given scores: the ground-truth targets of
+ * anchor_based/train.py:79) and keep_scores / keep_boxes are not read.  Outputs: pos_scores [total_rows], frame_scores
  * [total_frames], seg_scores [total_seg], picked [total_seg] (0/1), summary [total_frames] (0/1). */
 int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, const edsnet_shots* shots,
                            const int32_t* keep_count, const float* keep_scores, const int32_t* keep_boxes,

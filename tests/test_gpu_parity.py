@@ -596,6 +596,22 @@ def test_keyshot_summary_packed_vs_oracle():
     assert seg.max() <= 1000 and seg.min() >= 0
 
 
+def test_training_targets_from_gtscore_vs_oracle():
+    """anchor_based/train.py:79-84 on the device: get_keyshot_summ on ground-truth scores (no proposals) for a packed
+    split, then downsample_summ -- bit-exact against the oracle's host restatement."""
+    from edsnet_b200 import ShotPlan, training_targets
+    rng = np.random.default_rng(21)
+    model = make_model(orc.synth_params(3, "default"), [4, 8], 5, "fp32", DEV)
+    lengths = [int(t) for t in rng.integers(30, 600, size=10)] + [1, 17]
+    vds = [_shots_for(t, rng) for t in lengths]
+    gts = [rng.random(t).astype(np.float32) for t in lengths]
+    shots = ShotPlan(vds, DEV)
+    got = training_targets(model, gts, shots, DEV)
+    for t, vd, g, m in zip(lengths, vds, gts, got):
+        want = orc.downsample_summ(orc.keyshot_summary(g, vd["cps"], vd["n_frames"], vd["nfps"], vd["picks"]))
+        assert m.shape == (t,) and np.array_equal(m, want)
+
+
 # ------------------------------------------------------------------------------------------------ evaluation metrics
 EV = load_npz("eval_golden.npz")
 
