@@ -602,8 +602,10 @@ template <int STAGES, int EPI>
 cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                         cudaStream_t st, std::string* msg);
 
-// variant: 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh), 0 = BK64 / 128B swizzle (default), 1 = BK32 / 64B swizzle, 2 = 128 x 64 tiles (4 accumulators, double-
-// buffered TMEM), 3 = 128 x 128 tiles with 2 accumulators (double-buffered TMEM)
+// variant (profiling knob, edsnet_debug_set_tc_variant / EDSNET_TC_VARIANT): 0 = default (128 x 128 tiles, BK 64, four
+// accumulators; two double-buffered accumulators when K <= 512), 3 = two double-buffered accumulators for every K,
+// 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh).  A BK 32 / 64-byte-swizzle variant and a 128 x 64
+// tile variant were measured slower (profiles/r01e_gemm_variants.log) and removed.
 inline int& variant_ref() {
     static int v = [] { const char* e = getenv("EDSNET_TC_VARIANT"); return e ? atoi(e) : 0; }();   // profiling knob
     return v;
@@ -617,8 +619,6 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
         if (PASSES == 3) {
             // four 128-column accumulators fill TMEM
             if (variant == 4) return launch_pair<4, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-            if (variant == 1) return launch_variant<128, 32, 4, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
-            if (variant == 2) return launch_variant<64, 64, 4, 3, EPI, 4>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 3) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             // K <= 512: the hi.hi products of one tile are <= 32 accumulation steps, so ONE main accumulator stays
             // inside the truncation budget of the K = 1024 case (3 x <= 24 steps) and the tile fits twice into TMEM:
@@ -626,7 +626,6 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
             if (variant == 0 && K <= 512) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 3, 3, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         } else {
-            if (variant == 1) return launch_variant<128, 32, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 6, 1, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         }
     }

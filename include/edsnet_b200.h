@@ -248,7 +248,8 @@ int edsnet_debug_stage_timing(int32_t enable);
 int edsnet_debug_stage_count(void);
 const char* edsnet_debug_stage_name(int32_t stage);
 int edsnet_debug_stage_times(double* ms_sum, int32_t* launches, int32_t n);
-/* Tile variant of the tcgen05 GEMM: 0 = BK 64 / 128-byte swizzle (default), 1 = BK 32 / 64-byte swizzle. */
+/* Variant of the tcgen05 GEMM (profiling): 0 = default, 3 = two double-buffered accumulators for every K,
+ * 4 = CTA-pair kernel (tcgen05.mma.cta_group::2). */
 int edsnet_debug_set_tc_variant(int32_t variant);
 
 #ifdef __cplusplus
