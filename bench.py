@@ -325,6 +325,31 @@ def main():
                 "share_of_step": qkv_ms / total_stage_ms if total_stage_ms else None,
                 "stage_ms_per_step": {k: round(v[0] / inst_steps, 4) for k, v in stages.items()}}
 
+    # per-stage roofline fractions from the same instrumented steps: ALGORITHMIC bytes / flops per feature row (SURVEY
+    # 8d; split-precision passes counted once) x rows per step / stage time, against the measured HBM / sustained bf16 peaks
+    peak_hbm = float(peaks.get("hbm_gbs", 6500.0))
+    per_row = {                                   # stage -> ("hbm", bytes per row) or ("tensor", flops per row)
+        "split_f16": ("hbm", 4096 + 4096 + 4), "to_qkv_gemm": ("tensor", 2.0 * 1024 * 1536),
+        "landmarks": ("hbm", 4096), "value_conv": ("hbm", 2048 + 2048 + 2048 + 4),
+        "to_out_gemm": ("tensor", 2.0 * 512 * 1024), "layernorm1024": ("hbm", 4096 + 4096 + 4),
+        "fc1_gemm": ("tensor", 2.0 * 1024 * 128), "fc_stack": ("tensor", FC_DEPTH * 2.0 * 128 * 128),
+        "roi_pool_heads": ("hbm", 4 * 128 + 12 * S), "decode_boxes": ("hbm", 8 * S + 16 * S), "nms": ("hbm", 25 * S),
+    }
+    stage_roof = {}
+    for name, (kind, amount) in per_row.items():
+        if name in stages and stages[name][0] > 0:
+            sec = stages[name][0] / inst_steps * 1e-3
+            if kind == "hbm":
+                ach = amount * R / sec / 1e9
+                stage_roof[name] = {"bound": "hbm", "achieved_GBps": round(ach, 1), "frac": round(ach / peak_hbm, 3)}
+            else:
+                ach = amount * R / sec / 1e12
+                stage_roof[name] = {"bound": "tensor", "achieved_TFLOPs": round(ach, 1), "frac": round(ach / peak_tf, 3)}
+    roofline["stages"] = stage_roof
+    roofline["stages_note"] = ("algorithmic work counted once; the tensor stages run 3 split-fp16 MMA passes (fp32-grade "
+                               "accuracy), so their ceiling is 1/3; the attention-core stages (landmark softmaxes, "
+                               "pseudo-inverse chain) are latency bound and not listed")
+
     vids_all = args.videos * world
     frames_all = R * world            # every rank has its own seeded lengths; close enough for the aggregate
     if world > 1:
