@@ -206,7 +206,7 @@ roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_ro
                       ScaleList scales, int halo, const float* __restrict__ w_cls, const float* __restrict__ b_cls,
                       const float* __restrict__ w_loc, const float* __restrict__ b_loc,
                       float* __restrict__ pred_cls, float* __restrict__ pred_loc) {
-    __shared__ float sd[3][128 + 2 * kRoiMaxHalo + 4];
+    __shared__ float sd[3][128 + 2 * kRoiMaxHalo + 8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 tile = tiles[blockIdx.x];
     const int v = tile.x, t0 = tile.y;
@@ -217,39 +217,49 @@ roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_ro
     const float4 w1 = ldg4(w_loc + kHidden + lane * 4);
     const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
     const int grp = (lane >> 3) & 3;                               // which of the 4 rows this lane ends up holding
-    for (int r4 = warp * 4; r4 < nrows; r4 += 32) {
-        float p[12];
+    for (int r8 = warp * 8; r8 < nrows; r8 += 64) {
+        // eight rows per warp and trip: eight independent 128-bit loads per lane in flight
+        float4 x[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int t = t0 - halo + r4 + k;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t >= 0 && t < vi.T && r4 + k < nrows) x = ldg4(u + (size_t)(vi.row0 + t) * kHidden + lane * 4);
-            p[k * 3 + 0] = fmaf(x.x, wc.x, fmaf(x.y, wc.y, fmaf(x.z, wc.z, x.w * wc.w)));
-            p[k * 3 + 1] = fmaf(x.x, w0.x, fmaf(x.y, w0.y, fmaf(x.z, w0.z, x.w * w0.w)));
-            p[k * 3 + 2] = fmaf(x.x, w1.x, fmaf(x.y, w1.y, fmaf(x.z, w1.z, x.w * w1.w)));
-        }
-        // packed butterfly: 12 -> 6 values (lanes 16 apart), 6 -> 3 (8 apart), then plain butterflies over 4, 2, 1;
-        // lanes 8 g .. 8 g + 7 end up with the three sums of row r4 + g
-        float q[6], r[3];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const float mine = b4 ? p[6 + i] : p[i], other = b4 ? p[i] : p[6 + i];
-            q[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        for (int k = 0; k < 8; ++k) {
+            const int t = t0 - halo + r8 + k;
+            x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < vi.T && r8 + k < nrows) x[k] = ldg4(u + (size_t)(vi.row0 + t) * kHidden + lane * 4);
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float mine = b3 ? q[3 + i] : q[i], other = b3 ? q[i] : q[3 + i];
-            r[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
-        }
+        for (int g4 = 0; g4 < 2; ++g4) {
+            const int r4 = r8 + g4 * 4;
+            float p[12];
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+            for (int k = 0; k < 4; ++k) {
+                const float4 v = x[g4 * 4 + k];
+                p[k * 3 + 0] = fmaf(v.x, wc.x, fmaf(v.y, wc.y, fmaf(v.z, wc.z, v.w * wc.w)));
+                p[k * 3 + 1] = fmaf(v.x, w0.x, fmaf(v.y, w0.y, fmaf(v.z, w0.z, v.w * w0.w)));
+                p[k * 3 + 2] = fmaf(v.x, w1.x, fmaf(v.y, w1.y, fmaf(v.z, w1.z, v.w * w1.w)));
+            }
+            // packed butterfly: 12 -> 6 values (lanes 16 apart), 6 -> 3 (8 apart), then plain butterflies over 4, 2, 1;
+            // lanes 8 g .. 8 g + 7 end up with the three sums of row r4 + g
+            float q[6], r[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
-        }
-        if ((lane & 7) == 0 && r4 + grp < nrows) {
-            sd[0][r4 + grp] = r[0];
-            sd[1][r4 + grp] = r[1];
-            sd[2][r4 + grp] = r[2];
+            for (int i = 0; i < 6; ++i) {
+                const float mine = b4 ? p[6 + i] : p[i], other = b4 ? p[i] : p[6 + i];
+                q[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float mine = b3 ? q[3 + i] : q[i], other = b3 ? q[i] : q[3 + i];
+                r[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
+            }
+            if ((lane & 7) == 0 && r4 + grp < nrows) {
+                sd[0][r4 + grp] = r[0];
+                sd[1][r4 + grp] = r[1];
+                sd[2][r4 + grp] = r[2];
+            }
         }
     }
     const float bc = __ldg(b_cls), bl0 = __ldg(b_loc), bl1 = __ldg(b_loc + 1);
