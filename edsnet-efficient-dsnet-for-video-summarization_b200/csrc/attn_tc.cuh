@@ -803,26 +803,14 @@ pinv_w_tc_kernel(const float* __restrict__ attn2, const float* __restrict__ stat
 constexpr int kConvRowsIn = 128 + kTaps - 1;                                 // 160
 constexpr int kConvSmemBytes = kConvRowsIn * 128 * 4;
 
-// PLANES = true: merged leaves as the to_out GEMM's operand planes (hi [R][512] | lo [R][512] | inverse row scale [R],
-// the layout of edsnet_split_f16) instead of fp32, which removes the separate split pass.  A plane scale only has to
-// keep the row's values inside fp16 range with the low plane normal for every element that matters, so it is taken
-// from a BOUND that all four column-group CTAs of a row tile can compute on their own: |attention part| <= max|W| of
-// the head (attn_out_tc_kernel leaves it in w_max), |convolution part| <= sum|taps| * max|v| over the window rows
-// (from v's plane scales); one power of two per 128-row tile, maximum over the 8 heads.
-template <bool PLANES>
 __global__ void __launch_bounds__(256, 2)
 value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const float* __restrict__ inv,
                   const int* __restrict__ cu_rows, const int2* __restrict__ tiles, const float* __restrict__ conv_w,
-                  float* __restrict__ merged, const float* __restrict__ w_max, __half* __restrict__ m_hi,
-                  __half* __restrict__ m_lo, float* __restrict__ m_inv) {
+                  float* __restrict__ merged) {
     extern __shared__ __align__(16) float vs[];                              // [160][128]
-    __shared__ unsigned s_vmax[kHeads];
-    __shared__ float s_scale;
     const int2 tile = tiles[blockIdx.x];
     const VidInfo vi = vid_info(cu_rows, tile.x);
     const int r0 = tile.y, cb = blockIdx.y * 128, tid = threadIdx.x;
-    if (PLANES && tid < kHeads) s_vmax[tid] = 0u;
-    if (PLANES) __syncthreads();
     for (int task = tid; task < kConvRowsIn * 16; task += 256) {
         const int rr = task >> 4, ch = task & 15;
         const int r = r0 - 16 + rr;
@@ -839,8 +827,6 @@ value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, 
             const float2 l0 = __half22float2(lp[0]), l1 = __half22float2(lp[1]), l2 = __half22float2(lp[2]), l3 = __half22float2(lp[3]);
             a = make_float4((h0.x + l0.x) * s, (h0.y + l0.y) * s, (h1.x + l1.x) * s, (h1.y + l1.y) * s);
             b = make_float4((h2.x + l2.x) * s, (h2.y + l2.y) * s, (h3.x + l3.x) * s, (h3.y + l3.y) * s);
-            // v's plane scale of every head of this window row (|v| < 2^15 * inverse scale)
-            if (PLANES && ch < kHeads) atomicMax(&s_vmax[ch], __float_as_uint(__ldg(inv + row * 24 + 16 + ch)));
         }
         st4(vs + rr * 128 + ch * 8, a);
         st4(vs + rr * 128 + ch * 8 + 4, b);
@@ -855,26 +841,6 @@ value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) an[j] = j < rows ? out[(size_t)j * kInner] : 0.f;
     __syncthreads();
-    float sc = 1.f;
-    if (PLANES) {
-        // one warp: lane = (head, quarter of the taps); bound = max over heads of max|W| + sum|taps| * max|v|
-        if (tid < 32) {
-            const int hd = tid >> 2, q = tid & 3;
-            float l1 = 0.f;
-            for (int t = q; t < kTaps; t += 4) l1 += fabsf(__ldg(conv_w + hd * kTaps + t));
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-            const float vb = 32768.f * __uint_as_float(s_vmax[hd]);
-            float bound = __ldg(w_max + ((size_t)tile.x * kHeads + hd) * 2) + l1 * vb;
-            bound = warp_max(bound);
-            if (tid == 0) s_scale = ldexpf(1.f, scale_exp(bound));
-        }
-        __syncthreads();
-        sc = s_scale;
-        if (blockIdx.y == 0 && tid < 128 && r0 + tid < vi.T) m_inv[vi.row0 + r0 + tid] = 1.f / sc;
-    }
-    __half* ohi = m_hi + (size_t)(vi.row0 + r0 + base) * kInner + cb + c;
-    __half* olo = m_lo + (size_t)(vi.row0 + r0 + base) * kInner + cb + c;
     float win[40];                           // win[i] = input row (base + b + i) of the staged window
 #pragma unroll
     for (int i = 0; i < 32; ++i) win[i] = vs[(base + i) * 128 + c];
@@ -888,17 +854,7 @@ value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, 
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
             for (int i = 0; i < kTaps; ++i) acc[j] = fmaf(w[i], win[j + i], acc[j]);
-            if (b + j < rows) {
-                if (PLANES) {
-                    // (pairing neighbouring lanes for 32-bit stores was measured slower than two 16-bit stores)
-                    const float x = acc[j] * sc;
-                    const __half h = __float2half_rn(x);
-                    ohi[(size_t)(b + j) * kInner] = h;
-                    olo[(size_t)(b + j) * kInner] = __float2half_rn(x - __half2float(h));
-                } else {
-                    out[(size_t)(b + j) * kInner] = acc[j];
-                }
-            }
+            if (b + j < rows) out[(size_t)(b + j) * kInner] = acc[j];
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) win[i] = win[i + 8];
@@ -919,7 +875,12 @@ value_conv_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, 
 //   * 12 K steps x {hi.hi -> main; hi.lo, lo.hi -> cross} per head, accumulators double-buffered in TMEM: the MMAs of
 //     head h+1 run under the epilogue of head h (TMEM -> + attention part -> plane scale -> hi / lo planes).
 // One CTA per 128-row tile, all 8 heads; 320 threads: warps 0..7 = rows (two threads per row, 32 columns each),
-// warp 8 = TMA producer, warp 9 = MMA issuer.  The output plane scale is the tile-wide bound of value_conv_kernel<true>.
+// warp 8 = TMA producer, warp 9 = MMA issuer.
+// Output: merged leaves as the to_out GEMM's operand planes (hi [R][512] | lo [R][512] | inverse row scale [R], the
+// layout of edsnet_split_f16), which removes the separate split pass.  A plane scale only has to keep the row's values
+// inside fp16 range with the low plane normal for every element that matters, so it is taken from a BOUND:
+// |attention part| <= max|W| of the head (attn_out_tc_kernel leaves it in w_max), |convolution part| <= sum|taps| *
+// max|v| over the window rows (from v's plane scales); one power of two per 128-row tile, maximum over the 8 heads.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kCvBandBytes = 3 * 32768;                                    // [kb][hi | lo][128 rows][128 B]
 constexpr int kCvVPlane = kConvRowsIn * 128;                                // 160 window rows x 128 B = 20 KB

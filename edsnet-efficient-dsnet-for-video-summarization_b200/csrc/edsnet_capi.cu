@@ -172,8 +172,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (!tc_attr) {
             CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
-            CU_CHECK(opt_in_smem(tc::value_conv_kernel<false>, tc::kConvSmemBytes), "smem opt-in value_conv");
-            CU_CHECK(opt_in_smem(tc::value_conv_kernel<true>, tc::kConvSmemBytes), "smem opt-in value_conv planes");
+            CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
             CU_CHECK(opt_in_smem(tc::value_conv_tc_kernel, tc::kCvSmemBytes), "smem opt-in value_conv_tc");
             CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
             tc_attr = true;
@@ -224,12 +223,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             __half* m_hi = static_cast<__half*>(merged16);
             __half* m_lo = m_hi + (size_t)b->total_rows * kInner;
             float* m_inv = reinterpret_cast<float*>(m_lo + (size_t)b->total_rows * kInner);
-            static const bool ffma_conv = getenv("EDSNET_CONV_FFMA") != nullptr;      // A/B knob: CUDA-core version
-            if (ffma_conv)
-                tc::value_conv_kernel<true><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
-                    p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, stats,
-                    m_hi, m_lo, m_inv);
-            else {
+            {
                 // v planes in boxes of 32 rows: the 160-row window is 5 boxes
                 CUtensorMap map32_hi, map32_lo;
                 std::string msg;
@@ -241,9 +235,8 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
                     stats, m_hi, m_lo, m_inv);
             }
         } else {
-            tc::value_conv_kernel<false><<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
-                p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged, nullptr,
-                nullptr, nullptr, nullptr);
+            tc::value_conv_kernel<<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
+                p_hi, p_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged);
         }
         CU_CHECK(cudaGetLastError(), "value_conv_kernel");
     } else {
