@@ -630,6 +630,41 @@ def test_training_targets_from_gtscore_vs_oracle():
         assert m.shape == (t,) and np.array_equal(m, want)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_forward_stays_inside_its_buffers(precision):
+    """edsnet_forward called through the C ABI with guard bands around the workspace (sized EXACTLY by
+    edsnet_workspace_bytes), the input and both outputs: no byte outside the declared extents may change, for ragged
+    packed batches whose tiles end in partial rows."""
+    capi, lib = _lib()
+    p = orc.synth_params(13, "xavier")
+    scales = [4, 8, 16, 32]
+    model = make_model(p, scales, 5, precision, DEV)
+    from edsnet_b200 import BatchPlan
+    G = 1 << 16                                          # guard bytes on either side
+    for lengths in ([1], [129, 64, 1, 37], [300, 255, 2]):
+        R, S = sum(lengths), len(scales)
+        batch = BatchPlan.build(lengths).to(DEV)
+        cfg = model._config()
+        st = torch.cuda.current_stream().cuda_stream
+        w = model._weights(torch.device(DEV), st)
+        need = lib.edsnet_workspace_bytes(cfg, R, len(lengths), None)
+        sizes = {"ws": need, "x": R * 4096, "cls": R * S * 4, "loc": R * S * 8}
+        bufs = {k: torch.full((n + 2 * G,), 0x5A, dtype=torch.uint8, device=DEV) for k, n in sizes.items()}
+        x = torch.cat([orc.synth_features(t, 40 + i) for i, t in enumerate(lengths)]).to(DEV)
+        bufs["x"][G:G + R * 4096] = x.view(-1).view(torch.uint8)
+        ptr = {k: v.data_ptr() + G for k, v in bufs.items()}
+        assert all(pp % 256 == 0 for pp in ptr.values())
+        capi.check(lib.edsnet_forward(cfg, w, batch.struct, ptr["x"], ptr["cls"], ptr["loc"], ptr["ws"], need, st))
+        _no_tc_timeout()
+        for k, v in bufs.items():
+            n = sizes[k]
+            assert bool((v[:G] == 0x5A).all()) and bool((v[G + n:] == 0x5A).all()), f"{k}: write outside the buffer"
+        assert torch.equal(bufs["x"][G:G + R * 4096].view(torch.float32).view(R, 1024), x), "input modified"
+        cls = bufs["cls"][G:G + R * S * 4].view(torch.float32).view(R, S)
+        ref_cls, _ = model.forward_packed(x, lengths)
+        assert torch.equal(cls, ref_cls)
+
+
 # ------------------------------------------------------------------------------------------------ evaluation metrics
 EV = load_npz("eval_golden.npz")
 
