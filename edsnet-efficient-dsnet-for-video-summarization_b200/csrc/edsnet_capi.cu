@@ -248,15 +248,17 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     return EDSNET_OK;
 }
 
+// heads_out != nullptr (tcgen05 precisions, edsnet_forward): the stack emits the three head projections per row and
+// u_out may be nullptr
 int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float* u_in, float* u_out, int rows,
-                  cudaStream_t st) {
+                  cudaStream_t st, float* heads_out = nullptr) {
     StageScope scope(ST_FC_STACK, st);
     if (cfg->precision != EDSNET_PREC_FP32) {
         // tensor-core version (fp16 hi/lo split, fp32-grade) for both tcgen05 precisions: the block is too small
         // and too error-sensitive for a single-pass variant to be worth having
         if (!w->fcb_w16) return fail(EDSNET_E_ARG, "fc_stack: tcgen05 precision needs fcb_w16 (edsnet_split_f16)");
         CU_CHECK(launch_fc_stack_tc(u_in, w->fcb_w16, w->fcb_b, w->fcb_ln_w, w->fcb_ln_b, u_out, rows, cfg->fc_depth,
-                                    st), "fc_stack_tc_kernel");
+                                    st, w->cls_w, w->loc_w, heads_out), "fc_stack_tc_kernel");
         return EDSNET_OK;
     }
     static bool attrs_done = false;
@@ -271,14 +273,19 @@ int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float
 }
 
 int roi_impl(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* b, const float* u,
-             float* pred_cls, float* pred_loc, cudaStream_t st) {
+             float* pred_cls, float* pred_loc, cudaStream_t st, bool from_heads = false) {
     int halo = 0;
     ScaleList sl = make_scales(cfg, &halo);
     if (halo > kRoiMaxHalo) return fail(EDSNET_E_UNSUPPORTED, "roi_pool_heads: anchor scale above 128");
     StageScope scope(ST_ROI, st);
-    roi_pool_heads_kernel<<<b->n_tiles128, 256, 0, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
-                                                             sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
-                                                             pred_cls, pred_loc);
+    if (from_heads)
+        roi_pool_heads_kernel<true><<<b->n_tiles128, 256, 0, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
+                                                                   sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
+                                                                   pred_cls, pred_loc);
+    else
+        roi_pool_heads_kernel<false><<<b->n_tiles128, 256, 0, st>>>(u, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128),
+                                                                    sl, halo, w->cls_w, w->cls_b, w->loc_w, w->loc_b,
+                                                                    pred_cls, pred_loc);
     CU_CHECK(cudaGetLastError(), "roi_pool_heads_kernel");
     return EDSNET_OK;
 }
@@ -510,10 +517,13 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
                        nullptr, 0, st, ST_FC1);
     if (rc) return rc;
     // 5. shared fc block x depth                                                (dsnet.py:107-108)
-    rc = fc_stack_impl(cfg, w, F(L.u0), F(L.u1), R, st);
+    //    (tcgen05: the stack's last layer emits the three head projections per row into the u1 region, 16 B per row,
+    //    instead of the 512-byte rows; pooling and heads are linear, so the windows then run over those)
+    const bool heads_fused = prec != EDSNET_PREC_FP32;
+    rc = fc_stack_impl(cfg, w, F(L.u0), heads_fused ? nullptr : F(L.u1), R, st, heads_fused ? F(L.u1) : nullptr);
     if (rc) return rc;
     // 6. ROI pooling + heads                                                    (dsnet.py:110-115)
-    return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st);
+    return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st, heads_fused);
 }
 
 int edsnet_eval_metrics(const edsnet_batch* batch, const int64_t* cu_frames, const uint8_t* summary,

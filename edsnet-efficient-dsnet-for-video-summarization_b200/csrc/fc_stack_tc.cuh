@@ -17,8 +17,10 @@ namespace tc {
 constexpr int kFcTile = 128;                                  // rows per warpgroup tile
 constexpr int kFcPlane = 128 * 128 * 2;                       // bytes of one fp16 128x128 plane
 // W hi | W lo | A hi (wg0) | A lo (wg0) | A hi (wg1) | A lo (wg1) | vectors | barriers
-constexpr int kFcXchBytes = 2 * 3 * 2 * 128 * 2 * 4;           // [group][slot][half][row][2] floats
-constexpr int kFcSmemBytes = 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes + 64 + 1024;
+constexpr int kFcSlots = 5;                                   // LayerNorm sums (2, by layer parity), row max, head dots (2)
+constexpr int kFcXchBytes = 2 * kFcSlots * 2 * 128 * 2 * 4;    // [group][slot][half][row][2] floats
+constexpr int kFcVecFloats = 7 * 128;                         // wscale bias gamma beta | w_cls w_loc0 w_loc1
+constexpr int kFcSmemBytes = 6 * kFcPlane + kFcVecFloats * 4 + kFcXchBytes + 64 + 1024;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -41,16 +43,20 @@ __device__ __forceinline__ uint32_t fc_plane_off(int r, int c16) {
 __global__ void __launch_bounds__(512, 1)
 fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_planes, const float* __restrict__ w_inv_scale,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* __restrict__ u_out, int rows, int depth) {
+                   float* __restrict__ u_out, int rows, int depth, const float* __restrict__ w_cls,
+                   const float* __restrict__ w_loc, float4* __restrict__ heads_out) {
+    // heads_out != nullptr: the three head projections of every output row (u . w_cls, u . w_loc[0], u . w_loc[1]; the
+    // ROI pooling and the heads are linear, so the pooling windows then run over these 3 channels) are emitted, 16 bytes
+    // per row; u_out may then be nullptr and the 512-byte rows are never written.
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t w_hi = base, w_lo = base + kFcPlane;
     float* vec = reinterpret_cast<float*>(gbase + 6 * kFcPlane);          // wscale[128] bias[128] gamma[128] beta[128]
-    float* xch = vec + 4 * 128;                                             // [group][slot 0..2][half][row][2]
-    const uint32_t bar0 = base + 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes;  // mbarrier per group, then the TMEM slot
+    float* xch = vec + kFcVecFloats;                                        // [group][slot][half][row][2]
+    const uint32_t bar0 = base + 6 * kFcPlane + kFcVecFloats * 4 + kFcXchBytes;   // mbarrier per group, then the TMEM slot
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(gbase + 6 * kFcPlane + 4 * 128 * 4 + kFcXchBytes + 16);
+        reinterpret_cast<volatile uint32_t*>(gbase + 6 * kFcPlane + kFcVecFloats * 4 + kFcXchBytes + 16);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;                              // group, thread within it
@@ -67,6 +73,11 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
         vec[128 + tid] = __ldg(bias + tid);
         vec[256 + tid] = __ldg(gamma + tid);
         vec[384 + tid] = __ldg(beta + tid);
+        if (heads_out != nullptr) {
+            vec[512 + tid] = __ldg(w_cls + tid);
+            vec[640 + tid] = __ldg(w_loc + tid);
+            vec[768 + tid] = __ldg(w_loc + 128 + tid);
+        }
     }
     if (tid == 0) {
         mbar_init(bar0, 1);
@@ -94,7 +105,7 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     int e_ln = 0;
     if (ln_bound > 0.f && ln_bound < INFINITY) e_ln = 14 - ilogbf(ln_bound);
     e_ln = max(-100, min(100, e_ln));
-    float* xg = xch + grp * (3 * 2 * 128 * 2);
+    float* xg = xch + grp * (kFcSlots * 2 * 128 * 2);
     uint32_t phase = 0;
     bool ok = true;
 
@@ -190,10 +201,27 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
 #pragma unroll
             for (int j = 0; j < 64; ++j) u[j] = fmaf(u[j] * rstd, vec[256 + cb + j], vec[384 + cb + j]);
         }
-        if (row < rows) {
+        if (u_out != nullptr && row < rows) {
             float* dst = u_out + (size_t)row * kHidden + cb;
 #pragma unroll
             for (int j = 0; j < 64; j += 4) st4(dst + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
+        }
+        if (heads_out != nullptr) {
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                d0 = fmaf(u[j], vec[512 + cb + j], d0);
+                d1 = fmaf(u[j], vec[640 + cb + j], d1);
+                d2 = fmaf(u[j], vec[768 + cb + j], d2);
+            }
+            float* s3 = xg + 3 * 512;                      // slots 3 and 4: written once per tile
+            s3[half * 256 + trow * 2] = d0;
+            s3[half * 256 + trow * 2 + 1] = d1;
+            s3[512 + half * 256 + trow * 2] = d2;
+            named_bar_sync(1 + grp, 256);
+            if (half == 0 && row < rows)
+                heads_out[row] = make_float4(d0 + s3[256 + trow * 2], d1 + s3[256 + trow * 2 + 1],
+                                             d2 + s3[512 + 256 + trow * 2], 0.f);
         }
     }
     tc_fence_before();
@@ -204,7 +232,9 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
 }  // namespace tc
 
 static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, const float* bias, const float* gamma,
-                                      const float* beta, float* u_out, int rows, int depth, cudaStream_t st) {
+                                      const float* beta, float* u_out, int rows, int depth, cudaStream_t st,
+                                      const float* w_cls = nullptr, const float* w_loc = nullptr,
+                                      float* heads_out = nullptr) {
     static bool opted = false;
     if (!opted) {
         cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -216,6 +246,6 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
     const int grid = n_pairs < tc::num_sms() ? n_pairs : tc::num_sms();
     tc::fc_stack_tc_kernel<<<grid, 512, tc::kFcSmemBytes, st>>>(
         u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
-        depth);
+        depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out));
     return cudaGetLastError();
 }

@@ -201,6 +201,9 @@ fc_stack_kernel(const float* __restrict__ u_in, const float* __restrict__ w, con
 struct ScaleList { int n; int s[kMaxScales]; };
 constexpr int kRoiMaxHalo = 64;                                   // scales <= 128
 
+// FROM_HEADS: `u` is the [rows][4] array of head projections the fc stack already emitted (fc_stack_tc_kernel), the
+// first phase is a plain copy.
+template <bool FROM_HEADS>
 __global__ void __launch_bounds__(256)
 roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
                       ScaleList scales, int halo, const float* __restrict__ w_cls, const float* __restrict__ b_cls,
@@ -217,7 +220,15 @@ roi_pool_heads_kernel(const float* __restrict__ u, const int* __restrict__ cu_ro
     const float4 w1 = ldg4(w_loc + kHidden + lane * 4);
     const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
     const int grp = (lane >> 3) & 3;                               // which of the 4 rows this lane ends up holding
-    for (int r8 = warp * 8; r8 < nrows; r8 += 64) {
+    if (FROM_HEADS) {
+        for (int r = tid; r < nrows; r += 256) {
+            const int t = t0 - halo + r;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < vi.T) d = ldg4(u + (size_t)(vi.row0 + t) * 4);
+            sd[0][r] = d.x; sd[1][r] = d.y; sd[2][r] = d.z;
+        }
+    }
+    for (int r8 = warp * 8; !FROM_HEADS && r8 < nrows; r8 += 64) {
         // eight rows per warp and trip: eight independent 128-bit loads per lane in flight
         float4 x[8];
 #pragma unroll
