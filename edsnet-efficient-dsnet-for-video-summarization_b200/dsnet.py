@@ -312,6 +312,42 @@ class DSNet(nn.Module):
             out.append((ks[o:o + c].copy(), kb[o:o + c].copy()))
         return out
 
+    # ------------------------------------------------------------------ CUDA-graph replay for repeated shapes
+    def graphed_forward(self, lengths: Sequence[int], device=None):
+        """Capture `forward_packed` for one fixed list of video lengths into a CUDA graph and return
+        `run(x) -> (pred_cls, pred_loc)`.  A single TVSum-sized video is 13 launches of a few microseconds each, so the
+        eager call is bound by launch latency; a replay submits them with one driver call.  `run` copies x into the
+        graph's static input and returns views of its static outputs (overwritten by the next call).  The graph holds
+        the weights' operand planes of the moment: capture again after a parameter update.  eval() / no_grad only."""
+        if self.training:
+            raise RuntimeError("graphed_forward replays the inference kernels: call model.eval() first")
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("graphed_forward needs the model on a CUDA device (there is no CPU fallback)")
+        plan = BatchPlan.build([int(t) for t in lengths])
+        batch = plan.to(dev)
+        x_static = torch.zeros((plan.total_rows, NUM_FEATURE), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            self._forward_nograd(x_static, batch)                      # warm-up: weight planes, workspace, smem opt-ins
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    out = self._forward_nograd(x_static, batch)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        keep = (batch, self._workspace, self._wcache)                  # everything the captured launches point at
+
+        def run(x: torch.Tensor):
+            self._check_input(x)
+            x_static.copy_(x.reshape(plan.total_rows, NUM_FEATURE))
+            graph.replay()
+            return out
+
+        run.graph, run.keep = graph, keep
+        return run
+
     # ------------------------------------------------------------------ reference surface
     def forward(self, x: torch.Tensor):
         """x: (1, T, 1024) float32 on a CUDA device -> pred_cls (T, S), pred_loc (T, S, 2)   (dsnet.py:100-115)."""

@@ -673,6 +673,21 @@ def test_forward_stays_inside_its_buffers(precision):
         assert torch.equal(cls, ref_cls)
 
 
+def test_graphed_forward_replays_identical_outputs():
+    """CUDA-graph replay of the forward for a fixed shape: bit-identical to the eager call, for fresh inputs."""
+    p = orc.synth_params(8, "xavier")
+    model = make_model(p, [12], 5, "fp16x3", DEV)
+    run = model.graphed_forward([320])
+    for seed in (1, 2, 3):
+        x = orc.synth_features(320, seed).to(DEV)
+        with torch.no_grad():
+            c0, l0 = model(x[None])
+        c1, l1 = run(x[None])
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c1) and torch.equal(l0, l1)
+    _no_tc_timeout()
+
+
 # ------------------------------------------------------------------------------------------------ evaluation metrics
 EV = load_npz("eval_golden.npz")
 

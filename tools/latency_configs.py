@@ -43,6 +43,17 @@ def main():
                     ts.append(e0.elapsed_time(e1))
                 res[what + "_ms"] = float(np.median(ts[3:]))
             res["kept"] = int(r["keep_count"].cpu()[0])
+            # the same forward replayed as a CUDA graph (launch latency removed)
+            run = m.graphed_forward([T])
+            ts = []
+            for it in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run.graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res["forward_graph_ms"] = float(np.median(ts[3:]))
         out[name] = res
         print(name, res, flush=True)
     if "--cpu" in sys.argv:
