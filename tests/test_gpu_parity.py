@@ -688,6 +688,28 @@ def test_graphed_forward_replays_identical_outputs():
     _no_tc_timeout()
 
 
+@pytest.mark.parametrize("scale", [1e-4, 30.0, 1e3])
+def test_input_magnitude_robustness(scale):
+    """Features scaled over seven orders of magnitude (the plane scales of the tensor-core path are partly taken from
+    bounds, not maxima): the fp16x3 path stays within a small multiple of the error floor the reference's own fp32
+    arithmetic has against float64 on the same input."""
+    p = orc.synth_params(5, "xavier")
+    scales = [4, 8, 16, 32]
+    x = orc.synth_features(100, 77) * scale
+    with torch.no_grad():
+        c64, l64 = orc.dsnet_forward(x.double(), {k: v.double() for k, v in p.items()}, scales, 5)
+        c32, l32 = orc.dsnet_forward(x, p, scales, 5)
+    floor = max(orc.rel_l2(l32.numpy(), l64.numpy()), orc.rel_l2(c32.numpy(), c64.numpy()))
+    model = make_model(p, scales, 5, "fp16x3", DEV)
+    with torch.no_grad():
+        c, l = model(x[None].to(DEV))
+    _no_tc_timeout()
+    e_cls = orc.rel_l2(c.cpu().numpy(), c64.numpy())
+    e_loc = orc.rel_l2(l.cpu().numpy(), l64.numpy())
+    print(scale, e_cls, e_loc, floor)
+    assert max(e_cls, e_loc) <= 5 * floor + 5e-6
+
+
 # ------------------------------------------------------------------------------------------------ evaluation metrics
 EV = load_npz("eval_golden.npz")
 
