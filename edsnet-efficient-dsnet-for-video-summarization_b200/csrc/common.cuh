@@ -3,6 +3,20 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <mutex>
+#include <set>
+#include <utility>
+
+// Function attributes (dynamic shared-memory opt-in) and device limits are per DEVICE, not per process: true exactly
+// once per (current device, tag), so a process that drives several GPUs configures each of them.
+inline bool first_use_on_device(const void* tag) {
+    static std::mutex m;
+    static std::set<std::pair<int, const void*>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(m);
+    return seen.insert({dev, tag}).second;
+}
 
 // Fixed geometry of the reference path (modules/models.py:135, anchor_based/dsnet.py:66-98).
 constexpr int kHeads    = 8;      // num_head

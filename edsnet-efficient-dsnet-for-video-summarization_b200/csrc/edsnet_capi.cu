@@ -168,22 +168,20 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (!tc::make_map(&map_hi, p_hi, (uint64_t)b->total_rows, kQkvCols, 64, 64, &msg) ||
             !tc::make_map(&map_lo, p_lo, (uint64_t)b->total_rows, kQkvCols, 64, 64, &msg))
             return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
-        static bool tc_attr = false;
-        if (!tc_attr) {
+        static const char tc_tag = 0;
+        if (first_use_on_device(&tc_tag)) {
             CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
             CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
             CU_CHECK(opt_in_smem(tc::value_conv_tc_kernel, tc::kCvSmemBytes), "smem opt-in value_conv_tc");
             CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
-            tc_attr = true;
         }
     }
-    static bool attrs_done = false;     // per-process; the attribute is per device function
-    if (!attrs_done) {
+    static const char f32_tag = 0;
+    if (first_use_on_device(&f32_tag)) {
         CU_CHECK(opt_in_smem(a3v_kernel, kA3vSmem), "smem opt-in a3v");
         CU_CHECK(opt_in_smem(pinv_w_kernel, kPinvSmem), "smem opt-in pinv");
         CU_CHECK(opt_in_smem(attn_out_kernel, kAttnOutSmem), "smem opt-in attn_out");
-        attrs_done = true;
     }
     const int V = b->n_videos;
     {
@@ -261,11 +259,8 @@ int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float
                                     st, w->cls_w, w->loc_w, heads_out), "fc_stack_tc_kernel");
         return EDSNET_OK;
     }
-    static bool attrs_done = false;
-    if (!attrs_done) {
-        CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
-        attrs_done = true;
-    }
+    static const char fcs_tag = 0;
+    if (first_use_on_device(&fcs_tag)) CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
     fc_stack_kernel<<<(rows + 63) / 64, 256, kFcStackSmem, st>>>(u_in, w->fcb_w, w->fcb_b, w->fcb_ln_w,
                                                                   w->fcb_ln_b, u_out, rows, cfg->fc_depth);
     CU_CHECK(cudaGetLastError(), "fc_stack_kernel");
@@ -459,11 +454,8 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
                            nullptr, nullptr, 0, st);
         if (rc) return rc;
         {
-            static bool mha_attr = false;
-            if (!mha_attr) {
-                CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
-                mha_attr = true;
-            }
+            static const char mha_tag = 0;
+            if (first_use_on_device(&mha_tag)) CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
             StageScope scope(ST_A3V, st);
             mha_flash_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kMhaSmem, st>>>(
                 F(L.qkv), batch->cu_rows, reinterpret_cast<const int2*>(batch->tiles64), F(L.merged));
@@ -563,12 +555,11 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
                   reinterpret_cast<const long long*>(shots->cu_frames), shots->capacity, shots->gcd,
                   reinterpret_cast<const long long*>(shots->dp_off)};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool stack_set = false;
-    if (!stack_set) {                     // numpy_pairwise_sum recurses (depth <= log2(n / 128) + 1)
+    static const char stack_tag = 0;
+    if (first_use_on_device(&stack_tag)) {        // numpy_pairwise_sum recurses (depth <= log2(n / 128) + 1)
         size_t cur = 0;
         if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < 4096)
             CU_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 4096), "stack size");
-        stack_set = true;
     }
     keyshot_summary_kernel<<<batch->n_videos, 256, 0, st>>>(batch->cu_rows, cfg->n_scales, sh, keep_count, keep_scores,
                                                            keep_boxes, pos_scores, frame_scores, seg_scores, picked,
@@ -623,11 +614,9 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     int cap = 32;
     while (cap < max_n && cap < kNmsSmemCap) cap <<= 1;
     const int nms_smem = cap * 24;
-    static int nms_opted = 0;
-    if (nms_smem > nms_opted) {
-        CU_CHECK(opt_in_smem(nms_kernel, nms_smem), "smem opt-in nms");
-        nms_opted = nms_smem;
-    }
+    // the largest size (4096 anchors x 24 B = 96 KB) once per device covers every launch
+    static const char nms_tag = 0;
+    if (first_use_on_device(&nms_tag)) CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemCap * 24), "smem opt-in nms");
     {
         StageScope scope(ST_DECODE, st);
         decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0, st>>>(

@@ -235,12 +235,11 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
                                       const float* beta, float* u_out, int rows, int depth, cudaStream_t st,
                                       const float* w_cls = nullptr, const float* w_loc = nullptr,
                                       float* heads_out = nullptr) {
-    static bool opted = false;
-    if (!opted) {
+    static const char tag = 0;
+    if (first_use_on_device(&tag)) {
         cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tc::kFcSmemBytes);
         if (e != cudaSuccess) return e;
-        opted = true;
     }
     const int n_pairs = ((rows + tc::kFcTile - 1) / tc::kFcTile + 1) / 2;
     const int grid = n_pairs < tc::num_sms() ? n_pairs : tc::num_sms();

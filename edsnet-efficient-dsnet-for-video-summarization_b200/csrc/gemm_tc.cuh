@@ -585,11 +585,10 @@ cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M
     if (!make_map(&mapA, A16, 2ull * M, K, BK, Cfg::BM, msg)) return cudaErrorUnknown;
     if (!make_map(&mapB, B16, 2ull * N, K, BK, BN, msg)) return cudaErrorUnknown;
     auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI, ACCS>;
-    static bool opted = false;
-    if (!opted) {
+    static const char tag = 0;                      // one per template instantiation
+    if (first_use_on_device(&tag)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
-        opted = true;
     }
     const int n_tiles = (N / BN) * ((M + Cfg::BM - 1) / Cfg::BM);
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();

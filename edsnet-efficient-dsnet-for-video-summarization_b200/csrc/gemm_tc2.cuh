@@ -233,11 +233,10 @@ cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, i
     if (!make_map(&mapA, A16, 2ull * M, K, Cfg::BK, Cfg::BM, msg)) return cudaErrorUnknown;
     if (!make_map(&mapB, B16, 2ull * N, K, Cfg::BK, Cfg::BN / 2, msg)) return cudaErrorUnknown;
     auto kern = gemm_tc2_kernel<STAGES, EPI>;
-    static bool opted = false;
-    if (!opted) {
+    static const char tag = 0;                      // one per template instantiation
+    if (first_use_on_device(&tag)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
-        opted = true;
     }
     const int n_tiles = (N / Cfg::BN) * ((M + 2 * Cfg::BM - 1) / (2 * Cfg::BM));
     const int max_pairs = num_sms() / 2;

@@ -205,11 +205,10 @@ static cudaError_t launch_nms_large(const float* scores_v, const int* boxes_v, i
     unsigned char* dead = scratch + (size_t)P * 24;
     int* counters = reinterpret_cast<int*>(scratch + (size_t)P * 24 + kNmsBlock);
     const int2* boxes = reinterpret_cast<const int2*>(boxes_v);
-    static bool opted = false;
-    if (!opted) {
+    static const char tag = 0;
+    if (first_use_on_device(&tag)) {
         cudaError_t ea = cudaFuncSetAttribute(nmsl_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsResolveSmem);
         if (ea != cudaSuccess) return ea;
-        opted = true;
     }
     cudaError_t e = cudaMemsetAsync(dead, 0, kNmsBlock, st);
     if (e != cudaSuccess) return e;
