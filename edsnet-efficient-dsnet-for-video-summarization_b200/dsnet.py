@@ -118,6 +118,7 @@ class DSNet(nn.Module):
         self._wcache = None
         self._wkey = None
         self._workspace = None
+        self._workspaces = {}
 
     # ------------------------------------------------------------------ weights / workspace
     def _named_weights(self):
@@ -184,12 +185,15 @@ class DSNet(nn.Module):
         return w
 
     def _get_workspace(self, cfg, total_rows: int, n_videos: int, device):
+        """One workspace per (device, stream): forwards enqueued on different streams may overlap on the GPU."""
         need = _capi.lib().edsnet_workspace_bytes(cfg, total_rows, n_videos, None)
-        ws = self._workspace
-        if ws is None or ws.device != device or ws.numel() < need:
-            self._workspace = None
-            ws = torch.empty(int(need * 1.0), dtype=torch.uint8, device=device)
-            self._workspace = ws
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < need:
+            self._workspaces.pop(key, None)
+            ws = torch.empty(int(need), dtype=torch.uint8, device=device)
+            self._workspaces[key] = ws
+        self._workspace = ws                              # the most recently used one (tests read intermediates from it)
         return ws, need
 
     def launches_per_forward(self) -> int:
