@@ -173,7 +173,8 @@ landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict_
 // TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kA3Stage = 8 * 8192;                                          // k_h0 k_h1 v_h0 v_h1, hi and lo
-constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4;                   // key scales [2 stages][4][64] + pair exchange
+constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32;              // key scales [2 stages][4][64] + pair exchange
+                                                                            // + largest v scale [2 stages][2 heads][2 warps]
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
 // 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
@@ -189,6 +190,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     constexpr int oQl = 0, oKV = 32768, oP = 32768 + 2 * kA3Stage, oVec = oP + 32768;
     float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
     float* s_pair = sc_vec + 2 * 4 * 64;                                    // [2 halves][128 rows]
+    float* s_vmx = s_pair + 2 * 128;                                        // [stage][head][warp 2 | warp 3]
     // barriers: K full[2] +0, K empty[2] +16, S done +32, P.V done +40, V full[2] +48, V empty[2] +64, S read out +80,
     // P in place +88; TMEM slot +96
     const uint32_t bars = base + oVec + kA3VecBytes;
@@ -224,8 +226,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         const int key = tid & 63, part = 1 + (tid >> 6);
         const bool in = key < vi.T;
         const float* ip = inv + (size_t)(vi.row0 + (in ? key : 0)) * 24 + part * 8 + h0;
-        sc_vec[((tid >> 6) * 2 + 0) * 64 + key] = in ? __ldg(ip) : 0.f;
-        sc_vec[((tid >> 6) * 2 + 1) * 64 + key] = in ? __ldg(ip + 1) : 0.f;
+        const float sc0 = in ? __ldg(ip) : 0.f, sc1 = in ? __ldg(ip + 1) : 0.f;
+        sc_vec[((tid >> 6) * 2 + 0) * 64 + key] = sc0;
+        sc_vec[((tid >> 6) * 2 + 1) * 64 + key] = sc1;
+        if (tid >= 64) {                                   // warps 2, 3 hold the v scales: their maxima per head
+            const float m0 = warp_max(sc0), m1 = warp_max(sc1);
+            if (lane == 0) { s_vmx[0 * 2 + (warp - 2)] = m0; s_vmx[1 * 2 + (warp - 2)] = m1; }
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -339,14 +346,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             const float* isk = sc_vec + (s * 4 + hh) * 64 + half * 32;
             const float* isv = sc_vec + (s * 4 + 2 + hh) * 64 + half * 32;
             const int kvalid = vi.T - i * 64 - half * 32;
-            float mx = -INFINITY, vmx = 0.f;
+            float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 p[j] = j < kvalid ? p[j] * (inv_ql * isk[j]) : -INFINITY;
                 mx = fmaxf(mx, p[j]);
             }
-#pragma unroll
-            for (int j = 0; j < 64; ++j) vmx = fmaxf(vmx, sc_vec[(s * 4 + 2 + hh) * 64 + j]);   // same for both halves
+            const float vmx = fmaxf(s_vmx[(s * 2 + hh) * 2], s_vmx[(s * 2 + hh) * 2 + 1]);   // largest v scale of the tile
             s_pair[half * 128 + row] = mx;
             tc_fence_before();
             mbar_arrive(bars + 80);                                         // this thread holds its S(i) values
@@ -355,6 +361,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             if (tid < 128) {
                 sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
                 sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 1) * 64 + (tid & 63)] = nsc1;
+                if (tid >= 64) {
+                    const float m0 = warp_max(nsc0), m1 = warp_max(nsc1);
+                    if (lane == 0) {
+                        s_vmx[(((i + 1) & 1) * 2 + 0) * 2 + (warp - 2)] = m0;
+                        s_vmx[(((i + 1) & 1) * 2 + 1) * 2 + (warp - 2)] = m1;
+                    }
+                }
             }
             const float new_max = fmaxf(run_max, fmaxf(mx, s_pair[(half ^ 1) * 128 + row]));
             const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
