@@ -7,6 +7,7 @@ Public surface:
   ScoringPipeline  host-buffer -> proposals throughput path (pinned H2D / compute / D2H overlapped)
   ShotPlan / keyshot_summaries   kept proposals -> keyshot summaries on the device (bbox2summary)
   TruthPlan / eval_metrics / evaluate   F-score and diversity of the summaries on the device (evaluate.py)
+  kts_change_points / kts_shots   kernel temporal segmentation (shot boundaries) on the device
   training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
 from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
@@ -15,5 +16,6 @@ from .pipeline import ScoringPipeline                            # noqa: F401
 from . import training                                           # noqa: F401
 from .summary import ShotPlan, keyshot_summaries, keyshot_from_scores, training_targets, split_summaries  # noqa: F401
 from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
+from .kts import kts_change_points, kts_shots                      # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 4
+EDSNET_ABI_VERSION = 5
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -71,6 +71,9 @@ SYMBOLS = {
     "edsnet_keyshot_summary": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), C.POINTER(Shots), _P, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _P]),
     "edsnet_eval_metrics": (C.c_int, [C.POINTER(Batch), _P, _P, C.POINTER(EvalTruth), _P, _P, _P, _P, _P, _P]),
+    "edsnet_kts_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "edsnet_kts": (C.c_int, [C.POINTER(Batch), _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                             _P, _P, _P, _P, _P]),
     "edsnet_decode_boxes": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_forward_launches": (C.c_int, [C.POINTER(Config)]),
     "edsnet_split_f16_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

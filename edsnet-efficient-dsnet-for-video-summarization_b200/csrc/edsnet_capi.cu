@@ -19,6 +19,7 @@
 #include "nms_large.cuh"
 #include "summary.cuh"
 #include "eval.cuh"
+#include "kts.cuh"
 
 namespace {
 
@@ -516,6 +517,40 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     if (rc) return rc;
     // 6. ROI pooling + heads                                                    (dsnet.py:110-115)
     return roi_impl(cfg, w, batch, F(L.u1), pred_cls, pred_loc, st, heads_fused);
+}
+
+size_t edsnet_kts_scratch_bytes(int32_t n) { return n > 0 ? kts_video_bytes(n) : 0; }
+
+int edsnet_kts(const edsnet_batch* batch, const edsnet_kts_video* videos, const float* x, int32_t ncp_cap,
+               int32_t m_fixed, double vmax, int32_t desc_rate, int32_t lmin, int32_t lmax, int32_t* n_cps,
+               int32_t* cps, double* objective, void* scratch, void* stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (!videos || !n_cps || !cps || !scratch) return fail(EDSNET_E_ARG, "kts: NULL operand");
+    if (lmin < 1 || lmax < lmin || desc_rate < 1) return fail(EDSNET_E_ARG, "kts: need 1 <= lmin <= lmax, desc_rate >= 1");
+    const int nmax = batch->max_rows;
+    const size_t dp_smem = 2 * (size_t)(nmax + 1) * sizeof(double);
+    if (nmax > 12800) return fail(EDSNET_E_UNSUPPORTED, "kts: more than 12800 frames in one video");
+    static_assert(sizeof(edsnet_kts_video) == sizeof(KtsVideo), "video record layout");
+    const KtsVideo* vids = reinterpret_cast<const KtsVideo*>(videos);
+    unsigned char* scr = static_cast<unsigned char*>(scratch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int V = batch->n_videos;
+    if (x != nullptr) {
+        const unsigned t16 = (unsigned)((nmax + 15) / 16);
+        kts_gram_kernel<<<dim3(t16, t16, V), 256, 0, st>>>(x, vids, scr);
+        CU_CHECK(cudaGetLastError(), "kts_gram_kernel");
+    }
+    kts_prefix_kernel<<<V, 256, 0, st>>>(vids, scr);
+    CU_CHECK(cudaGetLastError(), "kts_prefix_kernel");
+    kts_scatter_kernel<<<dim3((unsigned)(((size_t)nmax * nmax + 255) / 256), V), 256, 0, st>>>(vids, scr);
+    CU_CHECK(cudaGetLastError(), "kts_scatter_kernel");
+    static const char dp_tag = 0;
+    if (first_use_on_device(&dp_tag)) CU_CHECK(opt_in_smem(kts_dp_kernel, 2 * (12800 + 1) * (int)sizeof(double)), "smem opt-in kts_dp");
+    kts_dp_kernel<<<V, 1024, dp_smem, st>>>(vids, scr, ncp_cap, m_fixed, vmax, desc_rate, lmin, lmax, batch->cu_rows,
+                                           n_cps, cps, objective);
+    CU_CHECK(cudaGetLastError(), "kts_dp_kernel");
+    return EDSNET_OK;
 }
 
 int edsnet_eval_metrics(const edsnet_batch* batch, const int64_t* cu_frames, const uint8_t* summary,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 4
+#define EDSNET_ABI_VERSION 5
 
 enum {
     EDSNET_OK = 0,
@@ -199,6 +199,29 @@ typedef struct {
 int edsnet_eval_metrics(const edsnet_batch* batch, const int64_t* cu_frames, const uint8_t* summary,
                         const edsnet_eval_truth* truth, const float* x, double* fscore, double* diversity,
                         double* user_f1, int32_t* counts, void* stream);
+
+/* One video of an edsnet_kts call: its block inside the scratch buffer and its rows in the packed features. */
+typedef struct {
+    int64_t scratch_off;       /* byte offset, multiple of 256; the block holds edsnet_kts_scratch_bytes(n) bytes */
+    int32_t row0;              /* first packed feature row (== cu_rows[v])                                        */
+    int32_t n;                 /* frames (== T of the video)                                                      */
+} edsnet_kts_video;
+
+/* Kernel temporal segmentation (kts/cpd_auto.py:6-33, kts/cpd_nonlin.py:4-92), the shot boundaries the reference
+ * computes from the sub-sampled features (helpers/video_helper.py:109-126) before it scores a video.
+ *   videos [dev][n_videos]; x [dev][total_rows][1024] or NULL: with NULL every video's float32 kernel matrix
+ *   (n x n, row-major) must already sit at the start of its scratch block (np.matmul(features, features.T) of the
+ *   caller); ncp_cap < 0: at most n - 1 change points (video_helper.py:118); m_fixed >= 0: exactly that many
+ *   (cpd_nonlin) instead of cpd_auto's penalised choice; vmax / desc_rate / lmin / lmax as cpd_auto / cpd_nonlin.
+ *   Outputs: n_cps [dev][n_videos]; cps [dev][total_rows] (video v's change points, ascending, from entry cu_rows[v]);
+ *   objective [dev][total_rows] float64 (may be NULL): the objective for 0 .. n_cps[v] change points.
+ * For a given kernel matrix the change points are the reference's bit for bit (same float32 / float64 operations in
+ * the same order, first minimum); K = X X^T itself is computed in float32 in a fixed order, which the reference's
+ * BLAS does not promise.  n is limited to 12 800 frames (two DP rows in shared memory). */
+size_t edsnet_kts_scratch_bytes(int32_t n);
+int edsnet_kts(const edsnet_batch* batch, const edsnet_kts_video* videos, const float* x, int32_t ncp_cap,
+               int32_t m_fixed, double vmax, int32_t desc_rate, int32_t lmin, int32_t lmax, int32_t* n_cps,
+               int32_t* cps, double* objective, void* scratch, void* stream);
 
 /* decode only (what DSNet.predict returns, dsnet.py:146-153, plus the evaluate.py:26 clip/round):
  * boxes_f32 [dev][total_rows*S][2] (may be NULL), boxes_i32 [dev][total_rows*S][2] (may be NULL). */

@@ -484,6 +484,83 @@ def summ_diversity(pred_summ: np.ndarray, features: np.ndarray) -> float:
 
 
 # --------------------------------------------------------------------------
+# kernel temporal segmentation (the shot boundaries infer.py feeds the path with):
+# kts/cpd_nonlin.py:4-92, kts/cpd_auto.py:6-33, helpers/video_helper.py:109-126
+# --------------------------------------------------------------------------
+
+def kts_scatters(K: np.ndarray) -> np.ndarray:
+    """kts/cpd_nonlin.py:4-27.  J[i, j] = within-segment scatter of frames i..j (0 below the diagonal).  The 2-D
+    prefix sums run in K's own dtype (float32 for a float32 kernel matrix, sequential along each axis), everything
+    else in float64, in the reference's operation order."""
+    n = K.shape[0]
+    k1 = np.cumsum(np.concatenate([[0.0], np.diag(K).astype(np.float64)]))
+    k2 = np.zeros((n + 1, n + 1))
+    k2[1:, 1:] = np.cumsum(np.cumsum(K, axis=0), axis=1)
+    d2 = np.diag(k2)
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    length = (jj - ii + 1).astype(np.float32) + (jj == ii - 1).astype(np.float32)
+    cross = ((d2[1:][None, :] + d2[:-1][:, None]) - k2[1:, :-1].T) - k2[:-1, 1:]
+    J = (k1[1:][None, :] - k1[:-1][:, None]) - cross / length
+    J[jj < ii] = 0
+    return J
+
+
+def kts_dp(K: np.ndarray, m: int, lmin: int = 1, lmax: int = 100000):
+    """kts/cpd_nonlin.py:30-92 with back-tracking: change points of the best segmentation into m+1 pieces and the
+    objective for 0..m change points.  One vectorised row update per k (the reference loops over l in Python)."""
+    m = int(m)
+    n = K.shape[0]
+    assert (m + 1) * lmin <= n <= (m + 1) * lmax and 1 <= lmin <= lmax
+    J = kts_scatters(K)
+    BIG = 1e101
+    I = np.full((m + 1, n + 1), BIG)
+    hi = min(lmax, n + 1)
+    I[0, lmin:hi] = J[0, lmin - 1:hi - 1]
+    prev = np.zeros((m + 1, n + 1), dtype=np.int64)
+    for k in range(1, m + 1):
+        for l in range((k + 1) * lmin, n + 1):
+            t0, t1 = max(k * lmin, l - lmax), l - lmin + 1
+            c = J[t0:t1, l - 1] + I[k - 1, t0:t1]
+            a = int(np.argmin(c))
+            I[k, l] = c[a]
+            prev[k, l] = a + t0
+    cps = np.zeros(m, dtype=np.int64)
+    cur = n
+    for k in range(m, 0, -1):
+        cps[k - 1] = prev[k, cur]
+        cur = cps[k - 1]
+    scores = I[:, n].copy()
+    scores[scores > 1e99] = np.inf
+    return cps, scores
+
+
+def kts_auto(K: np.ndarray, ncp: int, vmax: float, desc_rate: int = 1, lmin: int = 1, lmax: int = 100000):
+    """kts/cpd_auto.py:6-33: number of change points chosen by the penalised objective, then the segmentation."""
+    m = int(ncp)
+    _, scores = kts_dp(K, m, lmin, lmax)
+    N = K.shape[0]
+    N2 = N * desc_rate
+    pen = np.zeros(m + 1)
+    q = np.arange(1, m + 1)
+    pen[1:] = (vmax * q / (2.0 * N2)) * (np.log(float(N2) / q) + 1)
+    costs = scores / float(N) + pen
+    m_best = int(np.argmin(costs))
+    return kts_dp(K, m_best, lmin, lmax)
+
+
+def kts_shots(n_frames: int, features: np.ndarray, sample_rate: int = 15):
+    """helpers/video_helper.py:109-126: (change_points [n_seg, 2] inclusive, frames per segment, picks)."""
+    T = len(features)
+    picks = np.arange(0, T) * sample_rate
+    K = np.matmul(features, features.T)
+    cps, _ = kts_auto(K, T - 1, 1)
+    cps = cps * sample_rate
+    cps = np.hstack((0, cps, n_frames))
+    begin, end = cps[:-1], cps[1:]
+    return np.vstack((begin, end - 1)).T, end - begin, picks
+
+
+# --------------------------------------------------------------------------
 # error metrics used by every parity test
 # --------------------------------------------------------------------------
 

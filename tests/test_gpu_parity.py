@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated golden vectors.
 Every test here needs a B200: `pytest -m gpu`."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -785,3 +786,54 @@ def test_evaluate_loop_vs_oracle():
     assert fs == float(sum(want_f) / len(want_f)), (fs, want_f)
     assert abs(dv - sum(want_d) / len(want_d)) < 1e-5
     assert 0.0 < fs < 1.0
+
+
+# ------------------------------------------------------------------------------------------------ temporal segmentation
+KTS = load_npz("kts_golden.npz")
+
+
+def _kts_features(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_kts_golden_helpers", os.path.join(os.path.dirname(__file__), "golden", "make_kts_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.piecewise_features(int(KTS[f"{name}/T"]), int(KTS[f"{name}/seed"]))
+
+
+def test_kts_bit_exact_on_reference_kernel_matrices():
+    """edsnet_kts on the float32 kernel matrices the reference computed: change points and float64 objective values of
+    cpd_auto (and of cpd_nonlin with 3 change points) bit for bit, all golden videos in one packed call."""
+    from edsnet_b200 import kts_change_points
+    names = [str(n) for n in KTS["cases"]]
+    lengths = [int(KTS[f"{n}/T"]) for n in names]
+    x = torch.zeros((sum(lengths), 1024), device=DEV)
+    kernels = [KTS[f"{n}/K"] for n in names]
+    cps, obj = kts_change_points(x, lengths, kernels=kernels)
+    for n, c, o in zip(names, cps, obj):
+        assert np.array_equal(c, KTS[f"{n}/cps"]), (n, c, KTS[f"{n}/cps"])
+        assert np.array_equal(o, KTS[f"{n}/scores"]), n
+    cps3, obj3 = kts_change_points(x, lengths, kernels=kernels, m_fixed=3)
+    for n, t, c, o in zip(names, lengths, cps3, obj3):
+        if t >= 4:
+            assert np.array_equal(c, KTS[f"{n}/cps3"]) and np.array_equal(o, KTS[f"{n}/scores3"]), n
+
+
+def test_kts_from_features_and_shot_tables():
+    """Features -> X X^T on the device -> segmentation: same change points as the reference found (its BLAS and the
+    device sum X X^T in different orders, the objective agrees to float32 rounding), and the shot tables of
+    VideoPreprocessor.kts."""
+    from edsnet_b200 import kts_change_points, kts_shots
+    names = [str(n) for n in KTS["cases"]]
+    feats = [_kts_features(n) for n in names]
+    for n, f in zip(names, feats):
+        assert orc.rel_l2(np.matmul(f, f.T), KTS[f"{n}/K"]) < 1e-6          # the committed generator reproduces the inputs
+    x = torch.from_numpy(np.concatenate(feats)).to(DEV)
+    cps, obj = kts_change_points(x, [len(f) for f in feats])
+    for n, c, o in zip(names, cps, obj):
+        assert np.array_equal(c, KTS[f"{n}/cps"]), (n, c, KTS[f"{n}/cps"])
+        assert np.allclose(o, KTS[f"{n}/scores"], rtol=1e-4, atol=1e-4)
+    n = "t150"
+    f = feats[names.index(n)]
+    cp, nfps, picks = kts_shots(int(KTS[f"{n}/n_frames"]), torch.from_numpy(f).to(DEV), int(KTS[f"{n}/rate"]))
+    assert np.array_equal(cp, KTS[f"{n}/change_points"]) and np.array_equal(nfps, KTS[f"{n}/nfps"])
+    assert np.array_equal(picks, np.arange(len(f)) * 15)
