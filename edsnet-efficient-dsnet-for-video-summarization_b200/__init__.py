@@ -8,6 +8,7 @@ Public surface:
   ShotPlan / keyshot_summaries   kept proposals -> keyshot summaries on the device (bbox2summary)
   TruthPlan / eval_metrics / evaluate   F-score and diversity of the summaries on the device (evaluate.py)
   kts_change_points / kts_shots   kernel temporal segmentation (shot boundaries) on the device
+  summarize        infer.py's chain from the sampled features on: segmentation -> scores -> NMS -> keyshot summary
   training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
 from .plan import BatchPlan, DeviceBatch, shard_videos          # noqa: F401
@@ -17,5 +18,6 @@ from . import training                                           # noqa: F401
 from .summary import ShotPlan, keyshot_summaries, keyshot_from_scores, training_targets, split_summaries  # noqa: F401
 from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
 from .kts import kts_change_points, kts_shots                      # noqa: F401
+from .infer import summarize                                       # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

@@ -590,12 +590,6 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
                   reinterpret_cast<const long long*>(shots->cu_frames), shots->capacity, shots->gcd,
                   reinterpret_cast<const long long*>(shots->dp_off)};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const char stack_tag = 0;
-    if (first_use_on_device(&stack_tag)) {        // numpy_pairwise_sum recurses (depth <= log2(n / 128) + 1)
-        size_t cur = 0;
-        if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < 4096)
-            CU_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 4096), "stack size");
-    }
     keyshot_summary_kernel<<<batch->n_videos, 256, 0, st>>>(batch->cu_rows, cfg->n_scales, sh, keep_count, keep_scores,
                                                            keep_boxes, pos_scores, frame_scores, seg_scores, picked,
                                                            summary, static_cast<unsigned char*>(dp_scratch));

@@ -9,6 +9,7 @@
 //            products pair-wise: agreement to ~1e-6 relative, not bit-wise).
 #pragma once
 #include "common.cuh"
+#include "summary.cuh"
 
 struct EvalTruth {
     const int* cu_users;              // [V+1] first user row of every video
@@ -43,30 +44,9 @@ __device__ __forceinline__ double block_sum_f64(double v, double* s_red) {
     return t;
 }
 
-// float64 sum of a[0..n) in NumPy's pairwise order (numpy/_core/src/umath/loops_utils.h.src)
-__device__ double numpy_pairwise_sum_f64(const double* __restrict__ a, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    }
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = a[k];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(numpy_pairwise_sum_f64(a, n2), numpy_pairwise_sum_f64(a + n2, n - n2));
+// float64 sum of a[0..n) in NumPy's pairwise order (summary.cuh)
+__device__ __forceinline__ double numpy_pairwise_sum_f64(const double* __restrict__ a, int n) {
+    return numpy_pairwise_sum_t<double>(a, n);
 }
 
 __global__ void __launch_bounds__(256)

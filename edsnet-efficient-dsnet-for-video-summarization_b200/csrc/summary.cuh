@@ -14,31 +14,59 @@
 #pragma once
 #include "common.cuh"
 
-// float32 sum of a[0..n) exactly as NumPy's pairwise_sum (numpy/_core/src/umath/loops_utils.h.src) computes it
-__device__ float numpy_pairwise_sum(const float* __restrict__ a, int n) {
+// float32 sum of a[0..n) exactly as NumPy's pairwise_sum (numpy/_core/src/umath/loops_utils.h.src) computes it:
+// blocks of at most 128 values are summed with 8 interleaved accumulators, longer ranges are split in two (the left half
+// a multiple of 8 long) and the halves' sums added.  The recursion is unrolled onto an explicit stack (depth
+// <= log2(n / 64)), so the kernel needs no device call stack.
+template <typename T>
+__device__ __forceinline__ T numpy_pairwise_leaf(const T* __restrict__ a, int n) {
     if (n < 8) {
-        float res = 0.f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        T res = 0;
+        for (int i = 0; i < n; ++i) res = res + a[i];
         return res;
     }
-    if (n <= 128) {
-        float r[8];
+    T r[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = a[k];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], a[i + k]);
-        }
-        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
-        return res;
+        for (int k = 0; k < 8; ++k) r[k] = r[k] + a[i + k];
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __fadd_rn(numpy_pairwise_sum(a, n2), numpy_pairwise_sum(a + n2, n - n2));
+    T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res = res + a[i];
+    return res;
 }
+template <typename T>
+__device__ T numpy_pairwise_sum_t(const T* __restrict__ a, int n) {
+    if (n <= 128) return numpy_pairwise_leaf(a, n);
+    int s_off[32], s_n[32];
+    T s_left[32];
+    unsigned char s_stage[32];
+    int sp = 0;
+    s_off[0] = 0; s_n[0] = n; s_stage[0] = 0;
+    T ret = 0;
+    while (sp >= 0) {
+        const int off = s_off[sp], len = s_n[sp];
+        if (len <= 128) { ret = numpy_pairwise_leaf(a + off, len); --sp; continue; }
+        int n2 = len / 2;
+        n2 -= n2 % 8;
+        if (s_stage[sp] == 0) {
+            s_stage[sp] = 1;
+            ++sp; s_off[sp] = off; s_n[sp] = n2; s_stage[sp] = 0;
+        } else if (s_stage[sp] == 1) {
+            s_left[sp] = ret;
+            s_stage[sp] = 2;
+            ++sp; s_off[sp] = off + n2; s_n[sp] = len - n2; s_stage[sp] = 0;
+        } else {
+            ret = s_left[sp] + ret;
+            --sp;
+        }
+    }
+    return ret;
+}
+// (plain + on float / double compiles to one IEEE add each: no contraction is possible without a multiply)
+__device__ __forceinline__ float numpy_pairwise_sum(const float* __restrict__ a, int n) { return numpy_pairwise_sum_t<float>(a, n); }
 
 struct ShotTables {
     const int* cu_seg;            // [V+1]

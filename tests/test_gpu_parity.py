@@ -623,6 +623,26 @@ def test_keyshot_summary_packed_vs_oracle():
     assert seg.max() <= 1000 and seg.min() >= 0
 
 
+def test_keyshot_summary_long_uneven_shots():
+    """Shots of 15 ... 1320 frames in one video (what KTS produces on real videos): the NumPy-exact pairwise shot means
+    split ranges above 128 frames recursively; the device does that on an explicit stack (a device-recursive version
+    crashed on such tables)."""
+    from edsnet_b200 import BatchPlan, ShotPlan, keyshot_from_scores
+    model = make_model(orc.synth_params(3, "default"), [4, 8], 5, "fp32", DEV)
+    T, nf = 150, 2243
+    g = np.random.default_rng(1).random(T).astype(np.float32)
+    for cps in ([[0, 209], [210, 404], [405, 419], [420, 539], [540, 1739], [1740, 2242]],
+                [[0, 209], [210, 404], [405, 419], [420, 1739], [1740, 2242]],
+                [[0, 209], [210, 419], [420, 539], [540, 1739], [1740, 1769], [1770, 2242]], [[0, 2242]]):
+        c = np.asarray(cps)
+        w = c[:, 1] - c[:, 0] + 1
+        vd = dict(cps=c, nfps=w, picks=np.arange(T) * 15, n_frames=nf)
+        out = keyshot_from_scores(model, torch.from_numpy(g).to(DEV), BatchPlan.build([T]).to(DEV), ShotPlan([vd], DEV))
+        torch.cuda.synchronize()
+        want = orc.keyshot_summary(g, c, nf, w, vd["picks"])
+        assert np.array_equal(out["summary"].cpu().numpy().astype(bool), want)
+
+
 def test_training_targets_from_gtscore_vs_oracle():
     """anchor_based/train.py:79-84 on the device: get_keyshot_summ on ground-truth scores (no proposals) for a packed
     split, then downsample_summ -- bit-exact against the oracle's host restatement."""
@@ -837,3 +857,32 @@ def test_kts_from_features_and_shot_tables():
     cp, nfps, picks = kts_shots(int(KTS[f"{n}/n_frames"]), torch.from_numpy(f).to(DEV), int(KTS[f"{n}/rate"]))
     assert np.array_equal(cp, KTS[f"{n}/change_points"]) and np.array_equal(nfps, KTS[f"{n}/nfps"])
     assert np.array_equal(picks, np.arange(len(f)) * 15)
+
+
+def test_infer_chain_vs_oracle():
+    """infer.py:22-36 from the sampled features on (segmentation -> scores -> NMS -> keyshot summary), packed over
+    several videos, against the oracle's host chain fed with the device's kept proposals."""
+    from edsnet_b200 import summarize, BatchPlan
+    names = ["t60", "t150", "t257"]
+    feats = [_kts_features(n) for n in names]
+    lengths = [len(f) for f in feats]
+    n_frames = [int(KTS[f"{n}/n_frames"]) for n in names]
+    scales = [4, 8, 16, 32]
+    model = make_model(orc.synth_params(9, "xavier"), scales, 5, "fp16x3", DEV)
+    x = torch.from_numpy(np.concatenate(feats)).to(DEV)
+    res = summarize(model, x, lengths, n_frames, 0.5)
+    batch = BatchPlan.build(lengths).to(DEV)
+    with torch.no_grad():
+        cls, loc = model.forward_packed(x, batch)
+        nms = model.nms_packed(cls, loc, batch, 0.5)
+    counts = nms["keep_count"].cpu().numpy()
+    ks, kb = nms["keep_scores"].cpu().numpy(), nms["keep_boxes"].cpu().numpy()
+    o = 0
+    for n, t, nf, r in zip(names, lengths, n_frames, res):
+        assert np.array_equal(r["change_points"], KTS[f"{n}/change_points"]) and np.array_equal(r["nfps"], KTS[f"{n}/nfps"])
+        a, c = o * len(scales), int(counts[names.index(n)])
+        want = orc.bbox_summary(t, ks[a:a + c], kb[a:a + c], r["change_points"], nf, r["nfps"], r["picks"])
+        assert r["summary"].shape == (nf,) and np.array_equal(r["summary"], want)
+        assert r["summary"].sum() <= int(nf * 0.15)          # (no shot of t60 fits the 15 % budget: an empty summary)
+        o += t
+    assert sum(int(r["summary"].sum()) for r in res) > 0
