@@ -119,11 +119,14 @@ typedef struct {
     size_t a3v;        /* softmax(q_land k^T) v                                       */
     size_t zmat;       /* pseudo-inverse of attn2                                     */
     size_t wmat;       /* zmat a3v                                                    */
-    size_t merged;     /* [rows][512] head-merged attention output + value conv ([rows][1024] for the attention base) */
+    size_t merged;     /* [rows][512] head-merged attention output + value conv ([rows][1024] for the attention base);
+                        * tcgen05 precisions, Nystrom base: attention part only, the sum with the value conv leaves as
+                        * the to_out operand planes at x16 */
     size_t y;          /* [rows][1024] to_out + bias + x                              */
     size_t yn;         /* [rows][1024] LayerNorm(y)           (aliases qkv)           */
     size_t u0;         /* [rows][128] fc1 output                                      */
-    size_t u1;         /* [rows][128] after the fc stack                              */
+    size_t u1;         /* [rows][128] after the fc stack; tcgen05 precisions: [rows][4] head projections
+                        * (u . w_cls, u . w_loc[0], u . w_loc[1], 0), the hidden rows are not written */
     size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
     size_t zeros;      /* [1024] zero bias (attention base: its projections have no bias) */
     size_t total;
