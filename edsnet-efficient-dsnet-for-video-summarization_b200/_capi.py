@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 5
+EDSNET_ABI_VERSION = 6
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -29,7 +29,8 @@ class Config(C.Structure):
 WEIGHT_FIELDS = ("to_qkv_w", "to_out_w", "to_out_b", "res_conv_w", "ln_w", "ln_b", "fc1_w", "fc1_b",
                  "fcb_w", "fcb_b", "fcb_ln_w", "fcb_ln_b", "cls_w", "cls_b", "loc_w", "loc_b",
                  "to_qkv_w16", "to_out_w16", "fc1_w16", "fcb_w16",
-                 "mha_qkv_w", "mha_fc_w", "mha_qkv_w16", "mha_fc_w16")
+                 "mha_qkv_w", "mha_fc_w", "mha_qkv_w16", "mha_fc_w16",
+                 "fc1_fold_w16", "fc1_fold_wgsum", "fc1_fold_b", "to_out_bc", "to_out_bounds")
 
 
 class Weights(C.Structure):
@@ -43,7 +44,7 @@ class Batch(C.Structure):
 
 
 LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",
-                 "u0", "u1", "x16", "zeros", "total")
+                 "u0", "u1", "x16", "zeros", "zstat", "xstat", "total")
 
 
 class WorkspaceLayout(C.Structure):

@@ -117,14 +117,19 @@ cudaError_t opt_in_smem(K kernel, int bytes) {
 
 int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, const float* B, const void* B16,
                   float* C, int M, int N, int K, const float* bias, const float* res, int qcols, cudaStream_t st,
-                  int stage = ST_QKV, float* aux = nullptr) {
+                  int stage = ST_QKV, float* aux = nullptr, const float* aux2 = nullptr, const float* aux3 = nullptr) {
     StageScope scope(stage, st);
     if (M < 1 || N < 1 || K < 1) return fail(EDSNET_E_ARG, "gemm: empty problem");
-    if (epilogue < 0 || epilogue > 4) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
+    if (epilogue < 0 || epilogue > EPI_LN_FOLD) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
+    if (epilogue == EPI_RES_LNPLANES &&
+        (precision == EDSNET_PREC_FP32 || N != kFeat || !bias || !res || !aux || !aux2 || !aux3))
+        return fail(EDSNET_E_ARG, "gemm: the LayerNorm-plane epilogue needs a tcgen05 precision, N = 1024 and its operands");
+    if (epilogue == EPI_LN_FOLD && (precision == EDSNET_PREC_FP32 || K != kFeat || !bias || !aux || !aux2))
+        return fail(EDSNET_E_ARG, "gemm: the LayerNorm-fold epilogue needs a tcgen05 precision, K = 1024 and its operands");
     if (epilogue == 4 && (precision == EDSNET_PREC_FP32 || !aux || N != kQkvCols))
         return fail(EDSNET_E_ARG, "gemm: the plane epilogue needs a tcgen05 precision, N = 1536 and the scale output");
     if (((epilogue == 2 || epilogue == 3) && !bias) || (epilogue == 3 && !res)) return fail(EDSNET_E_ARG, "gemm: epilogue operand is NULL");
-    GemmEpiArgs ep{bias, res, N, qcols, nullptr, nullptr, aux};
+    GemmEpiArgs ep{bias, res, N, qcols, nullptr, nullptr, aux, aux2, aux3};
     if (precision == EDSNET_PREC_FP32) {
         if (!A || !B || !C) return fail(EDSNET_E_ARG, "gemm: NULL operand");
         if (K % kGemmBK || N % 4) return fail(EDSNET_E_ARG, "gemm fp32: K must be a multiple of 16, N of 4");
@@ -313,12 +318,20 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.zmat = take(head_mat);
     L.wmat = take(head_mat);
     L.merged = take(R * (mha ? kMhaFeat : kInner) * sizeof(float));
-    L.y = take(R * kFeat * sizeof(float));
+    const bool tcp = cfg && cfg->precision != EDSNET_PREC_FP32;
+    // tcgen05 precisions, Nystrom base: y leaves to_out as the fc1 operand planes (+ 4 bytes of scale per row)
+    L.y = take(tcp ? split_f16_bytes(R, kFeat) : R * kFeat * sizeof(float));
     L.u0 = take(R * kHidden * sizeof(float));
     L.u1 = take(R * kHidden * sizeof(float));
     L.x16 = off;
     if (cfg && cfg->precision != EDSNET_PREC_FP32) take(split_f16_bytes(R, kFeat));
     L.zeros = take(kFeat * sizeof(float));
+    L.zstat = off;
+    L.xstat = off;
+    if (tcp && !mha) {
+        L.zstat = take(R * 32 * sizeof(float));
+        L.xstat = take(R * 2 * sizeof(float));
+    }
     L.total = off;
     if (layout) *layout = L;
     return L.total;
@@ -387,6 +400,7 @@ int edsnet_debug_set_tc_variant(int32_t variant) {
 int edsnet_gemm(int32_t precision, int32_t epilogue, const float* A, const void* A16, const float* B,
                 const void* B16, float* C, int32_t M, int32_t N, int32_t K, const float* bias, const float* res,
                 int32_t qcols, void* stream) {
+    if (epilogue > EPI_QKV_PLANES) return fail(EDSNET_E_ARG, "gemm: unknown epilogue");
     return gemm_dispatch(precision, epilogue, A, A16, B, B16, C, M, N, K, bias, res, qcols,
                          static_cast<cudaStream_t>(stream));
 }
@@ -440,10 +454,19 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     const void* x16 = nullptr;
     if (prec != EDSNET_PREC_FP32) {
         const bool nys = cfg->base_model == EDSNET_BASE_NYSTROM;
-        if ((nys && (!w->to_qkv_w16 || !w->to_out_w16)) || !w->fc1_w16 || !w->fcb_w16)
+        // LayerNorm(1024) folded into the to_out / fc1 epilogues: Nystrom base, split-fp16 precision (the single-pass
+        // mode has no digits to spare for the fold's  acc - mean wgsum  and keeps the LayerNorm kernel)
+        const bool fold = nys && prec == EDSNET_PREC_FP16X3;
+        if ((nys && (!w->to_qkv_w16 || !w->to_out_w16)) || (!fold && !w->fc1_w16) || !w->fcb_w16)
             return fail(EDSNET_E_ARG, "forward: tcgen05 precision needs the fp16 weight planes (edsnet_split_f16)");
-        rc = edsnet_split_f16(x, ws + L.x16, R, kFeat, stream);
-        if (rc) return rc;
+        if (fold && (!w->fc1_fold_w16 || !w->fc1_fold_wgsum || !w->fc1_fold_b || !w->to_out_bc || !w->to_out_bounds))
+            return fail(EDSNET_E_ARG, "forward: fp16x3 needs the LayerNorm-folded fc1 operands (fc1_fold_*, to_out_bounds)");
+        {
+            // operand planes of x; Nystrom base: also (mean, max|.|) per row for the to_out epilogue
+            StageScope scope(ST_SPLIT, st);
+            CU_CHECK(launch_split_f16(x, ws + L.x16, R, kFeat, st, fold ? reinterpret_cast<float2*>(ws + L.xstat) : nullptr),
+                     "split_f16_kernel");
+        }
         x16 = ws + L.x16;
     }
     if (cfg->base_model == EDSNET_BASE_ATTENTION) {
@@ -485,13 +508,26 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
                                F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, merged16_out);
         if (rc) return rc;
         // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
+        //    (fp16x3: z = y - mean(x row) - mean(bias) leaves as the fc1 operand planes with the row sums LayerNorm needs; step 4
+        //    then is ONE GEMM, fc1(LN(y)) = rstd (z (W o gamma)^T - mean(z) rowsum(W o gamma)) + (W beta + b))
         const void* merged16 = merged16_out;
-        rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
-                           kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
-        if (rc) return rc;
+        if (prec == EDSNET_PREC_FP16X3) {
+            rc = gemm_dispatch(prec, EPI_RES_LNPLANES, nullptr, merged16, nullptr, w->to_out_w16, F(L.y), R, kFeat, kInner,
+                               w->to_out_bc, x, 0, st, ST_TO_OUT, F(L.zstat), F(L.xstat), w->to_out_bounds);
+            if (rc) return rc;
+            rc = gemm_dispatch(prec, EPI_LN_FOLD, nullptr, ws + L.y, nullptr, w->fc1_fold_w16, F(L.u0), R, kHidden, kFeat,
+                               w->fc1_fold_b, nullptr, 0, st, ST_FC1, F(L.zstat), w->fc1_fold_wgsum);
+            if (rc) return rc;
+        } else {
+            rc = gemm_dispatch(prec, EPI_BIAS_RES, F(L.merged), merged16, w->to_out_w, w->to_out_w16, F(L.y), R, kFeat,
+                               kInner, w->to_out_b, x, 0, st, ST_TO_OUT);
+            if (rc) return rc;
+        }
     }
     // 4. LayerNorm(1024) -> fc1                                                 (dsnet.py:106)
     const void* yn16 = nullptr;
+    const bool ln_folded = prec == EDSNET_PREC_FP16X3 && cfg->base_model == EDSNET_BASE_NYSTROM;
+    if (!ln_folded) {
     {
         StageScope scope(ST_LN, st);
         if (prec != EDSNET_PREC_FP32) {
@@ -509,6 +545,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     rc = gemm_dispatch(prec, EPI_BIAS, F(L.yn), yn16, w->fc1_w, w->fc1_w16, F(L.u0), R, kHidden, kFeat, w->fc1_b,
                        nullptr, 0, st, ST_FC1);
     if (rc) return rc;
+    }
     // 5. shared fc block x depth                                                (dsnet.py:107-108)
     //    (tcgen05: the stack's last layer emits the three head projections per row into the u1 region, 16 B per row,
     //    instead of the 512-byte rows; pooling and heads are linear, so the windows then run over those)
@@ -600,9 +637,10 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
 int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
     // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add the operand split of x
-    // (and of merged for the attention base) and run the value convolution as its own kernel
+    // (and of merged for the attention base) and run the value convolution as its own kernel; fp16x3 with the Nystrom
+    // base has no LayerNorm kernel (folded into to_out's and fc1's epilogues)
     if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 9;
-    return cfg->precision == EDSNET_PREC_FP32 ? 11 : 13;
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : (cfg->precision == EDSNET_PREC_FP16X3 ? 12 : 13);
 }
 
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

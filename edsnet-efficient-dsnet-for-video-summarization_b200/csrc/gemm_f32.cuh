@@ -10,8 +10,13 @@ enum GemmEpi : int {
     EPI_QSCALE = 1,        // columns < qcols multiplied by 1/8 (q = q * dim_head^-0.5, nystroformer.py:91)
     EPI_BIAS = 2,          // + bias[n]
     EPI_BIAS_RES = 3,      // + bias[n] + res[m, n]   (to_out bias + residual x, dsnet.py:105)
-    EPI_QKV_PLANES = 4     // tcgen05 path only: q|k|v written as row-scaled fp16 hi/lo planes per (row, head), the
+    EPI_QKV_PLANES = 4,    // tcgen05 path only: q|k|v written as row-scaled fp16 hi/lo planes per (row, head), the
                            // operand format of the tensor-core attention kernels (nystrom_tc.cuh); C = hi plane base
+    // tcgen05 path only, the pair that folds LayerNorm(1024) into fc1 (dsnet.py:105-106):
+    //   fc1(LN(y)) = rstd (z . (W o gamma)^T - mean(z) rowsum(W o gamma)) + (W beta + b),   z = y - c (any row constant)
+    EPI_RES_LNPLANES = 5,  // to_out: z = acc + bias + res - c[m] written as fp16 hi/lo planes (edsnet_split_f16 layout at C,
+                           // power-of-two row scale from an a-priori bound) + per (row, 64-column slot) sum z, sum z^2
+    EPI_LN_FOLD = 6        // fc1 on those planes with B = W o gamma: rstd[m] (acc - mean[m] wgsum[n]) + bias[n]
 };
 
 struct GemmEpiArgs {
@@ -22,6 +27,9 @@ struct GemmEpiArgs {
     const float* a_scale;  // tcgen05 path: [M] power-of-two factor undoing the row scaling of A's fp16 planes
     const float* b_scale;  // tcgen05 path: [N] same for B
     float* aux;            // EPI_QKV_PLANES: [M][24] inverse scales, index part*8 + head (q's include the 1/8)
+                           // EPI_RES_LNPLANES (written) / EPI_LN_FOLD (read): [M][16][2] partial (sum z, sum z^2)
+    const float* aux2;     // EPI_RES_LNPLANES: [M][2] (mean, max|.|) of the residual rows; EPI_LN_FOLD: wgsum [N]
+    const float* aux3;     // EPI_RES_LNPLANES: [2] = { max_n sum_k |B[n,k]|, max_n |bias[n]| }
 };
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmLd = 132;

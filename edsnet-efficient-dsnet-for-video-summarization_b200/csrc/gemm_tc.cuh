@@ -206,6 +206,21 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
     const int row = row0 + lane;
     const float ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
     const int rr = lane >> 2, cc = (lane & 3) * 4;
+    // EPI_LN_FOLD: row statistics of z from the 16 partial (sum, sum of squares) pairs the producer left per row
+    float ln_mean = 0.f, ln_rstd = 0.f;
+    if (EPI == EPI_LN_FOLD && row < M) {
+        const float4* sp = reinterpret_cast<const float4*>(ep.aux + (size_t)row * 32);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float4 p = __ldg(sp + t);
+            s1 = (s1 + p.x) + p.z;
+            s2 = (s2 + p.y) + p.w;
+        }
+        ln_mean = s1 * (1.f / (float)kFeat);
+        const float var = fmaxf(s2 * (1.f / (float)kFeat) - ln_mean * ln_mean, 0.f);
+        ln_rstd = 1.f / sqrtf(var + 1e-5f);
+    }
     // residual: all 16 loads of this thread (post-transposition layout) in flight at once, one exposed latency per tile
     float4 resv[EPI == EPI_BIAS_RES ? 16 : 1];
     if (EPI == EPI_BIAS_RES) {
@@ -233,6 +248,11 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
                 const float4 b = ldg4(ep.bias + c);
                 o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
+            if (EPI == EPI_LN_FOLD) {
+                const float4 g = ldg4(ep.aux2 + c), b = ldg4(ep.bias + c);
+                o.x = ln_rstd * (o.x - ln_mean * g.x) + b.x; o.y = ln_rstd * (o.y - ln_mean * g.y) + b.y;
+                o.z = ln_rstd * (o.z - ln_mean * g.z) + b.z; o.w = ln_rstd * (o.w - ln_mean * g.w) + b.w;
+            }
             st4(scratch + lane * kEpiScratchLd + j, o);
         }
         __syncwarp();
@@ -251,6 +271,158 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
             }
         }
         __syncwarp();
+    }
+}
+
+// EPI_RES_LNPLANES (to_out when LayerNorm(1024) is folded into fc1): z = acc + bias + res - c[row] leaves as the fc1
+// operand planes (edsnet_split_f16 layout at C) instead of fp32, with the row statistics LayerNorm needs.
+//  * c[row] = mean of the residual row, and `bias` arrives with its own mean removed (any row constant cancels in
+//    LayerNorm; these keep mean(z)^2 small against var(z), so neither the variance nor the fc1 epilogue's
+//    acc - mean wgsum loses digits to cancellation, e.g. with tiny inputs under a large common bias);
+//  * the planes need ONE power-of-two scale per row although eight CTAs write the row's column tiles: it comes from a
+//    bound every one of them can evaluate, |z| <= 2 max|res row| + max|bias| + max|A row| max_n sum_k |B[n,k]|
+//    (max|A row| < 2^15 a_scale).  A loose bound costs nothing until it is off by ~2^14: hi and lo are floating point;
+//  * per (row, 64-column slot): sum z and sum z^2 in a fixed order -> aux[row][slot], 16 slots per row.
+// Same warp-private transposition as epi_store_f32, read back as 16 rows x 8 columns so that every plane store is 16 B.
+// Everything that does not depend on the accumulators is fetched BEFORE the wait for the tile's MMAs (the residual comes
+// from HBM: its latency then hides under the mainloop instead of sitting between the TMEM drain and the stores).
+struct LnPlanesPre {
+    float4 resv[16];
+    float2 xs[2];           // (mean, max|.|) of the residual rows this thread finishes
+    float ra, ra2[2];       // A row scale of the accumulator row / of those rows
+};
+__device__ __forceinline__ void lnplanes_prefetch(LnPlanesPre& pre, int row0, int lane, int nc0, int M, int N, float* C,
+                                                  const GemmEpiArgs& ep) {
+    const int row = row0 + lane;
+    const int rr = lane >> 1, c8 = (lane & 1) * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int grow = row0 + rr + 16 * i;
+            const float* rp = ep.res + (size_t)grow * ep.ldr + nc0 + q * 16 + c8;
+            pre.resv[q * 4 + i * 2] = grow < M ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pre.resv[q * 4 + i * 2 + 1] = grow < M ? ldg4(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    pre.ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int grow = row0 + rr + 16 * i;
+        pre.xs[i] = grow < M ? __ldg(reinterpret_cast<const float2*>(ep.aux2) + grow) : make_float2(0.f, 0.f);
+        pre.ra2[i] = grow < M ? __ldg(ep.a_scale + grow) : 0.f;
+    }
+}
+// ... and the same lines of the CTA's NEXT tile are pulled into L2 a whole tile ahead (no registers involved): the
+// epilogue is the longer leg of this kernel's pipeline, so nothing else would hide that tile's DRAM latency.
+__device__ __forceinline__ void lnplanes_prefetch_l2(int row0, int lane, int nc0, int M, const GemmEpiArgs& ep) {
+    const int row = row0 + lane;
+    if (row < M) {
+        const float* rp = ep.res + (size_t)row * ep.ldr + nc0;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
+    }
+    if (lane < 2 && row0 + lane * 16 < M)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.aux2 + 2 * (size_t)(row0 + lane * 16)));
+    if (lane == 2 && row0 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.a_scale + row0));
+}
+
+// Slab sources: the raw accumulator sums of columns 16 q .. 16 q + 15 of this thread's row -- from registers, or
+// straight out of TMEM one slab ahead (double-buffered two-accumulator tiles: the buffer is handed back after the last
+// slab, and only 16 + 32 instead of 64 accumulator values are live next to the 64 prefetched residual values).
+struct SlabFromRegs {
+    const float (&v)[64];
+    __device__ __forceinline__ void prefetch(int) {}
+    __device__ __forceinline__ void get(int q, float (&v16)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v16[j] = v[q * 16 + j];
+    }
+};
+struct SlabFromTmem2 {
+    uint32_t t0, bn;                 // TMEM address of this thread's row / first column; columns between the accumulators
+    uint32_t r0[16], r1[16];
+    __device__ __forceinline__ void prefetch(int q) {
+        tmem_ld16_nowait(t0 + (uint32_t)(q * 16), r0);
+        tmem_ld16_nowait(t0 + bn + (uint32_t)(q * 16), r1);
+    }
+    __device__ __forceinline__ void get(int, float (&v16)[16]) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v16[j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+    }
+};
+template <typename Slab>
+__device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre& pre, int row0, int lane,
+                                                   int nc0, int M, int N, float* C, const GemmEpiArgs& ep,
+                                                   float* scratch) {
+    const int rr = lane >> 1, c8 = (lane & 1) * 8;
+    const float ra = pre.ra;
+    const float4* resv = pre.resv;
+    __half* hi_base = reinterpret_cast<__half*>(C);
+    __half* lo_base = hi_base + (size_t)M * N;
+    float* z_inv = reinterpret_cast<float*>(lo_base + (size_t)M * N);
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    slab.prefetch(0);
+    const float l1max = __ldg(ep.aux3), bmax = __ldg(ep.aux3 + 1);
+    float shift[2], sc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int grow = row0 + rr + 16 * i;
+        const float bound = 2.f * pre.xs[i].y + bmax + 32768.f * pre.ra2[i] * l1max;
+        int e = 0;
+        if (bound > 0.f && bound < INFINITY) e = 14 - ilogbf(bound);
+        e = max(-100, min(100, e));
+        shift[i] = pre.xs[i].x;
+        sc[i] = ldexpf(1.f, e);
+        if (nc0 == 0 && (lane & 1) == 0 && grow < M) z_inv[grow] = ldexpf(1.f, -e);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[16];
+        slab.get(q, v);
+        if (q < 3) slab.prefetch(q + 1);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const int c = nc0 + q * 16 + j;
+            const float4 rb = ldg4(ep.b_scale + c), b = ldg4(ep.bias + c);
+            st4(scratch + lane * kEpiScratchLd + j,
+                make_float4(v[j] * (ra * rb.x) + b.x, v[j + 1] * (ra * rb.y) + b.y,
+                            v[j + 2] * (ra * rb.z) + b.z, v[j + 3] * (ra * rb.w) + b.w));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = rr + 16 * i, grow = row0 + r;
+            const float4 o0 = lds4(scratch + r * kEpiScratchLd + c8), o1 = lds4(scratch + r * kEpiScratchLd + c8 + 4);
+            if (grow < M) {
+                const float4 x0 = resv[q * 4 + i * 2], x1 = resv[q * 4 + i * 2 + 1];
+                const float z[8] = {o0.x + (x0.x - shift[i]), o0.y + (x0.y - shift[i]), o0.z + (x0.z - shift[i]),
+                                    o0.w + (x0.w - shift[i]), o1.x + (x1.x - shift[i]), o1.y + (x1.y - shift[i]),
+                                    o1.z + (x1.z - shift[i]), o1.w + (x1.w - shift[i])};
+                __half2 hh[4], ll[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s1[i] += z[2 * t] + z[2 * t + 1];
+                    s2[i] += z[2 * t] * z[2 * t] + z[2 * t + 1] * z[2 * t + 1];
+                    const float v0 = z[2 * t] * sc[i], v1 = z[2 * t + 1] * sc[i];
+                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                    hh[t] = __halves2half2(h0, h1);
+                    ll[t] = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
+                                           __float2half_rn(v1 - __half2float(h1)));
+                }
+                const size_t o = (size_t)grow * N + nc0 + q * 16 + c8;
+                *reinterpret_cast<uint4*>(hi_base + o) = *reinterpret_cast<uint4*>(hh);
+                *reinterpret_cast<uint4*>(lo_base + o) = *reinterpret_cast<uint4*>(ll);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float t1 = s1[i] + __shfl_xor_sync(0xffffffffu, s1[i], 1);
+        const float t2 = s2[i] + __shfl_xor_sync(0xffffffffu, s2[i], 1);
+        const int grow = row0 + rr + 16 * i;
+        if ((lane & 1) == 0 && grow < M)
+            *reinterpret_cast<float2*>(ep.aux + ((size_t)grow * 16 + (nc0 >> 6)) * 2) = make_float2(t1, t2);
     }
 }
 
@@ -399,11 +571,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int m0 = (tile / tiles_n) * Cfg::BM, n0 = (tile % tiles_n) * BN;
             const int buf = t % Cfg::kBufs;
             const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
+            const int nc0 = n0 + chalf * 64;                         // first global column of this thread
+            LnPlanesPre ln_pre;
+            if (EPI == EPI_RES_LNPLANES) {
+                lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep);
+                const int nxt = tile + gridDim.x;
+                if (nxt < n_tiles)
+                    lnplanes_prefetch_l2((nxt / tiles_n) * Cfg::BM + quarter * 32, lane, (nxt % tiles_n) * BN + chalf * 64,
+                                         M, ep);
+            }
             ok = mbar_wait(tfull_bar(buf), tph);
             tc_fence_after();
             const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) +
                                 (uint32_t)(chalf * 64);
-            const int nc0 = n0 + chalf * 64;                         // first global column of this thread
+            if (EPI == EPI_RES_LNPLANES && ACCS == 2 && Cfg::kBufs == 2) {
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
+                SlabFromTmem2 slab;
+                slab.t0 = t0;
+                slab.bn = (uint32_t)BN;
+                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                continue;
+            }
             float v[64];
             if (kPhased) {
                 // (acc0 + acc3) first, hand those two back, then + (acc1 + acc2); every add rounded to nearest
@@ -477,6 +668,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (EPI == EPI_QKV_PLANES) {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 epi_store_planes(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+            } else if (EPI == EPI_RES_LNPLANES) {
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
+                SlabFromRegs slab{v};
+                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
             } else {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 epi_store_f32<EPI>(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
@@ -493,7 +688,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 template <int COLS>
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
-                 float* __restrict__ inv_scale, int rows) {
+                 float* __restrict__ inv_scale, int rows, float2* __restrict__ row_stat = nullptr) {
     constexpr int V = COLS / 128;                       // float4 per lane
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -506,6 +701,13 @@ split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half*
         mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x[i].x), fabsf(x[i].y)), fmaxf(fabsf(x[i].z), fabsf(x[i].w))));
     }
     mx = warp_max(mx);
+    if (row_stat != nullptr) {                          // (mean, max|.|) of the row for EPI_RES_LNPLANES
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+        sum = warp_sum(sum);
+        if (lane == 0) row_stat[row] = make_float2(sum * (1.f / (float)COLS), mx);
+    }
     int e = 0;
     if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
     e = max(-100, min(100, e));
@@ -617,7 +819,7 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
     if (N % 128 == 0) {
         if (PASSES == 3) {
             // four 128-column accumulators fill TMEM
-            if (variant == 4) return launch_pair<4, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+            if (variant == 4 && EPI <= EPI_QKV_PLANES) return launch_pair<4, (EPI <= EPI_QKV_PLANES ? EPI : 0)>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 3) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             // K <= 512: the hi.hi products of one tile are <= 32 accumulation steps, so ONE main accumulator stays
             // inside the truncation budget of the K = 1024 case (3 x <= 24 steps) and the tile fits twice into TMEM:
@@ -638,8 +840,8 @@ static cudaError_t launch_gemm_tc(int passes, int epilogue, const __half* A16, c
                                   int N, int K, GemmEpiArgs ep, cudaStream_t st, std::string* msg) {
     if (K % 64 != 0) { if (msg) *msg = "K must be a multiple of 64"; return cudaErrorInvalidValue; }
 #define TC_CASE(P, E) if (passes == P && epilogue == E) return tc::launch_shape<P, E>(A16, B16, C, M, N, K, ep, st, msg);
-    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3) TC_CASE(3, 4)
-    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3) TC_CASE(1, 4)
+    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3) TC_CASE(3, 4) TC_CASE(3, 5) TC_CASE(3, 6)
+    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3) TC_CASE(1, 4) TC_CASE(1, 5) TC_CASE(1, 6)
 #undef TC_CASE
     if (msg) *msg = "unsupported passes/epilogue";
     return cudaErrorInvalidValue;
@@ -651,12 +853,13 @@ static inline const float* split_scales(const void* planes, size_t rows, size_t 
     return reinterpret_cast<const float*>(static_cast<const unsigned char*>(planes) + rows * cols * 4);
 }
 
-static cudaError_t launch_split_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st) {
+static cudaError_t launch_split_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st,
+                                    float2* row_stat = nullptr) {
     __half* hi = static_cast<__half*>(dst);
     __half* lo = hi + (size_t)rows * cols;
     float* sc = reinterpret_cast<float*>(lo + (size_t)rows * cols);
     const unsigned blocks = (unsigned)((rows + 7) / 8);
-    if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
+    if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows, row_stat);
     else if (cols == 128) tc::split_f16_kernel<128><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else if (cols == 512) tc::split_f16_kernel<512><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else return cudaErrorInvalidValue;

@@ -172,6 +172,24 @@ class DSNet(nn.Module):
             lib = _capi.lib()
             planes_of = (("mha_qkv_w16", "mha_qkv_w"), ("mha_fc_w16", "mha_fc_w")) \
                 if self.base_model_type == "attention" else (("to_qkv_w16", "to_qkv_w"), ("to_out_w16", "to_out_w"))
+            if self.base_model_type != "attention":
+                # LayerNorm(1024) folded into fc1 (edsnet_b200.h, fc1_fold_*): derived operands, float64 sums
+                beta, w1 = tensors["ln_b"].double(), tensors["fc1_w"].double()
+                tensors["fc1_fold_w"] = (tensors["fc1_w"] * tensors["ln_w"][None, :]).contiguous()
+                bc = (tensors["to_out_b"].double() - tensors["to_out_b"].double().mean()).float()
+                derived = {
+                    "fc1_fold_wgsum": tensors["fc1_fold_w"].double().sum(1).float(),
+                    "fc1_fold_b": (w1 @ beta + tensors["fc1_b"].double()).float(),
+                    "to_out_bc": bc,
+                    "to_out_bounds": (torch.stack([tensors["to_out_w"].double().abs().sum(1).max(),
+                                                   bc.double().abs().max()]) * 1.001).float(),
+                }
+                for field, t in derived.items():
+                    t = t.contiguous()
+                    keep.append(t)
+                    setattr(w, field, t.data_ptr())
+                keep.append(tensors["fc1_fold_w"])
+                planes_of = planes_of + (("fc1_fold_w16", "fc1_fold_w"),)
             for field, src_name in planes_of + (("fc1_w16", "fc1_w"), ("fcb_w16", "fcb_w")):
                 src = tensors[src_name]
                 planes = torch.empty(lib.edsnet_split_f16_bytes(src.shape[0], src.shape[1]), dtype=torch.uint8,

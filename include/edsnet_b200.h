@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 5
+#define EDSNET_ABI_VERSION 6
 
 enum {
     EDSNET_OK = 0,
@@ -91,6 +91,15 @@ typedef struct {
     const float* mha_fc_w;     /* base_model.fc.0.weight        (1024, 1024) */
     const void* mha_qkv_w16;   /* planes of (3072, 1024) */
     const void* mha_fc_w16;    /* planes of (1024, 1024) */
+    /* EDSNET_PREC_FP16X3, Nystrom base: LayerNorm(1024) is folded into fc1 (dsnet.py:105-106),
+     *   fc1(LN(y)) = rstd (y (W o gamma)^T - mean(y) rowsum(W o gamma)) + (W beta + b),
+     * so the forward needs these derived operands instead of fc1_w16 (required; edsnet_b200/dsnet.py builds them): */
+    const void* fc1_fold_w16;      /* planes of fc1.weight * layer_norm.weight[None, :]   (128, 1024) */
+    const float* fc1_fold_wgsum;   /* row sums of that product                            (128)       */
+    const float* fc1_fold_b;       /* fc1.weight @ layer_norm.bias + fc1.bias             (128)       */
+    const float* to_out_bc;        /* to_out.bias - mean(to_out.bias): LayerNorm ignores a row constant, and a
+                                    * large common bias would otherwise cost the statistics digits      (1024)      */
+    const float* to_out_bounds;    /* { max_n sum_k |to_out.weight[n,k]|, max_n |to_out_bc[n]| }, rounded up (2) */
 } edsnet_weights;
 
 /* A packed batch of videos.  Arrays [dev] int32 unless noted.  Tile tables are built by the host (see
@@ -122,13 +131,16 @@ typedef struct {
     size_t merged;     /* [rows][512] head-merged attention output + value conv ([rows][1024] for the attention base);
                         * tcgen05 precisions, Nystrom base: attention part only, the sum with the value conv leaves as
                         * the to_out operand planes at x16 */
-    size_t y;          /* [rows][1024] to_out + bias + x                              */
+    size_t y;          /* [rows][1024] to_out + bias + x; EDSNET_PREC_FP16X3, Nystrom base: fc1 operand planes of
+                        * z = y - mean(x row) (edsnet_split_f16 layout), LayerNorm being folded into fc1 */
     size_t yn;         /* [rows][1024] LayerNorm(y)           (aliases qkv)           */
     size_t u0;         /* [rows][128] fc1 output                                      */
     size_t u1;         /* [rows][128] after the fc stack; tcgen05 precisions: [rows][4] head projections
                         * (u . w_cls, u . w_loc[0], u . w_loc[1], 0), the hidden rows are not written */
     size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
     size_t zeros;      /* [1024] zero bias (attention base: its projections have no bias) */
+    size_t zstat;      /* EDSNET_PREC_FP16X3, Nystrom base: [rows][16][2] (sum z, sum z^2) per 64-column slot */
+    size_t xstat;      /* EDSNET_PREC_FP16X3, Nystrom base: [rows][2] (mean, max|.|) of the input rows */
     size_t total;
 } edsnet_workspace_layout;
 

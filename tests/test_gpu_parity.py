@@ -151,6 +151,19 @@ def test_forward_stages_match_oracle(precision):
         want = stages["hidden"] @ hw.t()
         got = view(L.u1, (T, 4))[:, :3]
         assert orc.rel_l2(got.numpy(), want.numpy()) < 2e-5
+        # LayerNorm(1024) is folded into to_out's and fc1's epilogues: y never exists in fp32; fc1's output does
+        with torch.no_grad():
+            y = orc.nystrom_attention(x, p, orc.HEADS, None) + x
+            u0 = orc.layer_norm(y, p["layer_norm.weight"], p["layer_norm.bias"]) @ p["fc1.weight"].t() + p["fc1.bias"]
+        got0 = view(L.u0, (T, 128))
+        err0 = orc.rel_l2(got0.numpy(), u0.numpy())
+        print("fc1(LN(y))", err0)
+        assert err0 < 2e-5
+        # and the row statistics the fold uses: sum over the 16 column slots = (sum z, sum z^2), z = y - mean(x row)
+        zs = view(L.zstat, (T, 16, 2)).double().sum(1)
+        z = (y - x.mean(1, keepdim=True) - p["base_model.to_out.0.bias"].mean()).double()
+        assert orc.rel_l2(zs[:, 0].numpy(), z.sum(1).numpy()) < 1e-4      # a cancelling sum: absolute accuracy
+        assert orc.rel_l2(zs[:, 1].numpy(), (z * z).sum(1).numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])

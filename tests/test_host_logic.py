@@ -43,7 +43,7 @@ def test_workspace_sizing_and_argument_errors_without_gpu():
     bad = _capi.make_config([5], 5, 0)
     assert lib.edsnet_decode_boxes(bad, None, None, None, None, None) == _capi.E_ARG
     assert "odd anchor scale" in _capi.last_error()
-    assert lib.edsnet_forward_launches(cfg) == 13
+    assert lib.edsnet_forward_launches(cfg) == 12
 
 
 def test_batch_plan_tables():
