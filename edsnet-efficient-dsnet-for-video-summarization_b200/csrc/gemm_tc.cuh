@@ -287,23 +287,27 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
 // Everything that does not depend on the accumulators is fetched BEFORE the wait for the tile's MMAs (the residual comes
 // from HBM: its latency then hides under the mainloop instead of sitting between the TMEM drain and the stores).
 struct LnPlanesPre {
-    float4 resv[16];
+    float4 resv[2][4];      // residual of column slabs 0 and 1; slabs 2 and 3 are fetched (from L2) as these are used up
     float2 xs[2];           // (mean, max|.|) of the residual rows this thread finishes
     float ra, ra2[2];       // A row scale of the accumulator row / of those rows
 };
+__device__ __forceinline__ void lnplanes_load_res(float4 (&dst)[4], int q, int row0, int lane, int nc0, int M,
+                                                  const GemmEpiArgs& ep) {
+    const int rr = lane >> 1, c8 = (lane & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int grow = row0 + rr + 16 * i;
+        const float* rp = ep.res + (size_t)grow * ep.ldr + nc0 + q * 16 + c8;
+        dst[i * 2] = grow < M ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[i * 2 + 1] = grow < M ? ldg4(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
 __device__ __forceinline__ void lnplanes_prefetch(LnPlanesPre& pre, int row0, int lane, int nc0, int M, int N, float* C,
                                                   const GemmEpiArgs& ep) {
     const int row = row0 + lane;
-    const int rr = lane >> 1, c8 = (lane & 1) * 8;
+    const int rr = lane >> 1;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int grow = row0 + rr + 16 * i;
-            const float* rp = ep.res + (size_t)grow * ep.ldr + nc0 + q * 16 + c8;
-            pre.resv[q * 4 + i * 2] = grow < M ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
-            pre.resv[q * 4 + i * 2 + 1] = grow < M ? ldg4(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int q = 0; q < 2; ++q) lnplanes_load_res(pre.resv[q], q, row0, lane, nc0, M, ep);
     pre.ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -356,7 +360,11 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
                                                    float* scratch) {
     const int rr = lane >> 1, c8 = (lane & 1) * 8;
     const float ra = pre.ra;
-    const float4* resv = pre.resv;
+    float4 resv[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) resv[q][t] = pre.resv[q][t];
     __half* hi_base = reinterpret_cast<__half*>(C);
     __half* lo_base = hi_base + (size_t)M * N;
     float* z_inv = reinterpret_cast<float*>(lo_base + (size_t)M * N);
@@ -394,7 +402,7 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
             const int r = rr + 16 * i, grow = row0 + r;
             const float4 o0 = lds4(scratch + r * kEpiScratchLd + c8), o1 = lds4(scratch + r * kEpiScratchLd + c8 + 4);
             if (grow < M) {
-                const float4 x0 = resv[q * 4 + i * 2], x1 = resv[q * 4 + i * 2 + 1];
+                const float4 x0 = resv[q & 1][i * 2], x1 = resv[q & 1][i * 2 + 1];
                 const float z[8] = {o0.x + (x0.x - shift[i]), o0.y + (x0.y - shift[i]), o0.z + (x0.z - shift[i]),
                                     o0.w + (x0.w - shift[i]), o1.x + (x1.x - shift[i]), o1.y + (x1.y - shift[i]),
                                     o1.z + (x1.z - shift[i]), o1.w + (x1.w - shift[i])};
@@ -414,6 +422,7 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
                 *reinterpret_cast<uint4*>(lo_base + o) = *reinterpret_cast<uint4*>(ll);
             }
         }
+        if (q < 2) lnplanes_load_res(resv[q & 1], q + 2, row0, lane, nc0, M, ep);
         __syncwarp();
     }
 #pragma unroll
