@@ -302,7 +302,7 @@ __device__ __forceinline__ void lnplanes_load_res(float4 (&dst)[4], int q, int r
         dst[i * 2 + 1] = grow < M ? ldg4(rp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-__device__ __forceinline__ void lnplanes_prefetch(LnPlanesPre& pre, int row0, int lane, int nc0, int M, int N, float* C,
+__device__ __forceinline__ void lnplanes_prefetch(LnPlanesPre& pre, int row0, int lane, int nc0, int M,
                                                   const GemmEpiArgs& ep) {
     const int row = row0 + lane;
     const int rr = lane >> 1;
@@ -583,7 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int nc0 = n0 + chalf * 64;                         // first global column of this thread
             LnPlanesPre ln_pre;
             if (EPI == EPI_RES_LNPLANES) {
-                lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep);
+                lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, ep);
                 const int nxt = tile + gridDim.x;
                 if (nxt < n_tiles)
                     lnplanes_prefetch_l2((nxt / tiles_n) * Cfg::BM + quarter * 32, lane, (nxt % tiles_n) * BN + chalf * 64,

@@ -97,6 +97,54 @@ def anchor_labels(target_mask: np.ndarray, scales: Sequence[int], rng: np.random
     return cls, loc
 
 
+class LabelCache:
+    """The deterministic part of `anchor_labels`, computed once per video (precompute / cache).
+
+    The reference redoes three IoU sweeps over all T x S anchors for every video of every epoch
+    (anchor_based/train.py:86-108) although they only depend on the ground-truth mask; what changes from step to step is
+    the random choice of negatives.  `labels(key, rng)` consumes the random stream exactly like `anchor_labels` does
+    (two shuffles, same index arrays), so both return identical labels for the same generator state."""
+
+    def __init__(self, scales: Sequence[int], pos_iou_thresh: float = 0.6, neg_iou_thresh: float = 0.0,
+                 incomplete_iou_thresh: float = 0.3, neg_sample_ratio: float = 2.0,
+                 incomplete_sample_ratio: float = 1.0):
+        self.scales = [int(s) for s in scales]
+        self.thresholds = (pos_iou_thresh, neg_iou_thresh, incomplete_iou_thresh)
+        self.ratios = (neg_sample_ratio, incomplete_sample_ratio)
+        self._store = {}
+
+    def add(self, key, target_mask: np.ndarray) -> bool:
+        """False (nothing stored) for an empty mask: the training loop skips such videos."""
+        target_mask = np.asarray(target_mask, dtype=bool)
+        if not target_mask.any():
+            self._store[key] = None
+            return False
+        T = target_mask.size
+        tg = mask_to_segments(target_mask)
+        cls, loc = positive_labels(T, self.scales, tg, self.thresholds[0])
+        neg, _ = positive_labels(T, self.scales, tg, self.thresholds[1])
+        inc, _ = positive_labels(T, self.scales, tg, self.thresholds[2])
+        self._store[key] = (cls, loc, neg, inc, int(cls.sum()))
+        return True
+
+    def __contains__(self, key) -> bool:
+        return key in self._store
+
+    def labels(self, key, rng: np.random.Generator) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+        entry = self._store[key]
+        if entry is None:
+            return None
+        cls, loc, neg, inc, num_pos = entry
+        neg = sample_negatives(neg, int(self.ratios[0] * num_pos), rng)
+        inc = inc.copy()
+        inc[neg != 1] = 1
+        inc = sample_negatives(inc, int(self.ratios[1] * num_pos), rng)
+        out = cls.copy()
+        out[neg == -1] = -1
+        out[inc == -1] = -1
+        return out, loc
+
+
 # ----------------------------------------------------------------------------------------------- losses (torch)
 def cls_loss(pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     """0.5 * (mean over positives of -log p + mean over negatives of -log(1 - p)); label in {1, -1, 0 = ignored}."""

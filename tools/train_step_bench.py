@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--scales", type=int, nargs="+", default=[4, 8, 16, 32])
     ap.add_argument("--cpu", action="store_true", help="also time the same step on the host cores")
     ap.add_argument("--graphs", action="store_true", help="replay the step as CUDA graphs (GraphedDataParallelStep)")
+    ap.add_argument("--cache-labels", action="store_true",
+                    help="IoU sweeps once per video (training.LabelCache); only the negatives are drawn per step")
     args = ap.parse_args()
     rank, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -62,11 +64,18 @@ def main():
     stepper = (tr.GraphedDataParallelStep if args.graphs else tr.DataParallelStep)(model, world_size=world)
     k = args.videos_per_rank
     label_s = [0.0]
+    cache = tr.LabelCache(args.scales) if args.cache_labels else None
+    if cache is not None:
+        for i, (_, mask) in enumerate(vids):
+            cache.add(i, mask)
 
     def one_step(i):
         sel = [(i * k + j) % len(vids) for j in range(k)]
         t0 = time.perf_counter()
-        labs = [tr.anchor_labels(vids[s][1], args.scales, rng) for s in sel]       # host NumPy, as the reference
+        if cache is not None:
+            labs = [cache.labels(s, rng) for s in sel]
+        else:
+            labs = [tr.anchor_labels(vids[s][1], args.scales, rng) for s in sel]   # host NumPy, as the reference
         label_s[0] += time.perf_counter() - t0
         cls_l = [torch.from_numpy(c).to(dev, non_blocking=True) for c, _ in labs]
         loc_l = [torch.from_numpy(l).float().to(dev, non_blocking=True) for _, l in labs]
