@@ -6,9 +6,12 @@
 //   PASSES = 3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi   (fp32-grade accuracy: drops only the lo.lo term)
 //   PASSES = 1: A_hi.B_hi                           (plain fp16 operands)
 // The tensor core adds each K=16 step into the fp32 accumulator with TRUNCATION (measured: a relative bias of about
-// 2e-8 per tcgen05.mma, 3.7e-6 after the 192 steps of a K=1024 three-pass product).  PASSES = 3 therefore keeps FOUR
-// accumulators in TMEM (4 x 128 columns = all 512): the hi.hi products rotate over three of them by K block (<= 24
-// steps each for K = 1024), the two small cross terms go to the fourth, and the epilogue adds the four in fp32 with
+// 2e-8 per tcgen05.mma, 3.7e-6 after the 192 steps of a K=1024 three-pass product into one accumulator).  PASSES = 3
+// therefore keeps the large hi.hi products apart from the two small cross terms, in (main | cross) accumulator PAIRS
+// that are adjacent in TMEM: A_hi . [B_hi | B_lo]^T is ONE tcgen05.mma with N = 2 BN (B's two planes sit back to back in
+// the stage, so A_hi leaves shared memory once for two of the three passes), A_lo . B_hi^T goes into the cross half.
+// Two pairs (4 x 128 columns = all 512) with the K blocks alternating between them (<= 32 steps per main accumulator
+// for K = 1024), or one pair (K <= 512: the tile then fits twice into TMEM); the epilogue adds them in fp32 with
 // round-to-nearest.
 // Persistent CTAs, 128 x 128 output tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..9 =
 // epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, 64 columns each).  K is consumed in BK-wide blocks through a STAGES-deep smem ring guarded
@@ -435,7 +438,7 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
     }
 }
 
-// ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (hi.hi rotating over three + cross terms) or 2 (hi.hi | cross terms);
+// ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (two main | cross pairs, K blocks alternate) or 2 (one pair);
 // PASSES == 1: 1.  Whatever fits twice into the 512 TMEM columns is double-buffered (MMAs of tile t+1 overlap the
 // drain of tile t).
 template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES == 3 ? 4 : 1)>
@@ -475,8 +478,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + Cfg::kBufs + b); };
-    // four single-buffered accumulators: accumulators 0 and 3 (first K block: hi.hi and the cross terms) are handed
-    // back to the MMA warp half way through the drain, 1 and 2 at its end (tempty2)
+    // two single-buffered accumulator pairs: pair 0 (even K blocks) is handed back to the MMA warp half way through the
+    // drain, pair 1 at its end (tempty2)
     constexpr bool kPhased = ACCS == 4 && Cfg::kBufs == 1;
     const uint32_t tempty2_bar = bar_base + 8u * (2 * STAGES + 2 * Cfg::kBufs);
     constexpr int kSlotOff = 8 * (2 * STAGES + 2 * Cfg::kBufs + 1);
@@ -518,12 +521,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
                     const uint32_t st = smem_base + s * Cfg::kStageBytes;
                     mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                    // stage layout: A_hi | B_hi | (A_lo | B_lo).  Plane p of an operand with R rows starts at row p*R.
+                    // stage layout: PASSES == 1: A_hi | B_hi; PASSES == 3: A_hi | A_lo | B_hi | B_lo (the two B planes
+                    // back to back: together they are ONE 2 BN-row operand).  Plane p of an operand with R rows starts
+                    // at row p*R.
                     tma_load_2d(st, &mapA, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
                     if (PASSES == 3) {
-                        tma_load_2d(st + Cfg::kATile + Cfg::kBTile, &mapA, full_bar(s), kb * BK, M + m0);
+                        tma_load_2d(st + Cfg::kATile, &mapA, full_bar(s), kb * BK, M + m0);
+                        tma_load_2d(st + 2 * Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
                         tma_load_2d(st + 2 * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
+                    } else {
+                        tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
                     }
                 }
             }
@@ -544,24 +551,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int s = it % STAGES;
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     ok = mbar_wait(full_bar(s), ph);
-                    if (kPhased && kb == 1) ok = mbar_wait(tempty2_bar, tph ^ 1u) && ok;   // accumulators 1, 2 drained
+                    if (kPhased && kb == 1) ok = mbar_wait(tempty2_bar, tph ^ 1u) && ok;   // pair 1 drained
                     tc_fence_after();
                     const uint32_t st = smem_base + s * Cfg::kStageBytes;
-                    const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
-                    const uint32_t a_lo = st + Cfg::kATile + Cfg::kBTile, b_lo = st + 2 * Cfg::kATile + Cfg::kBTile;
-                    // PASSES == 3: hi.hi of K block kb -> accumulator kb % 3, both cross terms -> accumulator 3
-                    const uint32_t acc_main = tmem_acc + (ACCS == 4 ? (uint32_t)((kb % 3) * BN) : 0u);
-                    const uint32_t acc_lo = tmem_acc + (uint32_t)((ACCS - 1) * BN);
+                    if (PASSES == 3) {
+                        // A_hi . [B_hi | B_lo]^T as ONE N = 2 BN instruction into an adjacent (main | cross)
+                        // accumulator pair -- A_hi leaves shared memory once for two of the three passes -- then
+                        // A_lo . B_hi^T into the cross accumulator.  ACCS == 4: K blocks alternate between two pairs.
+                        constexpr uint32_t idesc2 = make_idesc(Cfg::BM, 2 * BN);
+                        const uint32_t a_hi = st, a_lo = st + Cfg::kATile, b_hi = st + 2 * Cfg::kATile;
+                        const uint32_t acc_pair = tmem_acc + (ACCS == 4 ? (uint32_t)((kb & 1) * 2 * BN) : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t koff = k * 32;       // 16 fp16 = 32 bytes further along K inside the atom
-                        const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dbh = make_smem_desc<BK>(b_hi + koff);
-                        const bool first_main = ACCS == 4 ? (kb < 3 && k == 0) : ((kb | k) == 0);
-                        umma_f16(acc_main, dah, dbh, idesc, first_main ? 0u : 1u);
-                        if (PASSES == 3) {
-                            const uint64_t dal = make_smem_desc<BK>(a_lo + koff), dbl = make_smem_desc<BK>(b_lo + koff);
-                            umma_f16(acc_lo, dah, dbl, idesc, (kb | k) != 0 ? 1u : 0u);
-                            umma_f16(acc_lo, dal, dbh, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes further along K inside the atom
+                            const uint64_t dah = make_smem_desc<BK>(a_hi + koff), dal = make_smem_desc<BK>(a_lo + koff);
+                            const uint64_t dbh = make_smem_desc<BK>(b_hi + koff);
+                            const bool first = ACCS == 4 ? (kb < 2 && k == 0) : ((kb | k) == 0);
+                            umma_f16(acc_pair, dah, dbh, idesc2, first ? 0u : 1u);
+                            umma_f16(acc_pair + (uint32_t)BN, dal, dbh, idesc, 1u);
+                        }
+                    } else {
+                        const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t koff = k * 32;
+                            umma_f16(tmem_acc, make_smem_desc<BK>(a_hi + koff), make_smem_desc<BK>(b_hi + koff), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(empty_bar(s));              // frees the smem slot once these MMAs have read it
@@ -573,7 +588,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread <-> 64 columns of one output row ----
         const int quarter = warp & 3;
         const int chalf = (warp - 2) >> 2;                       // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127 (BN 128)
-        const int n_main = ACCS == 4 ? (nk < 3 ? nk : 3) : 1;       // accumulators that received hi.hi products
+        const int n_pairs = ACCS == 4 ? (nk < 2 ? nk : 2) : 1;      // (main | cross) accumulator pairs in use
         bool ok = true;
         int t = 0;
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
@@ -606,32 +621,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             float v[64];
             if (kPhased) {
-                // (acc0 + acc3) first, hand those two back, then + (acc1 + acc2); every add rounded to nearest
+                // pair 0 (main + cross of the even K blocks) first, hand it back, then + pair 1; every add rounded to nearest
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 16) {
-                    uint32_t r0[16], r3[16];
+                    uint32_t r0[16], r1[16];
                     tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
-                    tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
+                    tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r3[j]));
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
-                if (n_main > 1) {
+                if (n_pairs > 1) {
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 16) {
-                        uint32_t r1[16], r2[16];
-                        tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
-                        if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                        uint32_t r2[16], r3[16];
+                        tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                        tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float a12 = n_main > 2 ? __fadd_rn(__uint_as_float(r1[j]), __uint_as_float(r2[j]))
-                                                         : __uint_as_float(r1[j]);
-                            v[c0 + j] = __fadd_rn(v[c0 + j], a12);
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            v[c0 + j] = __fadd_rn(v[c0 + j], __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
                     }
                 }
                 tc_fence_before();
@@ -649,19 +661,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
                 } else if (ACCS == 4) {
-                    // (acc0 + acc1) + (acc2 + acc3), every add rounded to nearest
+                    // (main0 + cross0) + (main1 + cross1), every add rounded to nearest
                     uint32_t r1[16], r2[16], r3[16];
-                    tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
-                    if (n_main > 1) tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
-                    if (n_main > 2) tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                    tmem_ld16_nowait(t0 + 1u * BN + (uint32_t)c0, r1);
+                    if (n_pairs > 1) {
+                        tmem_ld16_nowait(t0 + 2u * BN + (uint32_t)c0, r2);
+                        tmem_ld16_nowait(t0 + 3u * BN + (uint32_t)c0, r3);
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float a0 = __uint_as_float(r0[j]);
-                        const float a01 = n_main > 1 ? __fadd_rn(a0, __uint_as_float(r1[j])) : a0;
-                        const float a23 = n_main > 2 ? __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j]))
-                                                     : __uint_as_float(r3[j]);
-                        v[c0 + j] = __fadd_rn(a01, a23);
+                        const float a01 = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                        v[c0 + j] = n_pairs > 1 ? __fadd_rn(a01, __fadd_rn(__uint_as_float(r2[j]), __uint_as_float(r3[j])))
+                                                : a01;
                     }
                 } else {
                     tmem_ld_wait();
