@@ -309,16 +309,16 @@ def main():
     flops_per_launch = 2.0 * (R / len(chunks)) * 1024 * 1536          # algorithmic: one pass, real rows
     avg_ms = qkv_ms / max(qkv_n, 1)
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
-    # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/r01l_kernels_full.md:
-    # dram__bytes_read 0.947373 GB + dram__bytes_write 1.391973 GB for a 229 489-row launch), scaled to this launch's
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/r01m_kernels_full.md:
+    # dram__bytes_read 0.967633 GB + dram__bytes_write 1.392453 GB for a 229 489-row launch), scaled to this launch's
     # rows; algorithmic bytes are 4 KB (x planes in) + 6 KB (q|k|v planes out) + 96 B (scales) per row.
     rows_per_launch = R / len(chunks)
-    traffic = (0.947373e9 + 1.391973e9) * rows_per_launch / 229489.0
+    traffic = (0.967633e9 + 1.392453e9) * rows_per_launch / 229489.0
     roofline = {"kernel": "gemm_tc_kernel<BN128,BK64,3 stages,3 passes,QKV_PLANES> (to_qkv, fp16 hi/lo split = 3 tcgen05 "
                           "passes, epilogue writes the q|k|v operand planes)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": peak_src, "traffic": traffic,
-                "traffic_source": "ncu --set full, profiles/r01l_kernels_full.md (bytes per row x rows of this launch)",
+                "traffic_source": "ncu --set full, profiles/r01m_kernels_full.md (bytes per row x rows of this launch)",
                 "algorithmic_bytes_per_launch": rows_per_launch * (4096 + 6144 + 96),
                 "mma_passes": 3, "frac_counting_passes": 3 * achieved / peak_tf,
                 "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": avg_ms,
