@@ -44,6 +44,23 @@ def test_workspace_sizing_and_argument_errors_without_gpu():
     assert lib.edsnet_decode_boxes(bad, None, None, None, None, None) == _capi.E_ARG
     assert "odd anchor scale" in _capi.last_error()
     assert lib.edsnet_forward_launches(cfg) == 12
+    assert lib.edsnet_forward_launches(_capi.make_config([4, 8], 5, _capi.PREC_FP16)) == 13    # keeps the LayerNorm kernel
+    assert lib.edsnet_forward_launches(_capi.make_config([4, 8], 5, _capi.PREC_FP32)) == 11
+    # the LayerNorm-fold layout: fc1 operand planes of z in the y region (+ 4 bytes of scale per row), row statistics
+    assert L.u0 - L.y >= 1000 * 1024 * 4 + 1000 * 4 and L.zstat > L.zeros and L.xstat >= L.zstat + 1000 * 32 * 4
+    # the stage entry point only exposes the general epilogues (the LayerNorm-fold pair is internal to the forward)
+    assert lib.edsnet_gemm(_capi.PREC_FP16X3, 5, None, None, None, None, None, 128, 1024, 512, None, None, 0, None) == _capi.E_ARG
+    assert "unknown epilogue" in _capi.last_error()
+    # a tcgen05 forward without the derived LayerNorm-fold operands is refused before any launch
+    plan = BatchPlan.build([100, 200])
+    fake = 1 << 20                                              # never dereferenced: validation comes first
+    w = _capi.Weights()
+    for name in _capi.WEIGHT_FIELDS:
+        setattr(w, name, None if name.startswith(("fc1_fold", "to_out_b")) and name != "to_out_b" else fake)
+    b = _capi.Batch(2, 300, 200, fake, fake, plan.tiles64.shape[0], fake, plan.tiles128.shape[0], None)
+    need = lib.edsnet_workspace_bytes(cfg, 300, 2, None)
+    assert lib.edsnet_forward(cfg, C.byref(w), C.byref(b), fake, fake, fake, fake, need, None) == _capi.E_ARG
+    assert "LayerNorm-folded" in _capi.last_error()
 
 
 def test_batch_plan_tables():
