@@ -287,8 +287,9 @@ __device__ __forceinline__ void epi_store_f32(const float (&v)[64], int row0, in
 //    (max|A row| < 2^15 a_scale).  A loose bound costs nothing until it is off by ~2^14: hi and lo are floating point;
 //  * per (row, 64-column slot): sum z and sum z^2 in a fixed order -> aux[row][slot], 16 slots per row.
 // Same warp-private transposition as epi_store_f32, read back as 16 rows x 8 columns so that every plane store is 16 B.
-// Everything that does not depend on the accumulators is fetched BEFORE the wait for the tile's MMAs (the residual comes
-// from HBM: its latency then hides under the mainloop instead of sitting between the TMEM drain and the stores).
+// What does not depend on the accumulators is fetched BEFORE the wait for the tile's MMAs: the row constants and the
+// residual of the first two column slabs; the other two slabs follow as those registers free up (168 registers per
+// thread is the ceiling for 10 warps, and spilled loop state reloads from an L1 that this stream keeps evicting).
 struct LnPlanesPre {
     float4 resv[2][4];      // residual of column slabs 0 and 1; slabs 2 and 3 are fetched (from L2) as these are used up
     float2 xs[2];           // (mean, max|.|) of the residual rows this thread finishes
@@ -335,7 +336,7 @@ __device__ __forceinline__ void lnplanes_prefetch_l2(int row0, int lane, int nc0
 
 // Slab sources: the raw accumulator sums of columns 16 q .. 16 q + 15 of this thread's row -- from registers, or
 // straight out of TMEM one slab ahead (double-buffered two-accumulator tiles: the buffer is handed back after the last
-// slab, and only 16 + 32 instead of 64 accumulator values are live next to the 64 prefetched residual values).
+// slab, and only 16 + 32 instead of 64 accumulator values are live next to the 32 prefetched residual values).
 struct SlabFromRegs {
     const float (&v)[64];
     __device__ __forceinline__ void prefetch(int) {}
