@@ -71,6 +71,24 @@ class AttentionExtractor(nn.Module):
         raise RuntimeError("edsnet_b200.AttentionExtractor only holds parameters; call DSNet.forward")
 
 
+def layernorm_fold_operands(ln_w, ln_b, fc1_w, fc1_b, to_out_w, to_out_b):
+    """Derived operands that fold LayerNorm(1024) into fc1 (dsnet.py:105-106; include/edsnet_b200.h, fc1_fold_*):
+
+        fc1(LN(y)) = rstd * (z @ (W * gamma).T - mean(z) * rowsum(W * gamma)) + (W @ beta + b),   z = y - c
+
+    for ANY per-row constant c (LayerNorm ignores it); mean / rstd are those of z.  The kernels use
+    c = mean(x row) + mean(to_out bias), which is why the to_out bias arrives centred.  float64 sums, fp32 results."""
+    fold_w = (fc1_w * ln_w[None, :]).contiguous()
+    bc = (to_out_b.double() - to_out_b.double().mean()).float()
+    return {
+        "fc1_fold_w": fold_w,
+        "fc1_fold_wgsum": fold_w.double().sum(1).float(),
+        "fc1_fold_b": (fc1_w.double() @ ln_b.double() + fc1_b.double()).float(),
+        "to_out_bc": bc,
+        "to_out_bounds": (torch.stack([to_out_w.double().abs().sum(1).max(), bc.double().abs().max()]) * 1.001).float(),
+    }
+
+
 class DSNet(nn.Module):
     """`DSNet(base_model, num_feature, num_hidden, anchor_scales, num_head, fc_depth=5, orientation='paper',
     pooling_type='fft')` -- reference signature (dsnet.py:66-67).  Accelerated configuration only:
@@ -173,17 +191,9 @@ class DSNet(nn.Module):
             planes_of = (("mha_qkv_w16", "mha_qkv_w"), ("mha_fc_w16", "mha_fc_w")) \
                 if self.base_model_type == "attention" else (("to_qkv_w16", "to_qkv_w"), ("to_out_w16", "to_out_w"))
             if self.base_model_type != "attention":
-                # LayerNorm(1024) folded into fc1 (edsnet_b200.h, fc1_fold_*): derived operands, float64 sums
-                beta, w1 = tensors["ln_b"].double(), tensors["fc1_w"].double()
-                tensors["fc1_fold_w"] = (tensors["fc1_w"] * tensors["ln_w"][None, :]).contiguous()
-                bc = (tensors["to_out_b"].double() - tensors["to_out_b"].double().mean()).float()
-                derived = {
-                    "fc1_fold_wgsum": tensors["fc1_fold_w"].double().sum(1).float(),
-                    "fc1_fold_b": (w1 @ beta + tensors["fc1_b"].double()).float(),
-                    "to_out_bc": bc,
-                    "to_out_bounds": (torch.stack([tensors["to_out_w"].double().abs().sum(1).max(),
-                                                   bc.double().abs().max()]) * 1.001).float(),
-                }
+                derived = layernorm_fold_operands(tensors["ln_w"], tensors["ln_b"], tensors["fc1_w"], tensors["fc1_b"],
+                                                  tensors["to_out_w"], tensors["to_out_b"])
+                tensors["fc1_fold_w"] = derived.pop("fc1_fold_w")
                 for field, t in derived.items():
                     t = t.contiguous()
                     keep.append(t)

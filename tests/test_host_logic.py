@@ -146,3 +146,28 @@ def test_attention_base_state_dict_matches_reference_layout():
     want = ref_state_dict(p, 3)
     assert set(m.state_dict()) == set(want)
     m.load_state_dict(want, strict=True)
+
+
+def test_layernorm_fold_algebra_on_cpu():
+    """The operands dsnet.py derives for the LayerNorm-folded fc1 reproduce fc1(LayerNorm(y)) for any row shift."""
+    from edsnet_b200.dsnet import layernorm_fold_operands
+    g = torch.Generator().manual_seed(3)
+    R = 37
+    ln_w, ln_b = torch.rand(1024, generator=g) + 0.5, torch.randn(1024, generator=g) * 0.1
+    fc1_w, fc1_b = torch.randn(128, 1024, generator=g) / 32, torch.randn(128, generator=g) * 0.1
+    to_out_w, to_out_b = torch.randn(1024, 512, generator=g) / 22, torch.full((1024,), 0.1) + torch.randn(1024, generator=g) * 0.01
+    x = torch.relu(torch.randn(R, 1024, generator=g)) * 0.03
+    merged = torch.randn(R, 512, generator=g) * 0.02
+    op = layernorm_fold_operands(ln_w, ln_b, fc1_w, fc1_b, to_out_w, to_out_b)
+    y = (merged.double() @ to_out_w.double().t() + to_out_b.double() + x.double())
+    want = torch.nn.functional.layer_norm(y, (1024,), ln_w.double(), ln_b.double(), 1e-5) @ fc1_w.double().t() + fc1_b.double()
+    # what the two epilogues compute (in float64 here): z with the centred bias and the row mean of x removed
+    z = merged.double() @ to_out_w.double().t() + op["to_out_bc"].double() + (x.double() - x.double().mean(1, keepdim=True))
+    mean = z.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt((z * z).mean(1, keepdim=True) - mean * mean + 1e-5)
+    got = rstd * (z @ op["fc1_fold_w"].double().t() - mean * op["fc1_fold_wgsum"].double()[None, :]) + op["fc1_fold_b"].double()[None, :]
+    assert float((got - want).norm() / want.norm()) < 1e-6           # the operands themselves are fp32
+    # the row-scale bound the to_out epilogue uses really bounds |z|
+    l1max, bmax = [float(v) for v in op["to_out_bounds"]]
+    bound = 2 * x.abs().amax(1) + bmax + merged.abs().amax(1) * l1max
+    assert bool((z.abs().amax(1) <= bound.double()).all())
