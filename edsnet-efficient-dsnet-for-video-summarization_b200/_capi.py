@@ -131,6 +131,19 @@ def check(rc: int) -> None:
         raise EdsnetError(rc, last_error())
 
 
+def raise_on_tc_timeout() -> None:
+    """Call at a point where the device work of interest has been synchronised (after .cpu(), stream.synchronize()).
+    A tcgen05 pipeline wait that gave up (about one second without progress: preemption, a debugger, a hung peer) makes
+    the kernel drain with undefined results instead of hanging; the flag it leaves is read AND cleared here, so one
+    stall fails exactly the call it corrupted and does not poison later ones."""
+    rc = lib().edsnet_debug_tc_status(1)
+    if rc > 0:
+        raise EdsnetError(E_CUDA, "a tcgen05 pipeline wait timed out; the results of this call are undefined "
+                                  "(flag cleared, the call can be repeated)")
+    if rc < 0:
+        raise EdsnetError(E_CUDA, last_error())
+
+
 def make_config(scales, fc_depth: int, precision: int, base_model: int = 0) -> Config:
     scales = [int(s) for s in scales]
     if not 1 <= len(scales) <= EDSNET_MAX_SCALES:

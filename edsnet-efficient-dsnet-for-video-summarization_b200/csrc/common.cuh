@@ -7,16 +7,26 @@
 #include <set>
 #include <utility>
 
-// Function attributes (dynamic shared-memory opt-in) and device limits are per DEVICE, not per process: true exactly
-// once per (current device, tag), so a process that drives several GPUs configures each of them.
-inline bool first_use_on_device(const void* tag) {
-    static std::mutex m;
-    static std::set<std::pair<int, const void*>> seen;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> g(m);
-    return seen.insert({dev, tag}).second;
-}
+// Function attributes (dynamic shared-memory opt-in) and device limits are per DEVICE, not per process: a DeviceOnce is
+// true exactly once per (current device, tag), so a process that drives several GPUs configures each of them.  It
+// holds the registry lock for as long as it lives -- `if (DeviceOnce once{&tag}) { opt-in }` keeps every other host
+// thread out until the opt-in has actually run, so none of them can launch the kernel before its attribute is set.
+class DeviceOnce {
+    static std::mutex& mtx() { static std::mutex m; return m; }
+    std::unique_lock<std::mutex> lock_;
+    bool first_;
+public:
+    explicit DeviceOnce(const void* tag) : lock_(mtx()) {
+        static std::set<std::pair<int, const void*>> seen;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        first_ = seen.insert({dev, tag}).second;
+        if (!first_) lock_.unlock();
+    }
+    DeviceOnce(const DeviceOnce&) = delete;
+    DeviceOnce& operator=(const DeviceOnce&) = delete;
+    explicit operator bool() const { return first_; }
+};
 
 // Fixed geometry of the reference path (modules/models.py:135, anchor_based/dsnet.py:66-98).
 constexpr int kHeads    = 8;      // num_head

@@ -175,7 +175,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             !tc::make_map(&map_lo, p_lo, (uint64_t)b->total_rows, kQkvCols, 64, 64, &msg))
             return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
         static const char tc_tag = 0;
-        if (first_use_on_device(&tc_tag)) {
+        if (DeviceOnce once_{&tc_tag}) {
             CU_CHECK(opt_in_smem(tc::attn_out_tc_kernel, tc::kAoSmemBytes), "smem opt-in attn_out_tc");
             CU_CHECK(opt_in_smem(tc::a3v_tc_kernel, tc::kA3SmemBytes), "smem opt-in a3v_tc");
             CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
@@ -184,7 +184,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         }
     }
     static const char f32_tag = 0;
-    if (first_use_on_device(&f32_tag)) {
+    if (DeviceOnce once_{&f32_tag}) {
         CU_CHECK(opt_in_smem(a3v_kernel, kA3vSmem), "smem opt-in a3v");
         CU_CHECK(opt_in_smem(pinv_w_kernel, kPinvSmem), "smem opt-in pinv");
         CU_CHECK(opt_in_smem(attn_out_kernel, kAttnOutSmem), "smem opt-in attn_out");
@@ -266,7 +266,7 @@ int fc_stack_impl(const edsnet_config* cfg, const edsnet_weights* w, const float
         return EDSNET_OK;
     }
     static const char fcs_tag = 0;
-    if (first_use_on_device(&fcs_tag)) CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
+    if (DeviceOnce once_{&fcs_tag}) CU_CHECK(opt_in_smem(fc_stack_kernel, kFcStackSmem), "smem opt-in fc_stack");
     fc_stack_kernel<<<(rows + 63) / 64, 256, kFcStackSmem, st>>>(u_in, w->fcb_w, w->fcb_b, w->fcb_ln_w,
                                                                   w->fcb_ln_b, u_out, rows, cfg->fc_depth);
     CU_CHECK(cudaGetLastError(), "fc_stack_kernel");
@@ -479,7 +479,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         if (rc) return rc;
         {
             static const char mha_tag = 0;
-            if (first_use_on_device(&mha_tag)) CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
+            if (DeviceOnce once_{&mha_tag}) CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
             StageScope scope(ST_A3V, st);
             mha_flash_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kMhaSmem, st>>>(
                 F(L.qkv), batch->cu_rows, reinterpret_cast<const int2*>(batch->tiles64), F(L.merged));
@@ -583,7 +583,7 @@ int edsnet_kts(const edsnet_batch* batch, const edsnet_kts_video* videos, const 
     kts_scatter_kernel<<<dim3((unsigned)(((size_t)nmax * nmax + 255) / 256), V), 256, 0, st>>>(vids, scr);
     CU_CHECK(cudaGetLastError(), "kts_scatter_kernel");
     static const char dp_tag = 0;
-    if (first_use_on_device(&dp_tag)) CU_CHECK(opt_in_smem(kts_dp_kernel, 2 * (12800 + 1) * (int)sizeof(double)), "smem opt-in kts_dp");
+    if (DeviceOnce once_{&dp_tag}) CU_CHECK(opt_in_smem(kts_dp_kernel, 2 * (12800 + 1) * (int)sizeof(double)), "smem opt-in kts_dp");
     kts_dp_kernel<<<V, 1024, dp_smem, st>>>(vids, scr, ncp_cap, m_fixed, vmax, desc_rate, lmin, lmax, batch->cu_rows,
                                            n_cps, cps, objective);
     CU_CHECK(cudaGetLastError(), "kts_dp_kernel");
@@ -683,7 +683,7 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
     const int nms_smem = cap * 24;
     // the largest size (4096 anchors x 24 B = 96 KB) once per device covers every launch
     static const char nms_tag = 0;
-    if (first_use_on_device(&nms_tag)) CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemCap * 24), "smem opt-in nms");
+    if (DeviceOnce once_{&nms_tag}) CU_CHECK(opt_in_smem(nms_kernel, kNmsSmemCap * 24), "smem opt-in nms");
     {
         StageScope scope(ST_DECODE, st);
         decode_boxes_kernel<<<dim3((unsigned)((max_n + 255) / 256), batch->n_videos), 256, 0, st>>>(

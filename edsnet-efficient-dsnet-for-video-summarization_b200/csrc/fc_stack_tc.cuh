@@ -236,7 +236,7 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
                                       const float* w_cls = nullptr, const float* w_loc = nullptr,
                                       float* heads_out = nullptr) {
     static const char tag = 0;
-    if (first_use_on_device(&tag)) {
+    if (DeviceOnce once_{&tag}) {
         cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tc::kFcSmemBytes);
         if (e != cudaSuccess) return e;

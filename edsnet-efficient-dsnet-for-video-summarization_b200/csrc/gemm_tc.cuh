@@ -810,7 +810,7 @@ cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M
     if (!make_map(&mapB, B16, 2ull * N, K, BK, BN, msg)) return cudaErrorUnknown;
     auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI, ACCS>;
     static const char tag = 0;                      // one per template instantiation
-    if (first_use_on_device(&tag)) {
+    if (DeviceOnce once_{&tag}) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
     }

@@ -234,7 +234,7 @@ cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, i
     if (!make_map(&mapB, B16, 2ull * N, K, Cfg::BK, Cfg::BN / 2, msg)) return cudaErrorUnknown;
     auto kern = gemm_tc2_kernel<STAGES, EPI>;
     static const char tag = 0;                      // one per template instantiation
-    if (first_use_on_device(&tag)) {
+    if (DeviceOnce once_{&tag}) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
     }

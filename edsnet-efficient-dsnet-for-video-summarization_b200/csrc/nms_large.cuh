@@ -206,7 +206,7 @@ static cudaError_t launch_nms_large(const float* scores_v, const int* boxes_v, i
     int* counters = reinterpret_cast<int*>(scratch + (size_t)P * 24 + kNmsBlock);
     const int2* boxes = reinterpret_cast<const int2*>(boxes_v);
     static const char tag = 0;
-    if (first_use_on_device(&tag)) {
+    if (DeviceOnce once_{&tag}) {
         cudaError_t ea = cudaFuncSetAttribute(nmsl_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsResolveSmem);
         if (ea != cudaSuccess) return ea;
     }

@@ -12,6 +12,7 @@ multi-video entry points -- `forward_packed`, `proposals_packed` -- used by the 
 """
 from __future__ import annotations
 
+import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -135,8 +136,19 @@ class DSNet(nn.Module):
         self.fc_loc = nn.Sequential(nn.Linear(num_hidden, 2))
         self._wcache = None
         self._wkey = None
+        self._wlock = threading.Lock()
         self._workspace = None
         self._workspaces = {}
+
+    # caches and the lock are per-process state: a pickled / deep-copied model starts without them
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.update(_wcache=None, _wkey=None, _wlock=None, _workspace=None, _workspaces={})
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._wlock = threading.Lock()
 
     # ------------------------------------------------------------------ weights / workspace
     def _named_weights(self):
@@ -168,9 +180,17 @@ class DSNet(nn.Module):
         self._wkey = None
 
     def _weights(self, device, stream: int) -> _capi.Weights:
+        with self._wlock:
+            return self._weights_locked(device, stream)
+
+    def _weights_locked(self, device, stream: int) -> _capi.Weights:
         named = self._named_weights()
         key = (self.precision, str(device)) + tuple((n, p.data_ptr(), p._version) for n, p in named.items())
         if self._wkey == key:
+            # the operand planes were built on another stream: this one must not read them before they are complete
+            built_on, ready = self._wcache[2], self._wcache[3]
+            if built_on != stream:
+                torch.cuda.current_stream(device).wait_event(ready)
             return self._wcache[0]
         keep = []
         w = _capi.Weights()
@@ -208,7 +228,9 @@ class DSNet(nn.Module):
                                                  stream))
                 keep.append(planes)
                 setattr(w, field, planes.data_ptr())
-        self._wcache = (w, keep)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(device))
+        self._wcache = (w, keep, stream, ready)
         self._wkey = key
         return w
 
@@ -336,6 +358,7 @@ class DSNet(nn.Module):
         counts = r["keep_count"].cpu().numpy()
         ks = r["keep_scores"].cpu().numpy()
         kb = r["keep_boxes"].cpu().numpy()
+        _capi.raise_on_tc_timeout()
         S = self.num_scales
         out = []
         for v in range(batch.plan.n_videos):
@@ -400,7 +423,9 @@ class DSNet(nn.Module):
         with torch.no_grad():
             batch = BatchPlan.build([seq.shape[1]]).to(seq.device)
             boxes_f, _ = self.decode_packed(pred_loc.detach(), batch)
-        return pred_cls.cpu().numpy().reshape(-1), boxes_f.cpu().numpy().reshape(-1, 2)
+        out = pred_cls.detach().cpu().numpy().reshape(-1), boxes_f.cpu().numpy().reshape(-1, 2)
+        _capi.raise_on_tc_timeout()
+        return out
 
     def proposals(self, seq: torch.Tensor, nms_thresh: float = 0.5):
         """evaluate.py:24-28 in one call: predict -> clip/round -> nms.  Returns (keep_scores, keep_boxes)."""

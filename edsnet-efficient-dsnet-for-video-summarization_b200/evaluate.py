@@ -102,5 +102,6 @@ def evaluate(model, val_loader: Iterable, nms_thresh: float, device) -> Tuple[fl
         met = eval_metrics(x, batch, shots, truth, summ["summary"])
     f = met["fscore"].cpu().numpy()
     d = met["diversity"].cpu().numpy()
+    _capi.raise_on_tc_timeout()
     # data_helper.AverageMeter: running sums of python floats divided by the count
     return float(sum(float(v) for v in f) / len(f)), float(sum(float(v) for v in d) / len(d))

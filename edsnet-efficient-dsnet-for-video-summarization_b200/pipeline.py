@@ -145,5 +145,7 @@ class ScoringPipeline:
         cur.wait_stream(s_cmp)
         cur.wait_stream(s_in)
         torch.cuda.current_stream(device).synchronize()
+        from . import _capi
+        _capi.raise_on_tc_timeout()
         del pending
         return keep_count, keep_scores, keep_boxes, torch.from_numpy(cu.astype(np.int32))

@@ -131,5 +131,6 @@ def training_targets(model, gtscores: Sequence[np.ndarray], shots: ShotPlan, dev
 
 def split_summaries(summary: torch.Tensor, shots: ShotPlan) -> List[np.ndarray]:
     s = summary.cpu().numpy().astype(bool)
+    _capi.raise_on_tc_timeout()
     cf = shots.cu_frames_host
     return [s[cf[v]:cf[v + 1]] for v in range(shots.n_videos)]

@@ -230,9 +230,11 @@ def _cls_loss_static(pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     expression can be captured in a CUDA graph)."""
     pred, label = pred.reshape(-1), label.reshape(-1)
     pos, neg = label == 1, label == -1
-    zero = torch.zeros((), dtype=pred.dtype, device=pred.device)
-    lp = torch.where(pos, pred.log(), zero).sum() / pos.sum()
-    ln = torch.where(neg, (1 - pred).log(), zero).sum() / neg.sum()
+    # mask the ARGUMENT of the logarithm, not its result: log(0) of an unselected (or saturated) anchor would otherwise
+    # put 0 * inf = NaN into the gradient of every weight
+    one = torch.ones((), dtype=pred.dtype, device=pred.device)
+    lp = torch.where(pos, pred, one).log().sum() / pos.sum()
+    ln = torch.where(neg, 1 - pred, one).log().sum() / neg.sum()
     return 0.5 * (-lp - ln)
 
 

@@ -18,6 +18,21 @@ CASES = list(FWD["forward_cases"])
 DEV = "cuda:0"
 
 
+_PARITY_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_r02.jsonl")
+
+
+def _record_parity(test, case, rec):
+    """Append one line per case to gpurun_out/parity_r02.jsonl (copied to profiles/ and committed): how close the GPU
+    path is to the REFERENCE RUN where exact identity cannot be demanded unconditionally."""
+    import json
+    try:
+        os.makedirs(os.path.dirname(_PARITY_LOG), exist_ok=True)
+        with open(_PARITY_LOG, "a") as f:
+            f.write(json.dumps({"test": test, "case": case, **rec}) + "\n")
+    except OSError:
+        pass
+
+
 def _lib():
     from edsnet_b200 import _capi
     return _capi, _capi.lib()
@@ -256,9 +271,10 @@ def test_decode_nms_bit_exact_vs_reference_golden(name):
     assert np.array_equal(bi, orc.clip_round(want, T))
     # ... and within NumPy's own float32-exp error (<= 2.5 ulp of the width) of the reference run
     assert np.abs(bf - DN[f"{name}/lr"]).max() <= 4e-6 * np.abs(DN[f"{name}/lr"]).max()
+    # the correctly rounded exp reproduces the reference run's int32 boxes on every golden anchor (no edge of these cases
+    # lies within NumPy's 2.5-ulp exp error of k + 0.5): hard requirement, so the NMS comparison below is unconditional
     same_int = np.array_equal(bi, DN[f"{name}/boxes_i32"])
-    print(name, "int boxes identical to the reference run:", same_int)
-    assert (bi == DN[f"{name}/boxes_i32"]).all(axis=1).mean() > 0.9995
+    assert same_int, f"{name}: int32 boxes differ from the reference run"
     sc = DN[f"{name}/scores"]
     for thresh, suffix in ((0.5, ""), (0.3, "_t03")):
         r = model.nms_packed(scores, loc, batch, thresh)
@@ -294,10 +310,17 @@ def test_predict_and_proposals_match_reference_golden(name):
     # oracle NMS on OUR scores/boxes must agree bit for bit with the device NMS
     rs, rb, _ = orc.nms_1d(scores, ib, 0.5)
     assert np.array_equal(ks, rs) and np.array_equal(kb, rb)
-    if frac_same == 1.0 and len(np.unique(g["pred_cls"])) == g["pred_cls"].size:
-        # identical integer boxes: the kept boxes must equal the reference's unless two scores swapped order
-        same = len(kb) == len(g["keep_boxes"]) and np.array_equal(kb, g["keep_boxes"])
-        print(name, "kept set identical to the reference:", same)
+    same = len(kb) == len(g["keep_boxes"]) and np.array_equal(kb, g["keep_boxes"])
+    ref_scores = np.asarray(g["pred_cls"]).reshape(-1)
+    same_order = np.array_equal(np.argsort(scores, kind="stable"), np.argsort(ref_scores, kind="stable"))
+    _record_parity("predict_proposals", name, {"T": T, "scales": scales, "frac_int_boxes_equal_reference": frac_same,
+                                               "score_order_equal_reference": bool(same_order),
+                                               "kept_set_equal_reference": bool(same), "kept": int(len(kb)),
+                                               "kept_reference": int(len(g["keep_boxes"]))})
+    if frac_same == 1.0 and same_order:
+        # identical integer boxes visited in the identical order: greedy NMS is then a pure integer function of its
+        # input, so the kept boxes MUST equal what the reference's bbox_helper.nms returned
+        assert same, f"{name}: kept set differs from the reference although boxes and score order agree"
 
 
 def test_nms_packed_many_videos_vs_oracle():

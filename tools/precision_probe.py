@@ -30,6 +30,11 @@ def mm(a, b, mode):
         ah, bh = rnd(a, base), rnd(b, base)
         al, bl = rnd(a - ah, base), rnd(b - bh, base)
         return ah @ bh + (ah @ bl + al @ bh)
+    if mode.endswith("x2w"):     # only B (the weight) split: A_hi . [B_hi | B_lo], ONE N = 256 tcgen05 instruction
+        base = mode[:-3]
+        ah, bh = rnd(a, base), rnd(b, base)
+        bl = rnd(b - bh, base)
+        return ah @ bh + ah @ bl
     if mode.endswith("x2"):      # only A split (B single)
         base = mode[:-2]
         ah, bh = rnd(a, base), rnd(b, base)
@@ -92,6 +97,12 @@ PLANS = {
   "big3 bf16": plan(qkv="bf16", out="bf16", fc1="bf16"),
   "big3+fcb bf16x3": plan(qkv="bf16x3", out="bf16x3", fc1="bf16x3", fcb="bf16x3"),
   "big3+fcb fp16x2(A split)": plan(qkv="fp16x2", out="fp16x2", fc1="fp16x2", fcb="fp16x2"),
+  "big3 fp16x2w, fcb fp16x3": plan(qkv="fp16x2w", out="fp16x2w", fc1="fp16x2w", fcb="fp16x3"),
+  "qkv fp16x2w, rest fp16x3": plan(qkv="fp16x2w", out="fp16x3", fc1="fp16x3", fcb="fp16x3"),
+  "out fp16x2w, rest fp16x3": plan(qkv="fp16x3", out="fp16x2w", fc1="fp16x3", fcb="fp16x3"),
+  "fc1 fp16x2w, rest fp16x3": plan(qkv="fp16x3", out="fp16x3", fc1="fp16x2w", fcb="fp16x3"),
+  "qkv+out fp16x2w, rest fp16x3": plan(qkv="fp16x2w", out="fp16x2w", fc1="fp16x3", fcb="fp16x3"),
+  "big3 fp16x2 (A split), fcb fp16x3": plan(qkv="fp16x2", out="fp16x2", fc1="fp16x2", fcb="fp16x3"),
   "big3+fcb fp16x3": plan(qkv="fp16x3", out="fp16x3", fc1="fp16x3", fcb="fp16x3"),
   "big3+fcb tf32x3": plan(qkv="tf32x3", out="tf32x3", fc1="tf32x3", fcb="tf32x3"),
   "attn core tf32 (sim,agg), pinv fp32": plan(sim="tf32", sim2="tf32", agg="tf32"),
