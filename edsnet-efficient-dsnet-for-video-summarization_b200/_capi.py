@@ -12,12 +12,12 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 6
+EDSNET_ABI_VERSION = 7
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
-PREC_FP32, PREC_FP16X3, PREC_FP16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16}
+PREC_FP32, PREC_FP16X3, PREC_FP16, PREC_FP16X2 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "fp16": PREC_FP16, "fp16x2": PREC_FP16X2}
 BASE_MODELS = {"nystromformer": 0, "attention": 1}
 
 

@@ -4,6 +4,8 @@
 //   hi = fp16(x 2^s) and lo = fp16(x 2^s - hi) stay normal fp16 numbers for every element that matters), and the
 //   epilogue multiplies the accumulator by 2^-s_m 2^-s_n -- exact, powers of two.
 //   PASSES = 3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi   (fp32-grade accuracy: drops only the lo.lo term)
+//   PASSES = 2: A_hi.B_hi + A_hi.B_lo               (A rounded to fp16's 11 bits, B = the weight at 22 bits; ONE
+//                                                    tcgen05.mma with N = 2 BN per K step and no A_lo traffic)
 //   PASSES = 1: A_hi.B_hi                           (plain fp16 operands)
 // The tensor core adds each K=16 step into the fp32 accumulator with TRUNCATION (measured: a relative bias of about
 // 2e-8 per tcgen05.mma, 3.7e-6 after the 192 steps of a K=1024 three-pass product into one accumulator).  PASSES = 3
@@ -442,19 +444,21 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
 // ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (two main | cross pairs, K blocks alternate) or 2 (one pair);
 // PASSES == 1: 1.  Whatever fits twice into the 512 TMEM columns is double-buffered (MMAs of tile t+1 overlap the
 // drain of tile t).
-template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES == 3 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES >= 2 ? 4 : 1)>
 struct TcCfg {
     static constexpr int BM = 128;
     static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
     static constexpr int kBTile = BN * BK * 2;
-    static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
+    static constexpr int kAPlanes = PASSES == 3 ? 2 : 1;   // A_hi (| A_lo)
+    static constexpr int kBPlanes = PASSES >= 2 ? 2 : 1;   // B_hi (| B_lo)
     static constexpr int kAccs = ACCS;
     static constexpr int kBufs = (2 * ACCS * BN <= 512) ? 2 : 1;      // tiles in flight in TMEM
     static constexpr int kTmemCols = kAccs * kBufs * BN;
     static_assert(BN == 128 || BN == 64, "an epilogue thread keeps 64 columns of an output row in registers");
-    static_assert(PASSES == 3 ? (ACCS == 4 || ACCS == 2) : ACCS == 1, "accumulator scheme");
+    static_assert(PASSES >= 1 && PASSES <= 3, "1, 2 or 3 MMA passes");
+    static_assert(PASSES >= 2 ? (ACCS == 4 || ACCS == 2) : ACCS == 1, "accumulator scheme");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
-    static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
+    static constexpr int kStageBytes = kAPlanes * kATile + kBPlanes * kBTile;
     static constexpr int kEpiWarps = BN / 16;              // 8 (two per TMEM lane quarter) or 4
     static constexpr int kScratchOff = STAGES * kStageBytes + 256;    // after the barriers
     static constexpr int kSmemBytes = kScratchOff + kEpiWarps * kEpiScratchWarp + 1024 /*alignment slack*/;
@@ -466,7 +470,7 @@ struct TcCfg {
 // boundaries, so the smem ring is full again by the time the epilogue has drained TMEM.  The epilogue pulls the
 // whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
 // residual and stores -- the next tile's MMAs overlap those global accesses.
-template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES == 3 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1)>
 __global__ void __launch_bounds__(64 + 2 * BN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
@@ -522,17 +526,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
                     const uint32_t st = smem_base + s * Cfg::kStageBytes;
                     mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                    // stage layout: PASSES == 1: A_hi | B_hi; PASSES == 3: A_hi | A_lo | B_hi | B_lo (the two B planes
-                    // back to back: together they are ONE 2 BN-row operand).  Plane p of an operand with R rows starts
-                    // at row p*R.
+                    // stage layout: PASSES == 1: A_hi | B_hi; 2: A_hi | B_hi | B_lo; 3: A_hi | A_lo | B_hi | B_lo (the two B
+                    // planes back to back: together they are ONE 2 BN-row operand).  Plane p of an operand with R rows
+                    // starts at row p*R.
                     tma_load_2d(st, &mapA, full_bar(s), kb * BK, m0);
-                    if (PASSES == 3) {
-                        tma_load_2d(st + Cfg::kATile, &mapA, full_bar(s), kb * BK, M + m0);
-                        tma_load_2d(st + 2 * Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
-                        tma_load_2d(st + 2 * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
-                    } else {
-                        tma_load_2d(st + Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
-                    }
+                    if (PASSES == 3) tma_load_2d(st + Cfg::kATile, &mapA, full_bar(s), kb * BK, M + m0);
+                    tma_load_2d(st + Cfg::kAPlanes * Cfg::kATile, &mapB, full_bar(s), kb * BK, n0);
+                    if (PASSES >= 2)
+                        tma_load_2d(st + Cfg::kAPlanes * Cfg::kATile + Cfg::kBTile, &mapB, full_bar(s), kb * BK, N + n0);
                 }
             }
         }
@@ -555,12 +556,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (kPhased && kb == 1) ok = mbar_wait(tempty2_bar, tph ^ 1u) && ok;   // pair 1 drained
                     tc_fence_after();
                     const uint32_t st = smem_base + s * Cfg::kStageBytes;
-                    if (PASSES == 3) {
+                    if (PASSES >= 2) {
                         // A_hi . [B_hi | B_lo]^T as ONE N = 2 BN instruction into an adjacent (main | cross)
                         // accumulator pair -- A_hi leaves shared memory once for two of the three passes -- then
-                        // A_lo . B_hi^T into the cross accumulator.  ACCS == 4: K blocks alternate between two pairs.
+                        // (PASSES == 3) A_lo . B_hi^T into the cross accumulator.  ACCS == 4: K blocks alternate between
+                        // two pairs.
                         constexpr uint32_t idesc2 = make_idesc(Cfg::BM, 2 * BN);
-                        const uint32_t a_hi = st, a_lo = st + Cfg::kATile, b_hi = st + 2 * Cfg::kATile;
+                        const uint32_t a_hi = st, a_lo = st + Cfg::kATile, b_hi = st + Cfg::kAPlanes * Cfg::kATile;
                         const uint32_t acc_pair = tmem_acc + (ACCS == 4 ? (uint32_t)((kb & 1) * 2 * BN) : 0u);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
@@ -569,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const uint64_t dbh = make_smem_desc<BK>(b_hi + koff);
                             const bool first = ACCS == 4 ? (kb < 2 && k == 0) : ((kb | k) == 0);
                             umma_f16(acc_pair, dah, dbh, idesc2, first ? 0u : 1u);
-                            umma_f16(acc_pair + (uint32_t)BN, dal, dbh, idesc, 1u);
+                            if (PASSES == 3) umma_f16(acc_pair + (uint32_t)BN, dal, dbh, idesc, 1u);
                         }
                     } else {
                         const uint32_t a_hi = st, b_hi = st + Cfg::kATile;
@@ -710,7 +712,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 template <int COLS>
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
-                 float* __restrict__ inv_scale, int rows, float2* __restrict__ row_stat = nullptr) {
+                 float* __restrict__ inv_scale, int rows, float2* __restrict__ row_stat = nullptr, bool write_lo = true) {
+    // write_lo == false: the consumer is a two-pass product (A_hi only), the lo plane keeps its place but is not written
     constexpr int V = COLS / 128;                       // float4 per lane
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -748,7 +751,7 @@ split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half*
         __half2 ll[2] = {__halves2half2(l[0], l[1]), __halves2half2(l[2], l[3])};
         const size_t o = (size_t)row * COLS + (i * 32 + lane) * 4;
         *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(hh);
-        *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(ll);
+        if (write_lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(ll);
     }
 }
 
@@ -801,7 +804,7 @@ inline int num_sms() {
     return n;
 }
 
-template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES == 3 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1)>
 cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                            cudaStream_t st, std::string* msg) {
     using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS>;
@@ -839,7 +842,11 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
                          cudaStream_t st, std::string* msg) {
     const int variant = variant_ref();
     if (N % 128 == 0) {
-        if (PASSES == 3) {
+        if (PASSES == 2) {
+            // same accumulator scheme as three passes; a stage is 48 instead of 64 KB, so the ring is four deep
+            if (K <= 512) return launch_variant<128, 64, 4, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
+            return launch_variant<128, 64, 4, 2, EPI>(A16, B16, C, M, N, K, ep, st, msg);
+        } else if (PASSES == 3) {
             // four 128-column accumulators fill TMEM
             if (variant == 4 && EPI <= EPI_QKV_PLANES) return launch_pair<4, (EPI <= EPI_QKV_PLANES ? EPI : 0)>(A16, B16, C, M, N, K, ep, st, msg);
             if (variant == 3) return launch_variant<128, 64, 3, 3, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
@@ -863,6 +870,7 @@ static cudaError_t launch_gemm_tc(int passes, int epilogue, const __half* A16, c
     if (K % 64 != 0) { if (msg) *msg = "K must be a multiple of 64"; return cudaErrorInvalidValue; }
 #define TC_CASE(P, E) if (passes == P && epilogue == E) return tc::launch_shape<P, E>(A16, B16, C, M, N, K, ep, st, msg);
     TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3) TC_CASE(3, 4) TC_CASE(3, 5) TC_CASE(3, 6)
+    TC_CASE(2, 0) TC_CASE(2, 1) TC_CASE(2, 2) TC_CASE(2, 3) TC_CASE(2, 4) TC_CASE(2, 5) TC_CASE(2, 6)
     TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3) TC_CASE(1, 4) TC_CASE(1, 5) TC_CASE(1, 6)
 #undef TC_CASE
     if (msg) *msg = "unsupported passes/epilogue";
@@ -876,12 +884,12 @@ static inline const float* split_scales(const void* planes, size_t rows, size_t 
 }
 
 static cudaError_t launch_split_f16(const float* src, void* dst, int rows, int cols, cudaStream_t st,
-                                    float2* row_stat = nullptr) {
+                                    float2* row_stat = nullptr, bool write_lo = true) {
     __half* hi = static_cast<__half*>(dst);
     __half* lo = hi + (size_t)rows * cols;
     float* sc = reinterpret_cast<float*>(lo + (size_t)rows * cols);
     const unsigned blocks = (unsigned)((rows + 7) / 8);
-    if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows, row_stat);
+    if (cols == 1024) tc::split_f16_kernel<1024><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows, row_stat, write_lo);
     else if (cols == 128) tc::split_f16_kernel<128><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else if (cols == 512) tc::split_f16_kernel<512><<<blocks, 256, 0, st>>>(src, hi, lo, sc, rows);
     else return cudaErrorInvalidValue;

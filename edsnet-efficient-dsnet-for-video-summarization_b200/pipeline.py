@@ -77,6 +77,60 @@ class ScoringPipeline:
             self._dev_x = [torch.empty((max_rows, 1024), dtype=torch.float32, device=device)
                            for _ in range(self.depth)]
 
+    def run_copies_only(self, x_host: torch.Tensor, lengths: Sequence[int], device=None) -> None:
+        """The host<->device traffic of `run` without any kernel: the same chunks on the same copy streams (H2D of
+        the features and the batch tables, D2H of result-sized buffers).  Its duration is the floor the link and the
+        host memory system put under the end-to-end number; bench.py reports e2e as a fraction of it."""
+        model = self.model
+        device = torch.device(device) if device is not None else next(model.parameters()).device
+        lengths = [int(t) for t in lengths]
+        S = model.num_scales
+        V, R = len(lengths), int(sum(lengths))
+        chunks = self.chunk_videos(lengths, self.chunk_rows)
+        cu = np.zeros(V + 1, dtype=np.int64)
+        cu[1:] = np.cumsum(lengths)
+        self._setup(device, max(int(cu[b] - cu[a]) for a, b in chunks))
+        s_in, _, s_out = self._streams
+        if self._out is None or self._out[0].numel() != V or self._out[1].numel() != R * S:
+            self._out = (torch.empty(V, dtype=torch.int32).pin_memory(),
+                         torch.empty(R * S, dtype=torch.float32).pin_memory(),
+                         torch.empty((R * S, 2), dtype=torch.int32).pin_memory())
+        keep_count, keep_scores, keep_boxes = self._out
+        max_rows = self._dev_x[0].shape[0]
+        if getattr(self, "_floor_src", None) is None or self._floor_src[1].numel() < max_rows * S:
+            self._floor_src = (torch.zeros(max(V, 1), dtype=torch.int32, device=device),
+                               torch.zeros(max_rows * S, dtype=torch.float32, device=device),
+                               torch.zeros((max_rows * S, 2), dtype=torch.int32, device=device))
+        d_cnt, d_sc, d_bx = self._floor_src
+        cur = torch.cuda.current_stream(device)
+        for s in (s_in, s_out):
+            s.wait_stream(cur)
+        free_ev = [None] * self.depth
+        pending = []
+        for ci, (a, b) in enumerate(chunks):
+            r0, r1 = int(cu[a]), int(cu[b])
+            buf = self._dev_x[ci % self.depth]
+            plan = BatchPlan.build(lengths[a:b])
+            with torch.cuda.stream(s_in):
+                if free_ev[ci % self.depth] is not None:
+                    s_in.wait_event(free_ev[ci % self.depth])
+                buf[: r1 - r0].copy_(x_host[r0:r1], non_blocking=True)
+                dbatch = plan.to(device)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ready)
+                keep_count[a:b].copy_(d_cnt[: b - a], non_blocking=True)
+                keep_scores[r0 * S:r1 * S].copy_(d_sc[: (r1 - r0) * S], non_blocking=True)
+                keep_boxes[r0 * S:r1 * S].copy_(d_bx[: (r1 - r0) * S], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(s_out)
+                free_ev[ci % self.depth] = done
+            pending.append(dbatch)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+        torch.cuda.current_stream(device).synchronize()
+
     def run(self, x_host: torch.Tensor, lengths: Sequence[int], device=None):
         """x_host: [sum(lengths), 1024] float32 in (preferably pinned) host memory.
         Returns (keep_count int32 [V], keep_scores float32 [R*S], keep_boxes int32 [R*S, 2], cu_rows int32 [V+1]) as

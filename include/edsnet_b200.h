@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 6
+#define EDSNET_ABI_VERSION 7
 
 enum {
     EDSNET_OK = 0,
@@ -40,7 +40,10 @@ enum {
 enum {
     EDSNET_PREC_FP32 = 0,      /* CUDA-core FFMA, fp32 operands                       (<= 1e-5 vs reference) */
     EDSNET_PREC_FP16X3 = 1,    /* tcgen05 fp16 hi/lo split, 3 MMA passes, fp32 accum  (<= 1e-5 vs reference) */
-    EDSNET_PREC_FP16 = 2       /* tcgen05 fp16 single pass, fp32 accumulate           (~ 1e-3 vs reference)  */
+    EDSNET_PREC_FP16 = 2,      /* tcgen05 fp16 single pass, fp32 accumulate           (~ 1e-3 vs reference)  */
+    EDSNET_PREC_FP16X2 = 3     /* tcgen05, to_qkv and to_out with TWO passes (activations rounded to fp16's 11 bits,
+                                * weights split hi/lo: A_hi.[B_hi|B_lo] is one N = 256 instruction), fc1 / fc block /
+                                * attention core as in FP16X3                          (<= 5e-4 vs reference) */
 };
 
 /* base model in front of the shared scoring tail (modules/models.py:118-147) */

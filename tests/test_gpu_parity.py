@@ -45,7 +45,7 @@ def _no_tc_timeout():
 
 
 # ------------------------------------------------------------------------------------------------ GEMM stage
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16x2"])
 @pytest.mark.parametrize("M,N,K,epi", [(320, 1536, 1024, 1), (320, 1024, 512, 3), (320, 128, 1024, 2),
                                         (37, 1536, 1024, 1), (1000, 1024, 512, 3), (129, 128, 1024, 2),
                                         (4096, 1536, 1024, 0)])
@@ -84,8 +84,22 @@ def _gemm_check(precision, M, N, K, epi, tol=None):
     out = Cd.cpu().double()
     assert torch.isfinite(out).all()
     err = float((out - ref).norm() / ref.norm())
-    # operand rounding: fp32/fp16x3 ~ 2^-22..2^-24 per product, fp16 ~ 2^-11
-    assert err < (tol or {"fp32": 1e-6, "fp16x3": 1e-6, "fp16": 1e-3}[precision]), err
+    # operand rounding: fp32/fp16x3 ~ 2^-22..2^-24 per product, fp16 ~ 2^-11 on both operands, fp16x2 ~ 2^-11 on A only
+    assert err < (tol or {"fp32": 1e-6, "fp16x3": 1e-6, "fp16": 1e-3, "fp16x2": 5e-4}[precision]), err
+    if precision == "fp16x2":
+        # two passes must be EXACTLY the product of the rounded A with the 22-bit B (up to fp32 accumulation): compare
+        # against that product to make sure the cross term A_hi.B_lo really is in the result
+        s = torch.ldexp(torch.ones(M, dtype=torch.float64), (14 - torch.floor(torch.log2(A.abs().amax(1).double()))).int())
+        A_hi = (A.double() * s[:, None]).half().double() / s[:, None]
+        ref2 = A_hi @ B.double().t()
+        if epi == 1:
+            ref2[:, :512] *= 0.125
+        if epi >= 2:
+            ref2 += bias.double()
+        if epi == 3:
+            ref2 += res.double()
+        err2 = float((out - ref2).norm() / ref2.norm())
+        assert err2 < 2e-6, err2
 
 
 @pytest.mark.parametrize("variant", [3, 4])
@@ -103,7 +117,7 @@ def test_gemm_kernel_variants(variant):
 
 
 # ------------------------------------------------------------------------------------------------ forward
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16x2"])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_reference_golden(name, precision):
     g, x, p = golden_case(FWD, name)

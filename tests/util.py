@@ -14,7 +14,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # tensor-core mode and is held to the fp32-mode bar.
 # The single-pass fp16 mode is an opt-in fast mode that does NOT meet 1e-3 on every input (measured 3e-4 .. 1.3e-3 on
 # pred_loc: eleven-bit operands through five LayerNorm blocks); it is held to 3e-3 and is never the default.
-TOL = {"fp32": 1e-5, "fp16x3": 1e-5, "fp16": 3e-3}
+# fp16x2 (two MMA passes on to_qkv / to_out: activations at 11 bits, weights at 22) is the fast mode that DOES meet
+# the 1e-3 bar, gated at half of it (profiles/r02_precision_probe.log: <= 4.2e-4 predicted).
+TOL = {"fp32": 1e-5, "fp16x3": 1e-5, "fp16": 3e-3, "fp16x2": 5e-4}
 
 
 def load_npz(name):
