@@ -189,7 +189,9 @@ class DSNet(nn.Module):
         if self._wkey == key:
             # the operand planes were built on another stream: this one must not read them before they are complete
             built_on, ready = self._wcache[2], self._wcache[3]
-            if built_on != stream:
+            # (not under stream capture: an event recorded outside a capture cannot be waited on inside it, and
+            # graphed_forward synchronises the device between its warm-up call and the capture anyway)
+            if built_on != stream and not torch.cuda.is_current_stream_capturing():
                 torch.cuda.current_stream(device).wait_event(ready)
             return self._wcache[0]
         keep = []
