@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 7
+EDSNET_ABI_VERSION = 8
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -51,6 +51,24 @@ class WorkspaceLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in LAYOUT_FIELDS]
 
 
+GRAD_FIELDS = ("to_qkv_w", "to_out_w", "to_out_b", "res_conv_w", "ln_w", "ln_b", "fc1_w", "fc1_b",
+               "fcb_w", "fcb_b", "fcb_ln_w", "fcb_ln_b", "cls_w", "cls_b", "loc_w", "loc_b")
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GRAD_FIELDS]
+
+
+TRAIN_LAYOUT_FIELDS = ("w_qkv16", "w_out16", "w_fc116", "w_fcb16", "qkv16", "qkv_inv", "q_land", "k_land", "attn2", "stats",
+                       "a3v", "zmat", "wmat", "merged", "y", "yn", "uin", "hs", "u_last", "heads", "qkv_f32", "dqkv", "m3",
+                       "l3", "acc0", "acc_bytes", "dw_att", "dkl", "dql", "db_att", "da2", "dc_part", "zhist", "g", "d_logit",
+                       "das", "du0", "dyn", "dy", "dmerged", "t_a", "t_b", "total")
+
+
+class TrainLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in TRAIN_LAYOUT_FIELDS]
+
+
 class Shots(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("cu_seg", "cps", "nfps", "picks", "cu_frames", "capacity", "gcd", "dp_off")]
 
@@ -84,6 +102,18 @@ SYMBOLS = {
     "edsnet_nystrom_core": (C.c_int, [C.c_int32, C.POINTER(Batch), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "edsnet_fc_stack": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), _P, _P, C.c_int32, _P]),
     "edsnet_roi_pool_heads": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, _P, _P, _P]),
+    "edsnet_train_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int32, C.c_int32, C.POINTER(TrainLayout)]),
+    "edsnet_train_launches": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "edsnet_train_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, C.c_int32, C.c_uint64,
+                                       C.c_uint64, _P, _P, _P, C.c_size_t, _P]),
+    "edsnet_dropout_mask": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, _P, _P]),
+    "edsnet_loss_grad": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P,
+                                   _P]),
+    "edsnet_train_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, _P, _P, _P, C.c_int32,
+                                        C.c_int32, C.POINTER(Grads), _P, C.c_size_t, _P]),
+    "edsnet_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_int64, C.c_float, _P]),
+    "edsnet_split_f16_t": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "edsnet_debug_tc_status": (C.c_int, [C.c_int32]),
     "edsnet_debug_stage_timing": (C.c_int, [C.c_int32]),
     "edsnet_debug_stage_count": (C.c_int, []),

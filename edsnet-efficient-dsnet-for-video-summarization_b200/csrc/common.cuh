@@ -139,3 +139,24 @@ __device__ __forceinline__ void load64_transposed(float* __restrict__ S, const f
         S[(c4 + 3) * kLd64 + r] = v.w;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Dropout mask: Philox4x32-10, counter = (row, layer, offset_lo, offset_hi), key = (seed_lo, seed_hi); the 128 output
+// bits decide the 128 hidden columns of one (row, layer): bit set = kept (p = 1/2, survivors scaled by 2).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 dropout_words(unsigned long long seed, unsigned long long offset, int row, int layer) {
+    return philox4x32_10(make_uint4((uint32_t)row, (uint32_t)layer, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+

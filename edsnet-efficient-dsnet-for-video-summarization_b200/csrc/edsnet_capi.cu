@@ -1,6 +1,8 @@
 // C ABI of libedsnet_b200.so -- see include/edsnet_b200.h for the contract of every entry point.
 #include "../../include/edsnet_b200.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -20,6 +22,7 @@
 #include "summary.cuh"
 #include "eval.cuh"
 #include "kts.cuh"
+#include "train.cuh"
 
 namespace {
 
@@ -43,10 +46,18 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- optional per-stage CUDA-event timing (bench / profiling only; off by default) ----
 enum Stage : int { ST_SPLIT = 0, ST_QKV, ST_LANDMARKS, ST_ATTN2, ST_A3V, ST_PINV, ST_CONV, ST_ATTN_OUT, ST_TO_OUT, ST_LN,
-                   ST_FC1, ST_FC_STACK, ST_ROI, ST_DECODE, ST_NMS, ST_COUNT };
+                   ST_FC1, ST_FC_STACK, ST_ROI, ST_DECODE, ST_NMS,
+                   // training step (train.cuh)
+                   ST_T_WSPLIT, ST_T_LOSS, ST_T_ROI_BWD, ST_T_FC_BWD, ST_T_SPLIT, ST_T_GEMM_DW, ST_T_GEMM_DX, ST_T_LN_BWD,
+                   ST_T_ATTN_PREP, ST_T_ATTN_ROWS, ST_T_PINV_BWD, ST_T_ATTN2_BWD, ST_T_ATTN_KEYS, ST_T_FINISH, ST_T_ADAM,
+                   ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"split_f16", "to_qkv_gemm", "landmarks", "attn2_softmax", "a3v_stream",
                                            "pinv_w", "value_conv", "attn_out", "to_out_gemm", "layernorm1024",
-                                           "fc1_gemm", "fc_stack", "roi_pool_heads", "decode_boxes", "nms"};
+                                           "fc1_gemm", "fc_stack", "roi_pool_heads", "decode_boxes", "nms",
+                                           "train_weight_planes", "train_loss_grad", "train_roi_heads_bwd",
+                                           "train_fc_stack_bwd", "train_split_planes", "train_gemm_dw", "train_gemm_dx",
+                                           "train_ln1024_bwd", "train_attn_prep", "train_attn_bwd_rows", "train_pinv_bwd",
+                                           "train_attn2_bwd", "train_attn_bwd_keys", "train_dqkv_finish", "train_adam"};
 struct StageEvents { int stage; cudaEvent_t e0, e1; };
 bool g_stage_timing = false;
 std::vector<StageEvents> g_stage_events;
@@ -724,6 +735,404 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
             }
         }
     }
+    return EDSNET_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Training step (BASELINE.json config 3; anchor_based/train.py:110-128): train-mode forward, losses, backward, Adam.
+// =====================================================================================================================
+namespace {
+
+size_t round64(size_t x) { return (x + 63) & ~(size_t)63; }
+size_t planes_bytes(size_t rows, size_t cols) { return rows * cols * 4 + rows * 4; }
+
+void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos, edsnet_train_layout* out) {
+    edsnet_train_layout L;
+    std::memset(&L, 0, sizeof(L));
+    const size_t R = (size_t)(total_rows > 0 ? total_rows : 0), V = (size_t)(n_videos > 0 ? n_videos : 0);
+    const size_t D = (size_t)(cfg && cfg->fc_depth > 0 ? cfg->fc_depth : 0), S = (size_t)(cfg ? cfg->n_scales : 1);
+    const size_t Rp = round64(R), K5 = round64(D * R);
+    const size_t head_mat = V * kHeads * 4096 * sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    // ---- forward: weight planes of the step, activations kept for the backward ----
+    L.w_qkv16 = take(planes_bytes(kQkvCols, kFeat));
+    L.w_out16 = take(planes_bytes(kFeat, kInner));
+    L.w_fc116 = take(planes_bytes(kHidden, kFeat));
+    L.w_fcb16 = take(planes_bytes(kHidden, kHidden));
+    L.qkv16 = take(R * kQkvCols * 4);
+    L.qkv_inv = take(R * 24 * sizeof(float));
+    L.q_land = take(head_mat);
+    L.k_land = take(head_mat);
+    L.attn2 = take(head_mat);
+    L.stats = take(V * kHeads * 2 * sizeof(float));
+    L.a3v = take(head_mat);
+    L.zmat = take(head_mat);
+    L.wmat = take(head_mat);
+    L.merged = take(R * kInner * sizeof(float));
+    L.y = take(R * kFeat * sizeof(float));
+    L.yn = take(R * kFeat * sizeof(float));
+    L.uin = take(std::max<size_t>(D, 1) * R * kHidden * sizeof(float));
+    L.hs = take(std::max<size_t>(D, 1) * R * kHidden * sizeof(float));
+    L.u_last = take(R * kHidden * sizeof(float));
+    L.heads = take(R * 4 * sizeof(float));
+    // ---- backward ----
+    L.qkv_f32 = take(R * kQkvCols * sizeof(float));
+    L.dqkv = take(R * kQkvCols * sizeof(float));
+    L.m3 = take(V * kHeads * 64 * sizeof(float));
+    L.l3 = take(V * kHeads * 64 * sizeof(float));
+    L.acc0 = off;                                    // dW | dkl | dql: zeroed by one memset at the start of the backward
+    L.dw_att = take(head_mat);
+    L.dkl = take(head_mat);
+    L.dql = take(head_mat);
+    L.acc_bytes = off - L.acc0;
+    L.db_att = take(head_mat);
+    L.da2 = take(head_mat);
+    L.dc_part = take(V * kHeads * sizeof(float));
+    L.zhist = take(head_mat * kPinvIters);
+    L.g = take(R * 4 * sizeof(float));
+    L.d_logit = take(R * S * sizeof(float));
+    L.das = take(std::max<size_t>(D, 1) * R * kHidden * sizeof(float));
+    L.du0 = take(R * kHidden * sizeof(float));
+    L.dyn = take(R * kFeat * sizeof(float));
+    L.dy = take(R * kFeat * sizeof(float));
+    L.dmerged = take(R * kInner * sizeof(float));
+    // operand-plane scratch of the GEMMs (A side / B side), reused launch after launch
+    L.t_a = take(std::max(std::max(planes_bytes(kQkvCols, Rp), planes_bytes(kHidden, K5)), planes_bytes(R, kFeat)));
+    L.t_b = take(std::max(std::max(planes_bytes(kFeat, Rp), planes_bytes(kHidden, K5)),
+                          std::max(planes_bytes(kFeat, kHidden), planes_bytes(kInner, kFeat))));
+    L.total = off;
+    *out = L;
+}
+
+SplitTJob split_t_job(const float* src, int rows, int cols, int ld, void* planes, int* cta) {
+    SplitTJob j;
+    j.src = src;
+    j.rows = rows;
+    j.cols = cols;
+    j.ld = ld;
+    j.kp = (int)round64((size_t)rows);
+    j.hi = static_cast<__half*>(planes);
+    j.lo = j.hi + (size_t)cols * j.kp;
+    j.inv = reinterpret_cast<float*>(j.lo + (size_t)cols * j.kp);
+    j.cta0 = *cta;
+    *cta += (cols + 31) / 32;
+    return j;
+}
+
+int launch_split_t(const SplitTJob* jobs, int n, int ctas, cudaStream_t st) {
+    StageScope scope(ST_T_SPLIT, st);
+    SplitTJobs js;
+    js.n = n;
+    for (int i = 0; i < 4; ++i) js.j[i] = jobs[i < n ? i : 0];
+    split_t_kernel<<<ctas, 256, 0, st>>>(js);
+    CU_CHECK(cudaGetLastError(), "split_t_kernel");
+    return EDSNET_OK;
+}
+
+int check_train_cfg(const edsnet_config* cfg) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (cfg->base_model != EDSNET_BASE_NYSTROM)
+        return fail(EDSNET_E_UNSUPPORTED, "training kernels cover the Nystrom base (the hot path) only");
+    if (cfg->fc_depth < 1) return fail(EDSNET_E_UNSUPPORTED, "training kernels need fc_depth >= 1");
+    return EDSNET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t edsnet_train_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos,
+                                    edsnet_train_layout* layout) {
+    edsnet_train_layout L;
+    train_layout(cfg, total_rows, n_videos, &L);
+    if (layout) *layout = L;
+    return L.total;
+}
+
+int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* backward) {
+    if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
+    if (forward) *forward = 4 + 1 + 1 + 6 + 1 + 1 + 1 + 1 + 1 + 1 + 1;       // weight planes, split, qkv, core, ..., roi
+    if (backward) *backward = 27;
+    return EDSNET_OK;
+}
+
+int edsnet_dropout_mask(uint64_t seed, uint64_t offset, int32_t rows, int32_t depth, uint8_t* out, void* stream) {
+    if (!out || rows < 1 || depth < 1) return fail(EDSNET_E_ARG, "dropout_mask: bad argument");
+    dropout_mask_kernel<<<(rows * depth + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, offset, rows, depth, out);
+    CU_CHECK(cudaGetLastError(), "dropout_mask_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_split_f16_t(const float* src, int64_t rows, int64_t cols, void* dst, void* stream) {
+    if (!src || !dst || rows < 1 || cols < 1 || rows > (1 << 30) || cols > (1 << 24))
+        return fail(EDSNET_E_ARG, "split_f16_t: bad argument");
+    int cta = 0;
+    SplitTJob j = split_t_job(src, (int)rows, (int)cols, (int)cols, dst, &cta);
+    return launch_split_t(&j, 1, cta, static_cast<cudaStream_t>(stream));
+}
+
+int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
+                         int32_t dropout, uint64_t seed, uint64_t offset, float* pred_cls, float* pred_loc,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_train_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!w || !x || !pred_cls || !pred_loc || !workspace) return fail(EDSNET_E_ARG, "train_forward: NULL operand");
+    edsnet_train_layout L;
+    train_layout(cfg, batch->total_rows, batch->n_videos, &L);
+    if (workspace_bytes < L.total) return fail(EDSNET_E_WORKSPACE, "train_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    const int R = batch->total_rows;
+    const int P3 = EDSNET_PREC_FP16X3;              // every projection with three split-fp16 passes: fp32-grade
+    // operand planes of this step's weights (they change every step)
+    {
+        StageScope scope(ST_T_WSPLIT, st);
+        CU_CHECK(launch_split_f16(w->to_qkv_w, ws + L.w_qkv16, kQkvCols, kFeat, st), "split to_qkv.weight");
+        CU_CHECK(launch_split_f16(w->to_out_w, ws + L.w_out16, kFeat, kInner, st), "split to_out.weight");
+        CU_CHECK(launch_split_f16(w->fc1_w, ws + L.w_fc116, kHidden, kFeat, st), "split fc1.weight");
+        CU_CHECK(launch_split_f16(w->fcb_w, ws + L.w_fcb16, kHidden, kHidden, st), "split fc_block.0.weight");
+    }
+    {
+        StageScope scope(ST_SPLIT, st);
+        CU_CHECK(launch_split_f16(x, ws + L.t_a, R, kFeat, st), "split x");
+    }
+    rc = gemm_dispatch(P3, EPI_QKV_PLANES, nullptr, ws + L.t_a, nullptr, ws + L.w_qkv16, F(L.qkv16), R, kQkvCols, kFeat,
+                       nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
+    if (rc) return rc;
+    rc = nystrom_core_impl(P3, batch, F(L.qkv16), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2),
+                           F(L.stats), F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, nullptr);
+    if (rc) return rc;
+    {
+        StageScope scope(ST_SPLIT, st);
+        CU_CHECK(launch_split_f16(F(L.merged), ws + L.t_a, R, kInner, st), "split merged");
+    }
+    rc = gemm_dispatch(P3, EPI_BIAS_RES, nullptr, ws + L.t_a, nullptr, ws + L.w_out16, F(L.y), R, kFeat, kInner,
+                       w->to_out_b, x, 0, st, ST_TO_OUT);
+    if (rc) return rc;
+    {
+        StageScope scope(ST_LN, st);
+        layernorm1024_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.y), w->ln_w, w->ln_b, F(L.yn), R);
+        CU_CHECK(cudaGetLastError(), "layernorm1024_kernel");
+    }
+    {
+        StageScope scope(ST_SPLIT, st);
+        CU_CHECK(launch_split_f16(F(L.yn), ws + L.t_a, R, kFeat, st), "split LayerNorm output");
+    }
+    rc = gemm_dispatch(P3, EPI_BIAS, nullptr, ws + L.t_a, nullptr, ws + L.w_fc116, F(L.uin), R, kHidden, kFeat, w->fc1_b,
+                       nullptr, 0, st, ST_FC1);
+    if (rc) return rc;
+    {
+        StageScope scope(ST_FC_STACK, st);
+        CU_CHECK(launch_fc_stack_tc(F(L.uin), ws + L.w_fcb16, w->fcb_b, w->fcb_ln_w, w->fcb_ln_b, F(L.u_last), R,
+                                    cfg->fc_depth, st, w->cls_w, w->loc_w, F(L.heads), F(L.hs), dropout ? 1 : 0, seed,
+                                    offset), "fc_stack_tc_kernel<train>");
+    }
+    return roi_impl(cfg, w, batch, F(L.heads), pred_cls, pred_loc, st, true);
+}
+
+int edsnet_loss_grad(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls, const float* pred_loc,
+                     const int32_t* cls_label, const float* loc_label, float lambda_reg, float scale, float* d_logit,
+                     float* d_loc, float* loss_out, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!pred_cls || !pred_loc || !cls_label || !loc_label || !d_logit || !d_loc || !loss_out)
+        return fail(EDSNET_E_ARG, "loss_grad: NULL operand");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StageScope scope(ST_T_LOSS, st);
+    loss_grad_kernel<<<batch->n_videos, 256, 0, st>>>(pred_cls, pred_loc, cls_label, loc_label, batch->cu_rows,
+                                                     cfg->n_scales, lambda_reg, scale, d_logit, d_loc, loss_out);
+    CU_CHECK(cudaGetLastError(), "loss_grad_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
+                          const float* pred_cls, const float* d_cls, const float* d_loc, int32_t d_cls_is_logit_grad,
+                          int32_t dropout, const edsnet_grads* grads, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    int rc = check_train_cfg(cfg);
+    if (rc) return rc;
+    rc = check_batch(batch);
+    if (rc) return rc;
+    if (!w || !x || !pred_cls || !d_cls || !d_loc || !grads || !workspace)
+        return fail(EDSNET_E_ARG, "train_backward: NULL operand");
+    const float* const* gp = reinterpret_cast<const float* const*>(grads);
+    for (size_t i = 0; i < sizeof(edsnet_grads) / sizeof(float*); ++i)
+        if (!gp[i]) return fail(EDSNET_E_ARG, "train_backward: a gradient buffer is NULL");
+    edsnet_train_layout L;
+    train_layout(cfg, batch->total_rows, batch->n_videos, &L);
+    if (workspace_bytes < L.total) return fail(EDSNET_E_WORKSPACE, "train_backward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    const int R = batch->total_rows, V = batch->n_videos, D = cfg->fc_depth, S = cfg->n_scales;
+    const int Rp = (int)round64((size_t)R), K5 = (int)round64((size_t)D * R);
+    const int P3 = EDSNET_PREC_FP16X3;
+    const int2* t64 = reinterpret_cast<const int2*>(batch->tiles64);
+    const int2* t128 = reinterpret_cast<const int2*>(batch->tiles128);
+    static const char bwd_tag = 0;
+    if (DeviceOnce once_{&bwd_tag}) {
+        CU_CHECK(opt_in_smem(fc_stack_bwd_kernel, kFcBwdSmem), "smem opt-in fc_stack_bwd");
+        CU_CHECK(opt_in_smem(attn_bwd_rows_kernel, kAttnBwdRowsSmem), "smem opt-in attn_bwd_rows");
+        CU_CHECK(opt_in_smem(pinv_bwd_kernel, kPinvBwdSmem), "smem opt-in pinv_bwd");
+        CU_CHECK(opt_in_smem(attn2_bwd_kernel, 4 * 64 * kLd64 * (int)sizeof(float)), "smem opt-in attn2_bwd");
+        CU_CHECK(opt_in_smem(attn_bwd_keys_kernel, kAttnBwdKeysSmem), "smem opt-in attn_bwd_keys");
+    }
+    CU_CHECK(cudaMemsetAsync(ws + L.acc0, 0, L.acc_bytes, st), "zero attention accumulators");
+    // 1. d logits
+    const float* d_logit = d_cls;
+    if (!d_cls_is_logit_grad) {
+        StageScope scope(ST_T_LOSS, st);
+        sigmoid_bwd_kernel<<<(R * S + 255) / 256, 256, 0, st>>>(pred_cls, d_cls, F(L.d_logit), R * S);
+        CU_CHECK(cudaGetLastError(), "sigmoid_bwd_kernel");
+        d_logit = F(L.d_logit);
+    }
+    // 2. pooling + heads
+    {
+        int halo = 0;
+        ScaleList sl = make_scales(cfg, &halo);
+        StageScope scope(ST_T_ROI_BWD, st);
+        roi_heads_bwd_kernel<<<batch->n_tiles128, 256, (size_t)S * 3 * (kRoiBwdRows + 1) * sizeof(float), st>>>(
+            d_logit, d_loc, batch->cu_rows, t128, sl, halo, F(L.g), grads->cls_b, grads->loc_b);
+        CU_CHECK(cudaGetLastError(), "roi_heads_bwd_kernel");
+    }
+    // 3. shared fc block x D
+    {
+        StageScope scope(ST_T_FC_BWD, st);
+        FcBwdGrads fg{grads->fcb_b, grads->fcb_ln_w, grads->fcb_ln_b, grads->fc1_b, grads->cls_w, grads->loc_w};
+        fc_stack_bwd_kernel<<<(R + 63) / 64, 256, kFcBwdSmem, st>>>(F(L.g), F(L.hs), F(L.uin), F(L.das), F(L.du0), w->fcb_w,
+                                                                   w->fcb_ln_w, w->fcb_ln_b, w->cls_w, w->loc_w, R, D,
+                                                                   dropout ? 2.f : 1.f, fg);
+        CU_CHECK(cudaGetLastError(), "fc_stack_bwd_kernel");
+    }
+    SplitTJob jobs[4];
+    int cta;
+    // 4. d fc_block.0.weight = sum_l da_l^T u_l  (one product with K = D x rows)
+    cta = 0;
+    jobs[0] = split_t_job(F(L.das), D * R, kHidden, kHidden, ws + L.t_a, &cta);
+    jobs[1] = split_t_job(F(L.uin), D * R, kHidden, kHidden, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 2, cta, st);
+    if (rc) return rc;
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fcb_w, kHidden, kHidden, K5, nullptr,
+                       nullptr, 0, st, ST_T_GEMM_DW);
+    if (rc) return rc;
+    // 5. d fc1.weight = du0^T LN(y)
+    cta = 0;
+    jobs[0] = split_t_job(F(L.du0), R, kHidden, kHidden, ws + L.t_a, &cta);
+    jobs[1] = split_t_job(F(L.yn), R, kFeat, kFeat, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 2, cta, st);
+    if (rc) return rc;
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fc1_w, kHidden, kFeat, Rp, nullptr,
+                       nullptr, 0, st, ST_T_GEMM_DW);
+    if (rc) return rc;
+    // 6. d LN(y) = du0 W1
+    {
+        StageScope scope(ST_T_SPLIT, st);
+        CU_CHECK(launch_split_f16(F(L.du0), ws + L.t_a, R, kHidden, st), "split du0");
+    }
+    cta = 0;
+    jobs[0] = split_t_job(w->fc1_w, kHidden, kFeat, kFeat, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 1, cta, st);
+    if (rc) return rc;
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, F(L.dyn), R, kFeat, kHidden, nullptr, nullptr,
+                       0, st, ST_T_GEMM_DX);
+    if (rc) return rc;
+    // 7. LayerNorm(1024)
+    {
+        StageScope scope(ST_T_LN_BWD, st);
+        ln1024_bwd_kernel<<<(R + 63) / 64, 256, 0, st>>>(F(L.y), F(L.dyn), w->ln_w, F(L.dy), R, grads->ln_w, grads->ln_b,
+                                                        grads->to_out_b);
+        CU_CHECK(cudaGetLastError(), "ln1024_bwd_kernel");
+    }
+    // 8. d to_out.weight = dy^T merged
+    cta = 0;
+    jobs[0] = split_t_job(F(L.dy), R, kFeat, kFeat, ws + L.t_a, &cta);
+    jobs[1] = split_t_job(F(L.merged), R, kInner, kInner, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 2, cta, st);
+    if (rc) return rc;
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_out_w, kFeat, kInner, Rp, nullptr,
+                       nullptr, 0, st, ST_T_GEMM_DW);
+    if (rc) return rc;
+    // 9. d merged = dy Wout
+    {
+        StageScope scope(ST_T_SPLIT, st);
+        CU_CHECK(launch_split_f16(F(L.dy), ws + L.t_a, R, kFeat, st), "split dy");
+    }
+    cta = 0;
+    jobs[0] = split_t_job(w->to_out_w, kFeat, kInner, kInner, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 1, cta, st);
+    if (rc) return rc;
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, F(L.dmerged), R, kInner, kFeat, nullptr,
+                       nullptr, 0, st, ST_T_GEMM_DX);
+    if (rc) return rc;
+    // 10. attention block
+    {
+        StageScope scope(ST_T_ATTN_PREP, st);
+        const __half* p_hi = reinterpret_cast<const __half*>(ws + L.qkv16);
+        qkv_planes_to_f32_kernel<<<(unsigned)(((size_t)R * (kQkvCols / 4) + 255) / 256), 256, 0, st>>>(
+            p_hi, p_hi + (size_t)R * kQkvCols, F(L.qkv_inv), F(L.qkv_f32), R);
+        CU_CHECK(cudaGetLastError(), "qkv_planes_to_f32_kernel");
+        a3_stats_kernel<<<dim3(kHeads, V), 256, 0, st>>>(F(L.qkv_f32), batch->cu_rows, F(L.q_land), F(L.m3), F(L.l3));
+        CU_CHECK(cudaGetLastError(), "a3_stats_kernel");
+    }
+    {
+        StageScope scope(ST_T_ATTN_ROWS, st);
+        attn_bwd_rows_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kAttnBwdRowsSmem, st>>>(
+            F(L.qkv_f32), F(L.dmerged), batch->cu_rows, t64, F(L.k_land), F(L.wmat), w->res_conv_w, F(L.dqkv), F(L.dw_att),
+            F(L.dkl), grads->res_conv_w);
+        CU_CHECK(cudaGetLastError(), "attn_bwd_rows_kernel");
+    }
+    {
+        StageScope scope(ST_T_PINV_BWD, st);
+        pinv_bwd_kernel<<<dim3(kHeads, V), 256, kPinvBwdSmem, st>>>(F(L.attn2), F(L.stats), F(L.a3v), F(L.dw_att), F(L.zhist),
+                                                                   F(L.db_att), F(L.da2), F(L.dc_part), kPinvIters);
+        CU_CHECK(cudaGetLastError(), "pinv_bwd_kernel");
+    }
+    {
+        StageScope scope(ST_T_ATTN2_BWD, st);
+        attn2_bwd_kernel<<<dim3(kHeads, V), 256, 4 * 64 * kLd64 * sizeof(float), st>>>(
+            F(L.attn2), F(L.stats), F(L.da2), F(L.dc_part), F(L.q_land), F(L.k_land), F(L.dql), F(L.dkl));
+        CU_CHECK(cudaGetLastError(), "attn2_bwd_kernel");
+    }
+    {
+        StageScope scope(ST_T_ATTN_KEYS, st);
+        attn_bwd_keys_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kAttnBwdKeysSmem, st>>>(
+            F(L.qkv_f32), batch->cu_rows, t64, F(L.q_land), F(L.a3v), F(L.db_att), F(L.m3), F(L.l3), F(L.dqkv), F(L.dql));
+        CU_CHECK(cudaGetLastError(), "attn_bwd_keys_kernel");
+    }
+    {
+        StageScope scope(ST_T_FINISH, st);
+        dqkv_finish_kernel<<<batch->n_tiles64, 256, 0, st>>>(batch->cu_rows, t64, F(L.dql), F(L.dkl), F(L.dqkv));
+        CU_CHECK(cudaGetLastError(), "dqkv_finish_kernel");
+    }
+    // 11. d to_qkv.weight = dqkv^T x
+    cta = 0;
+    jobs[0] = split_t_job(F(L.dqkv), R, kQkvCols, kQkvCols, ws + L.t_a, &cta);
+    jobs[1] = split_t_job(x, R, kFeat, kFeat, ws + L.t_b, &cta);
+    rc = launch_split_t(jobs, 2, cta, st);
+    if (rc) return rc;
+    return gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_qkv_w, kQkvCols, kFeat, Rp, nullptr,
+                         nullptr, 0, st, ST_T_GEMM_DW);
+}
+
+int edsnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || n > (1ll << 31) - 256 || step < 1)
+        return fail(EDSNET_E_ARG, "adam_step: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StageScope scope(ST_T_ADAM, st);
+    const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (int)n, lr, beta1, beta2, eps,
+                                                            weight_decay, (float)bc1, (float)std::sqrt(bc2), grad_scale);
+    CU_CHECK(cudaGetLastError(), "adam_kernel");
     return EDSNET_OK;
 }
 

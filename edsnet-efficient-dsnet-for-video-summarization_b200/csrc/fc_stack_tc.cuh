@@ -40,11 +40,16 @@ __device__ __forceinline__ uint32_t fc_plane_off(int r, int c16) {
 // LayerNorm outputs, bounded by sqrt(127) max|gamma| + max|beta|: one fixed scale, no exchange) and the row sum /
 // sum of squares of every LayerNorm.  Sixteen warps instead of eight keep the per-layer register arithmetic of one
 // group under the other group's MMAs and barriers.
+// SAVE (training forward, anchor_based/dsnet.py:91-95 in train() mode): Dropout(0.5) after the ReLU (Philox mask of
+// common.cuh, survivors x 2; off when drop == 0) and h_save [depth][rows][128] = the rows BEFORE the LayerNorm of every
+// application of the block -- all the backward needs (h > 0 <=> kept and active; the LayerNorm is recomputed).
+template <bool SAVE>
 __global__ void __launch_bounds__(512, 1)
 fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_planes, const float* __restrict__ w_inv_scale,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ u_out, int rows, int depth, const float* __restrict__ w_cls,
-                   const float* __restrict__ w_loc, float4* __restrict__ heads_out) {
+                   const float* __restrict__ w_loc, float4* __restrict__ heads_out, float* __restrict__ h_save, int drop,
+                   unsigned long long seed, unsigned long long offset) {
     // heads_out != nullptr: the three head projections of every output row (u . w_cls, u . w_loc[0], u . w_loc[1]; the
     // ROI pooling and the heads are linear, so the pooling windows then run over these 3 channels) are emitted, 16 bytes
     // per row; u_out may then be nullptr and the 512-byte rows are never written.
@@ -174,6 +179,14 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
             tc_fence_after();
             // ---- epilogue in registers: (main + lo) * scales + bias, ReLU, LayerNorm(128) ----
             float sum = 0.f, sq = 0.f;
+            uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;          // keep bits of this thread's 64 columns
+            float keep_mul = 1.f;
+            if (SAVE && drop) {
+                const uint4 dw = dropout_words(seed, offset, row, layer);
+                kw0 = half ? dw.z : dw.x;
+                kw1 = half ? dw.w : dw.y;
+                keep_mul = 2.f;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 uint32_t r0[16], r1[16];
@@ -184,9 +197,16 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
                 for (int j = 0; j < 16; ++j) {
                     const float acc = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
                     const float lin = fmaf(acc, inv_a * vec[cb + c0 + j], vec[128 + cb + c0 + j]);
-                    u[c0 + j] = fmaxf(lin, 0.f);
-                    sum += u[c0 + j];
+                    float val = fmaxf(lin, 0.f);
+                    if (SAVE) val = (((c0 + j) < 32 ? kw0 : kw1) >> ((c0 + j) & 31)) & 1u ? val * keep_mul : 0.f;
+                    u[c0 + j] = val;
+                    sum += val;
                 }
+            }
+            if (SAVE && row < rows) {
+                float* hd = h_save + ((size_t)layer * rows + row) * kHidden + cb;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) st4(hd + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
             }
             // mean over the whole row first, then the centred sum of squares (two exchanges, two-pass variance)
             float* slot = xg + ((layer & 1) * 2) * 256;
@@ -234,17 +254,26 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
 static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, const float* bias, const float* gamma,
                                       const float* beta, float* u_out, int rows, int depth, cudaStream_t st,
                                       const float* w_cls = nullptr, const float* w_loc = nullptr,
-                                      float* heads_out = nullptr) {
+                                      float* heads_out = nullptr, float* h_save = nullptr, int drop = 0,
+                                      unsigned long long seed = 0, unsigned long long offset = 0) {
     static const char tag = 0;
     if (DeviceOnce once_{&tag}) {
-        cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tc::kFcSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tc::kFcSmemBytes);
         if (e != cudaSuccess) return e;
     }
     const int n_pairs = ((rows + tc::kFcTile - 1) / tc::kFcTile + 1) / 2;
     const int grid = n_pairs < tc::num_sms() ? n_pairs : tc::num_sms();
-    tc::fc_stack_tc_kernel<<<grid, 512, tc::kFcSmemBytes, st>>>(
-        u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
-        depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out));
+    if (h_save != nullptr)
+        tc::fc_stack_tc_kernel<true><<<grid, 512, tc::kFcSmemBytes, st>>>(
+            u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
+            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), h_save, drop, seed, offset);
+    else
+        tc::fc_stack_tc_kernel<false><<<grid, 512, tc::kFcSmemBytes, st>>>(
+            u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
+            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), nullptr, 0, 0ull, 0ull);
     return cudaGetLastError();
 }

@@ -139,6 +139,16 @@ class DSNet(nn.Module):
         self._wlock = threading.Lock()
         self._workspace = None
         self._workspaces = {}
+        self._drop_seed = None
+        self._drop_offset = 0
+
+    def _next_dropout_stream(self):
+        """(seed, offset) of the next train-mode forward's Philox dropout mask: the seed is torch's initial seed at the
+        first use (torch.manual_seed makes runs repeatable), the offset counts the calls."""
+        if self._drop_seed is None:
+            self._drop_seed = int(torch.initial_seed()) & ((1 << 64) - 1)
+        self._drop_offset += 1
+        return self._drop_seed, self._drop_offset
 
     # caches and the lock are per-process state: a pickled / deep-copied model starts without them
     def __getstate__(self):
@@ -270,13 +280,18 @@ class DSNet(nn.Module):
         self._check_input(x)
         if x.dim() != 2 or x.shape[1] != NUM_FEATURE:
             raise RuntimeError(f"expected [rows, {NUM_FEATURE}] features, got {tuple(x.shape)}")
-        if self.training:
-            # train(): Dropout(0.5) inside the shared fc block is active (dsnet.py:91-95) -> differentiable torch-op
-            # graph on the GPU (training is the next row to go native, see autograd.py)
-            from .autograd import scoring_with_grad
-            return scoring_with_grad(self, x, batch)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            from .autograd import kernel_forward_with_grad
+        wants_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.training or wants_grad:
+            # train(): Dropout(0.5) inside the shared fc block is active (dsnet.py:91-95); with gradients enabled the call
+            # is differentiable with respect to the parameters.  Nystrom base: the training kernels (native_train.py:
+            # edsnet_train_forward / edsnet_train_backward).  The comparison base ('attention') and gradients with respect
+            # to the INPUT features are outside the hot path and go through the torch-op graph of autograd.py.
+            if self.base_model_type == "nystromformer" and not x.requires_grad:
+                from .native_train import scoring_with_native_grad
+                return scoring_with_native_grad(self, x, batch)
+            from .autograd import kernel_forward_with_grad, scoring_with_grad
+            if self.training:
+                return scoring_with_grad(self, x, batch)
             return kernel_forward_with_grad(self, x, batch)
         return self._forward_nograd(x, batch)
 

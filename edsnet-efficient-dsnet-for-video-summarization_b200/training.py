@@ -9,8 +9,11 @@ What each function restates (reference files relative to /root/reference/src):
   DataParallelStep     the per-video loop body of anchor_based/train.py:110-128, batched over the videos of a rank and
                        made data parallel: the reference has no collective at all; averaging the
                        gradient over W ranks turns its batch-1 SGD into batch-W, which is what config 3 asks for.
-The forward in train() mode is the differentiable torch-op graph of autograd.py (Dropout active); native backward
-kernels are the next row.
+  NativeDataParallelStep  (native_train.py) the same step on the training kernels of libedsnet_b200.so: train-mode forward,
+                       loss gradient, backward, ONE flat NCCL all-reduce, Adam -- no torch op computes any part of it.
+DataParallelStep / GraphedDataParallelStep drive the model through torch autograd (model(x) in train() mode lands in the
+same kernels via native_train._NativeScoring; the losses and Adam are torch ops there): they are the reference-shaped
+loop, NativeDataParallelStep is the fast path bench.py --config c3 measures.
 """
 from __future__ import annotations
 
@@ -19,6 +22,9 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+from .native_train import NativeDataParallelStep      # noqa: E402,F401  (re-exported: training.NativeDataParallelStep)
 
 
 # ----------------------------------------------------------------------------------------------- labels (host, NumPy)

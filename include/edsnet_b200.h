@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 7
+#define EDSNET_ABI_VERSION 8
 
 enum {
     EDSNET_OK = 0,
@@ -255,6 +255,91 @@ int edsnet_forward_launches(const edsnet_config* cfg);
  * lo plane [rows][cols] fp16 (lo = fp16(x 2^s - hi)) | inverse scales [rows] fp32 (2^-s). */
 size_t edsnet_split_f16_bytes(int64_t rows, int64_t cols);
 int edsnet_split_f16(const float* src, void* dst_hi_lo, int64_t rows, int64_t cols, void* stream);
+
+/* ---- training step (BASELINE.json config 3) ------------------------------------------------------------------------
+ * What the reference's loop body runs per video (anchor_based/train.py:110-128): `model(seq)` in train() mode,
+ * calc_cls_loss + calc_loc_loss (anchor_based/losses.py:5-57), `loss.backward()`, `optimizer.step()` (Adam, :53-55) -- as
+ * CUDA kernels on a packed batch of videos.  Nystrom base only, fc_depth >= 1.  All projections and their dW / dX
+ * products run on tcgen05 with three split-fp16 passes; the 64-wide attention backward is fp32 on CUDA cores.
+ * The input features get no gradient (the reference's features are data). */
+
+/* Gradient buffers, fp32 [dev], one per parameter, same shapes as the weights of the same name.  They must be ZERO on
+ * entry to edsnet_train_backward (the small ones are accumulated atomically); on exit they hold d loss / d parameter. */
+typedef struct {
+    float* to_qkv_w;   float* to_out_w;  float* to_out_b;  float* res_conv_w;
+    float* ln_w;       float* ln_b;      float* fc1_w;     float* fc1_b;
+    float* fcb_w;      float* fcb_b;     float* fcb_ln_w;  float* fcb_ln_b;
+    float* cls_w;      float* cls_b;     float* loc_w;     float* loc_b;
+} edsnet_grads;
+
+/* Byte offsets inside the training workspace (tests / profiling).  The forward fills the first group and the backward
+ * reads it, so ONE workspace must be passed to both calls of a step. */
+typedef struct {
+    size_t w_qkv16, w_out16, w_fc116, w_fcb16;   /* operand planes of the step's weights (edsnet_split_f16 layout)       */
+    size_t qkv16, qkv_inv;                       /* q | k | v operand planes [rows][1536] hi, lo; scales [rows][24]      */
+    size_t q_land, k_land, attn2, stats, a3v, zmat, wmat;   /* as in edsnet_workspace_layout                             */
+    size_t merged;                               /* [rows][512] fp32: attention + value convolution, head-merged         */
+    size_t y;                                    /* [rows][1024] to_out + bias + x                                      */
+    size_t yn;                                   /* [rows][1024] LayerNorm(y)                                           */
+    size_t uin;                                  /* [depth][rows][128] input of every application of the fc block       */
+    size_t hs;                                   /* [depth][rows][128] Dropout(ReLU(Linear)) of every application        */
+    size_t u_last;                               /* [rows][128] final hidden rows                                        */
+    size_t heads;                                /* [rows][4] head projections                                          */
+    size_t qkv_f32;                              /* [rows][1536] fp32 copy of q/8 | k | v (backward)                     */
+    size_t dqkv;                                 /* [rows][1536] gradient of the to_qkv output                           */
+    size_t m3, l3;                               /* [videos][8][64] row maximum / normaliser of softmax(q_land k^T)      */
+    size_t acc0, acc_bytes;                      /* dw_att | dkl | dql, zeroed at the start of the backward             */
+    size_t dw_att, dkl, dql, db_att, da2;        /* [videos][8][64][64] each                                            */
+    size_t dc_part;                              /* [videos][8] gradient of the pseudo-inverse start scale, per head     */
+    size_t zhist;                                /* [videos][8][6][64][64] inputs of the six pinv iterations             */
+    size_t g;                                    /* [rows][4] gradient of the head projections                           */
+    size_t d_logit;                              /* [rows][S]                                                            */
+    size_t das;                                  /* [depth][rows][128] gradient of every Linear output of the fc block   */
+    size_t du0, dyn, dy, dmerged;                /* [rows][128], [rows][1024], [rows][1024], [rows][512]                 */
+    size_t t_a, t_b;                             /* operand-plane scratch of the backward GEMMs                          */
+    size_t total;
+} edsnet_train_layout;
+
+size_t edsnet_train_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos,
+                                    edsnet_train_layout* layout);
+/* Kernel launches of one forward / one backward call (bench bookkeeping). */
+int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* backward);
+
+/* DSNet.forward in train() mode (anchor_based/dsnet.py:100-115 with the Dropout(0.5) of the shared fc block, :91-95,
+ * active when dropout != 0) keeping every activation the backward needs.  The mask is Philox4x32-10 with counter
+ * (row, layer, offset) and key seed: bit c of the 128 output bits keeps hidden column c; edsnet_dropout_mask writes it
+ * out ([depth][rows][128] bytes, 1 = kept) for tests.  Only the fp32 weight pointers of `w` are read. */
+int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
+                         int32_t dropout, uint64_t seed, uint64_t offset, float* pred_cls, float* pred_loc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int edsnet_dropout_mask(uint64_t seed, uint64_t offset, int32_t rows, int32_t depth, uint8_t* out, void* stream);
+
+/* anchor_based/losses.py:5-57 combined as anchor_based/train.py:119-123, per video of the batch:
+ *   cls_label [dev][total_rows][S] int32 (1 positive, -1 negative, 0 ignored), loc_label [dev][total_rows][S][2] fp32.
+ * Outputs: loss_out [dev][n_videos][3] = {cls + lambda_reg * loc, cls, loc}; d_logit [total_rows][S] and d_loc
+ * [total_rows][S][2] = scale * d loss / d (logit before the sigmoid | offset), in closed form (no division by p or
+ * 1 - p).  scale is typically 1 / (videos of the optimiser step). */
+int edsnet_loss_grad(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls, const float* pred_loc,
+                     const int32_t* cls_label, const float* loc_label, float lambda_reg, float scale, float* d_logit,
+                     float* d_loc, float* loss_out, void* stream);
+
+/* loss.backward(): parameter gradients from d loss / d outputs.  d_cls is either the gradient with respect to the
+ * logits (d_cls_is_logit_grad != 0, what edsnet_loss_grad writes) or with respect to pred_cls after the sigmoid (what
+ * torch.autograd hands over); pred_cls = the forward's output; dropout = the forward's flag; workspace = the forward's. */
+int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
+                          const float* pred_cls, const float* d_cls, const float* d_loc, int32_t d_cls_is_logit_grad,
+                          int32_t dropout, const edsnet_grads* grads, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* torch.optim.Adam(lr, betas, eps, weight_decay) (anchor_based/train.py:53-55) on flat fp32 buffers of n values; the
+ * gradient is multiplied by grad_scale first (1 / world size after a summing all-reduce); step counts from 1. */
+int edsnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
+/* fp32 (rows, cols) -> operand planes of the TRANSPOSE: hi [cols][kp] fp16 | lo [cols][kp] fp16 | inverse scales [cols]
+ * fp32, kp = rows rounded up to 64 (zero padded), every output row scaled like edsnet_split_f16 does.  The operand format
+ * of every dW = dY^T X product of the backward.  dst needs edsnet_split_f16_bytes(cols, kp) bytes. */
+int edsnet_split_f16_t(const float* src, int64_t rows, int64_t cols, void* dst, void* stream);
 
 /* ---- stage-level entry points (tests, per-kernel timing, ncu) ---- */
 

@@ -241,18 +241,25 @@ def roi_pool_direct(u: torch.Tensor, scales: Sequence[int]) -> torch.Tensor:
 
 
 def dsnet_forward(x: torch.Tensor, p: Dict[str, torch.Tensor], scales: Sequence[int],
-                  fc_depth: int = 5, heads: int = HEADS, stages: dict | None = None, base: str = "nystromformer"
+                  fc_depth: int = 5, heads: int = HEADS, stages: dict | None = None, base: str = "nystromformer",
+                  keep: torch.Tensor | None = None, dropout_gen: torch.Generator | None = None
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """x: (T, F) float -> pred_cls (T, S), pred_loc (T, S, 2).  Eval mode
-    (Dropout is the identity).  anchor_based/dsnet.py:100-115."""
+    """x: (T, F) float -> pred_cls (T, S), pred_loc (T, S, 2).  anchor_based/dsnet.py:100-115.
+    Eval mode by default (Dropout is the identity).  Train mode (dsnet.py:91-95: Dropout(0.5) after the ReLU of every
+    application of the shared block): pass ``keep`` = bool (fc_depth, T, H) mask of the kept activations (what the CUDA
+    path draws with Philox, so both sides can use the SAME mask) or ``dropout_gen`` to draw one with torch."""
     if base == "attention":
         y = mha_attention(x, p, heads) + x
     else:
         y = nystrom_attention(x, p, heads, stages) + x
     u = layer_norm(y, p["layer_norm.weight"], p["layer_norm.bias"])
     u = u @ p["fc1.weight"].t() + p["fc1.bias"]
-    for _ in range(fc_depth):          # ONE shared block applied fc_depth times (dsnet.py:91-96)
+    for i in range(fc_depth):          # ONE shared block applied fc_depth times (dsnet.py:91-96)
         u = torch.relu(u @ p["fc_block.0.weight"].t() + p["fc_block.0.bias"])
+        if keep is not None:
+            u = u * keep[i].to(u.dtype) * 2.0
+        elif dropout_gen is not None:
+            u = u * (torch.rand(u.shape, generator=dropout_gen) < 0.5).to(u.dtype) * 2.0
         u = layer_norm(u, p["fc_block.3.weight"], p["fc_block.3.bias"])
     pooled = roi_pool_direct(u, scales)
     cls = torch.sigmoid(pooled @ p["fc_cls.0.weight"].t() + p["fc_cls.0.bias"]).reshape(x.shape[0], len(scales))
