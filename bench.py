@@ -472,6 +472,21 @@ def measure_c3(D, scales, videos_per_rank, steps, warmup, precision="fp16x3"):
         ms_no = D.timed(fn, steps)
         stepper.skip_allreduce = False
         t_ar = max(0.0, ms - ms_no) / steps
+    # where the step's time goes: per-stage CUDA events over a few instrumented steps (not part of the timed region)
+    stage_ms = None
+    try:
+        from edsnet_b200 import _capi
+        lib = _capi.lib()
+        _capi.check(lib.edsnet_debug_stage_timing(1))
+        n_inst = 10
+        for _ in range(n_inst):
+            fn()
+        torch.cuda.synchronize(dev)
+        st = _capi.stage_times()
+        _capi.check(lib.edsnet_debug_stage_timing(0))
+        stage_ms = {k: round(v[0] / n_inst, 5) for k, v in st.items() if v[1]}
+    except Exception as e:          # pragma: no cover
+        stage_ms = {"error": repr(e)}
     # forward-only latency of the same videos (inference kernels) for the "step <= 3 x forward" comparison
     model.eval()
     with torch.no_grad():
@@ -485,7 +500,8 @@ def measure_c3(D, scales, videos_per_rank, steps, warmup, precision="fp16x3"):
             "host_label_ms_per_step": label_ms, "loss": loss,
             "allreduce_ms_per_step": t_ar, "allreduce_bytes_per_step": stepper.n_params * 4 if D.world > 1 else 0,
             "forward_only_ms": fwd_ms, "step_over_forward": (ms / steps) / fwd_ms, "mean_rows_per_video": rows,
-            "launches_per_step": stepper.launches_per_step, "n_params": stepper.n_params, "scales": list(scales)}
+            "launches_per_step": stepper.launches_per_step, "n_params": stepper.n_params, "scales": list(scales),
+            "stage_ms_per_step": stage_ms}
 
 
 def cpu_c3(scales, k, budget_s=15.0):

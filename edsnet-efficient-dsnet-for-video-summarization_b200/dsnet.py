@@ -141,6 +141,23 @@ class DSNet(nn.Module):
         self._workspaces = {}
         self._drop_seed = None
         self._drop_offset = 0
+        self._batch_cache = {}
+
+    def _device_batch(self, batch, device) -> DeviceBatch:
+        """Batch tables on the device for a list of video lengths (or a BatchPlan), cached per length tuple: repeated
+        calls on the same videos (a training epoch, a CUDA-graph capture after its warm-up call) neither rebuild nor
+        re-upload them -- and allocate no pinned staging memory, which is illegal under stream capture."""
+        if isinstance(batch, DeviceBatch):
+            return batch
+        plan = batch if isinstance(batch, BatchPlan) else BatchPlan.build(batch)
+        key = (str(device), tuple(int(t) for t in plan.lengths))
+        hit = self._batch_cache.get(key)
+        if hit is None:
+            if len(self._batch_cache) >= 512:
+                self._batch_cache.clear()
+            hit = plan.to(device)
+            self._batch_cache[key] = hit
+        return hit
 
     def _next_dropout_stream(self):
         """(seed, offset) of the next train-mode forward's Philox dropout mask: the seed is torch's initial seed at the
@@ -153,7 +170,7 @@ class DSNet(nn.Module):
     # caches and the lock are per-process state: a pickled / deep-copied model starts without them
     def __getstate__(self):
         st = self.__dict__.copy()
-        st.update(_wcache=None, _wkey=None, _wlock=None, _workspace=None, _workspaces={})
+        st.update(_wcache=None, _wkey=None, _wlock=None, _workspace=None, _workspaces={}, _batch_cache={})
         return st
 
     def __setstate__(self, st):
@@ -297,8 +314,7 @@ class DSNet(nn.Module):
 
     def _forward_nograd(self, x, batch):
         if not isinstance(batch, DeviceBatch):
-            plan = batch if isinstance(batch, BatchPlan) else BatchPlan.build(batch)
-            batch = plan.to(x.device)
+            batch = self._device_batch(batch, x.device)
         if batch.plan.total_rows != x.shape[0]:
             raise RuntimeError(f"batch plan covers {batch.plan.total_rows} rows, x has {x.shape[0]}")
         x = x.detach().contiguous()

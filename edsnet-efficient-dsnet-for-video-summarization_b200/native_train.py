@@ -161,6 +161,33 @@ class _NativeScoring(torch.autograd.Function):
         return (None, None, None, None, None, None) + out
 
 
+class _NativeEvalScoring(torch.autograd.Function):
+    """eval()-mode call with gradients enabled.  The VALUES come from the inference kernels (bit-identical to the same
+    call under torch.no_grad(), whatever `precision` the model runs in); the backward recomputes the training forward
+    without dropout -- the same function -- to get the activations edsnet_train_backward needs."""
+
+    @staticmethod
+    def forward(ctx, model, batch, x, *params):
+        ctx.model, ctx.batch = model, batch
+        ctx.save_for_backward(x)
+        ctx.shapes = [(p.shape, p.requires_grad) for p in params]
+        with torch.no_grad():
+            return model._forward_nograd(x, batch)
+
+    @staticmethod
+    def backward(ctx, g_cls, g_loc):
+        (x,) = ctx.saved_tensors
+        tctx = train_forward(ctx.model, x, ctx.batch, False, 0, 0)
+        dev = x.device
+        grads = {name: torch.zeros(shape, dtype=torch.float32, device=dev)
+                 for name, (shape, _) in zip(_capi.GRAD_FIELDS, ctx.shapes)}
+        g_cls = torch.zeros_like(tctx.pred_cls) if g_cls is None else g_cls
+        g_loc = torch.zeros_like(tctx.pred_loc) if g_loc is None else g_loc
+        train_backward(tctx, g_cls, g_loc, grads, logit_grad=False)
+        out = tuple(grads[name] if req else None for name, (_, req) in zip(_capi.GRAD_FIELDS, ctx.shapes))
+        return (None, None, None) + out
+
+
 def scoring_with_native_grad(model, x: torch.Tensor, batch):
     """The differentiable call behind DSNet.forward / forward_packed: Dropout follows model.training."""
     if x.requires_grad:
@@ -168,6 +195,9 @@ def scoring_with_native_grad(model, x: torch.Tensor, batch):
                            "(the reference's features are data: anchor_based/train.py:113)")
     named = model._named_weights()
     params = [named[k] for k in _capi.GRAD_FIELDS]
+    batch = _as_batch(batch, x.device) if isinstance(batch, DeviceBatch) else model._device_batch(batch, x.device)
+    if not model.training:
+        return _NativeEvalScoring.apply(model, batch, x, *params)
     seed, offset = model._next_dropout_stream()
     p_drop = float(model.fc_block[2].p)
     if p_drop not in (0.0, 0.5):

@@ -11,9 +11,9 @@ What each function restates (reference files relative to /root/reference/src):
                        gradient over W ranks turns its batch-1 SGD into batch-W, which is what config 3 asks for.
   NativeDataParallelStep  (native_train.py) the same step on the training kernels of libedsnet_b200.so: train-mode forward,
                        loss gradient, backward, ONE flat NCCL all-reduce, Adam -- no torch op computes any part of it.
-DataParallelStep / GraphedDataParallelStep drive the model through torch autograd (model(x) in train() mode lands in the
-same kernels via native_train._NativeScoring; the losses and Adam are torch ops there): they are the reference-shaped
-loop, NativeDataParallelStep is the fast path bench.py --config c3 measures.
+DataParallelStep drives the model through torch autograd (model(x) in train() mode lands in the same kernels via
+native_train._NativeScoring; the losses and Adam are torch ops there): it is the reference-shaped loop,
+NativeDataParallelStep is the fast path bench.py --config c3 measures (and replays as CUDA graphs).
 """
 from __future__ import annotations
 
@@ -228,125 +228,3 @@ class DataParallelStep:
         allreduce_gradients(self.params, self.world_size, self.group)
         self.optimizer.step()
         return float(loss.detach())
-
-
-# ----------------------------------------------------------------------------------------------- CUDA-graph step
-def _cls_loss_static(pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
-    """cls_loss with masked sums instead of boolean indexing (same value; shapes do not depend on the labels, so the
-    expression can be captured in a CUDA graph)."""
-    pred, label = pred.reshape(-1), label.reshape(-1)
-    pos, neg = label == 1, label == -1
-    # mask the ARGUMENT of the logarithm, not its result: log(0) of an unselected (or saturated) anchor would otherwise
-    # put 0 * inf = NaN into the gradient of every weight
-    one = torch.ones((), dtype=pred.dtype, device=pred.device)
-    lp = torch.where(pos, pred, one).log().sum() / pos.sum()
-    ln = torch.where(neg, 1 - pred, one).log().sum() / neg.sum()
-    return 0.5 * (-lp - ln)
-
-
-def _loc_loss_static(pred_loc: torch.Tensor, loc_label: torch.Tensor, cls_label: torch.Tensor) -> torch.Tensor:
-    pos = (cls_label == 1).unsqueeze(-1)
-    sl1 = F.smooth_l1_loss(pred_loc, loc_label, reduction="none")
-    return torch.where(pos, sl1, torch.zeros((), dtype=sl1.dtype, device=sl1.device)).sum() / (2 * pos.sum())
-
-
-class GraphedDataParallelStep(DataParallelStep):
-    """DataParallelStep whose forward + loss + backward and whose Adam update are replayed as CUDA graphs, one pair
-    per distinct tuple of video lengths (a dataset has a fixed set of videos, so every graph is reused once per epoch).
-    The eager step is launch bound (about 700 small kernels per video); a replay submits them with two driver calls.
-    All gradients live in ONE flat buffer (`p.grad` are views of it), so the data-parallel reduction between the two
-    graphs is a single in-place all-reduce with no packing copies.  The first time a length tuple is seen the step
-    runs eagerly (lazy library initialisation must not happen under capture); the second time it is captured."""
-
-    def __init__(self, model, lr: float = 5e-5, weight_decay: float = 1e-5, lambda_reg: float = 1.0,
-                 world_size: int = 1, group=None):
-        super().__init__(model, lr, weight_decay, lambda_reg, world_size, group)
-        seen, uniq = set(), []
-        for p in self.params:
-            if id(p) not in seen:
-                seen.add(id(p))
-                uniq.append(p)
-        self.params = uniq
-        dev = uniq[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("GraphedDataParallelStep needs the model on a CUDA device")
-        self.flat_grad = torch.zeros(sum(p.numel() for p in uniq), dtype=torch.float32, device=dev)
-        o = 0
-        for p in uniq:
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-            o += p.numel()
-        self.optimizer = torch.optim.Adam(uniq, lr=lr, weight_decay=weight_decay, capturable=True, foreach=True)
-        self._graphs = {}
-        self._seen = set()
-        self._opt_graph = None
-        self._stream = torch.cuda.Stream(dev)
-
-    def _static_loss(self, x, lengths, cls_l, loc_l):
-        pred_cls, pred_loc = self.model.forward_packed(x, lengths)
-        total, o = 0.0, 0
-        for t, cl, ll in zip(lengths, cls_l, loc_l):
-            total = total + _cls_loss_static(pred_cls[o:o + t], cl) + \
-                self.lambda_reg * _loc_loss_static(pred_loc[o:o + t], ll, cl)
-            o += t
-        return total / len(lengths)
-
-    def _reduce(self):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat_grad /= self.world_size
-
-    def _eager(self, seqs, cls_labels, loc_labels):
-        self.flat_grad.zero_()
-        lengths = [int(s.shape[0]) for s in seqs]
-        loss = self._static_loss(torch.cat(seqs), lengths, cls_labels, loc_labels)
-        loss.backward()
-        self._reduce()
-        self.optimizer.step()
-        return loss.detach()
-
-    def step(self, seqs, cls_labels, loc_labels) -> float:
-        self.model.train()
-        key = tuple(int(s.shape[0]) for s in seqs)
-        if key not in self._graphs:
-            if key not in self._seen:
-                self._seen.add(key)
-                return float(self._eager(seqs, cls_labels, loc_labels))
-            self._graphs[key] = self._capture(key, seqs, cls_labels, loc_labels)
-        g, x_s, cls_s, loc_s, loss_s = self._graphs[key]
-        x_s.copy_(torch.cat(seqs))
-        for d, s in zip(cls_s, cls_labels):
-            d.copy_(s)
-        for d, s in zip(loc_s, loc_labels):
-            d.copy_(s)
-        g.replay()
-        self._reduce()
-        if self._opt_graph is None:
-            self._opt_graph = torch.cuda.CUDAGraph()
-            cur = torch.cuda.current_stream()
-            self._stream.wait_stream(cur)
-            with torch.cuda.stream(self._stream):
-                with torch.cuda.graph(self._opt_graph, stream=self._stream):
-                    self.optimizer.step()
-            cur.wait_stream(self._stream)
-        self._opt_graph.replay()
-        if hasattr(self.model, "invalidate_weight_cache"):
-            self.model.invalidate_weight_cache()      # a replay changes the weights without bumping their versions
-        return float(loss_s)
-
-    def _capture(self, key, seqs, cls_labels, loc_labels):
-        lengths = list(key)
-        x_s = torch.cat(seqs).clone()
-        cls_s = [c.clone() for c in cls_labels]
-        loc_s = [l.clone() for l in loc_labels]
-        g = torch.cuda.CUDAGraph()
-        cur = torch.cuda.current_stream()
-        self._stream.wait_stream(cur)
-        with torch.cuda.stream(self._stream):
-            with torch.cuda.graph(g, stream=self._stream):
-                self.flat_grad.zero_()
-                loss = self._static_loss(x_s, lengths, cls_s, loc_s)
-                loss.backward()
-                loss_s = loss.detach()
-        cur.wait_stream(self._stream)
-        return g, x_s, cls_s, loc_s, loss_s

@@ -496,12 +496,12 @@ def test_fc_stack_stage(precision, rows, depth):
 
 
 def test_training_step_single_gpu():
-    """Config-3 step on one GPU (world_size 1): labels from a synthetic keyshot mask, train()-mode forward with
-    Dropout, cls + loc loss, backward, flat-bucket gradient reduction, Adam.  The loss must go down."""
+    """Config-3 step on one GPU (world_size 1) through the reference-shaped loop (DataParallelStep: model(x) in train()
+    mode, torch losses, loss.backward() into the backward kernels, flat-bucket reduction, torch Adam): labels from a
+    synthetic keyshot mask.  With Dropout switched off the loss must go down step after step; with the reference's
+    Dropout(0.5) the steps stay finite and the updated weights reach the inference kernels."""
     from edsnet_b200 import training as tr
-    p = orc.synth_params(51, "xavier")
     scales = [4, 8, 16, 32]
-    model = make_model(p, scales, 5, "fp16x3", DEV)
     rng = np.random.default_rng(3)
     seqs, cls_l, loc_l = [], [], []
     for i, T in enumerate((120, 200)):
@@ -512,53 +512,21 @@ def test_training_step_single_gpu():
         seqs.append(orc.synth_features(T, 900 + i).to(DEV))
         cls_l.append(torch.from_numpy(c).to(DEV))
         loc_l.append(torch.from_numpy(l).float().to(DEV))
-    stepper = tr.DataParallelStep(model, lr=1e-3, world_size=1)
-    torch.manual_seed(0)
-    losses = [stepper.step(seqs, cls_l, loc_l) for _ in range(12)]
-    print(losses)
-    assert all(np.isfinite(losses)) and np.mean(losses[-3:]) < np.mean(losses[:3])
-    # the updated weights flow back into the kernel path (weight cache keyed on parameter versions)
-    model.eval()
-    with torch.no_grad():
-        c1, _ = model(seqs[0][None])
-    assert torch.isfinite(c1).all()
-
-
-def test_graphed_training_step_matches_eager():
-    """CUDA-graph replay of the config-3 step (forward + loss + backward graph, flat gradient buffer, capturable Adam)
-    against the eager step: same loss trajectory with Dropout switched off; the updated weights reach the kernel path."""
-    from edsnet_b200 import training as tr
-    scales = [4, 8]
-    rng = np.random.default_rng(9)
-    data = []
-    for i, T in enumerate((96, 150)):
-        mask = np.zeros(T, bool)
-        mask[10:17] = True
-        mask[60:65] = True
-        c, l = tr.anchor_labels(mask, scales, rng)
-        assert (c == 1).any() and (c == -1).any()
-        data.append((orc.synth_features(T, 1200 + i).to(DEV), torch.from_numpy(c).to(DEV),
-                     torch.from_numpy(l).float().to(DEV)))
-    traj = {}
-    for kind in ("eager", "graph"):
-        model = make_model(orc.synth_params(77, "xavier"), scales, 5, "fp16x3", DEV)
-        for m in model.modules():
-            if isinstance(m, torch.nn.Dropout):
-                m.p = 0.0
-        st = (tr.DataParallelStep if kind == "eager" else tr.GraphedDataParallelStep)(model, lr=1e-3, world_size=1)
-        losses = []
-        for it in range(8):                      # every video: eager, capture + replay, replay, replay
-            x, c, l = data[it % 2]
-            losses.append(st.step([x], [c], [l]))
+    for p_drop in (0.0, 0.5):
+        model = make_model(orc.synth_params(51, "xavier"), scales, 5, "fp16x3", DEV)
+        model.fc_block[2].p = p_drop
+        stepper = tr.DataParallelStep(model, lr=2e-4, world_size=1)
+        torch.manual_seed(0)
+        losses = [stepper.step(seqs, cls_l, loc_l) for _ in range(12)]
+        print(p_drop, losses)
+        assert all(np.isfinite(losses))
+        if p_drop == 0.0:
+            assert np.mean(losses[-3:]) < np.mean(losses[:3]) and losses[-1] < losses[0]
+        # the updated weights flow back into the kernel path (weight cache keyed on parameter versions)
         model.eval()
         with torch.no_grad():
-            out = model(data[0][0][None])[0].cpu().numpy()
-        traj[kind] = (np.asarray(losses), out)
-    le, lg = traj["eager"][0], traj["graph"][0]
-    print(le, lg)
-    assert np.all(np.isfinite(lg)) and np.allclose(le, lg, rtol=2e-3, atol=1e-4), (le, lg)
-    assert lg[-1] < lg[0]
-    assert orc.rel_l2(traj["graph"][1], traj["eager"][1]) < 2e-2          # same weights after 8 steps (fp32 reorderings)
+            c1, _ = model(seqs[0][None])
+        assert torch.isfinite(c1).all()
 
 
 # ------------------------------------------------------------------------------------------------ config 4: full MHA base
