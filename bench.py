@@ -454,16 +454,24 @@ def measure_c3(D, scales, videos_per_rank, steps, warmup, precision="fp16x3"):
         host_s[0] += time.perf_counter() - t0
         return stepper.step([feats[s] for s in sel], [c for c, _ in labs], [l for _, l in labs])
 
-    for i in range(warmup):
+    # every video of the split twice before timing: the second sighting of a length tuple captures its CUDA graph
+    n_warm = max(warmup, 2 * ((len(vids) + k - 1) // k))
+    for i in range(n_warm):
         one_step(i)
-    it = [warmup]
+    it = [n_warm]
 
     def fn():
         one_step(it[0])
         it[0] += 1
+
+    def fn_readback():                     # e2e: labels H2D and the loss back on the host every step
+        loss_dev = one_step(it[0])
+        it[0] += 1
+        return float(loss_dev[:, 0].mean())
     host_s[0] = 0.0
     ms = D.timed(fn, steps)
     label_ms = 1e3 * host_s[0] / steps
+    ms_e2e = D.timed(fn_readback, steps)
     loss = stepper.last_loss()
     # share of the collective: the same steps with the all-reduce skipped (gradients stay local)
     t_ar = None
@@ -495,8 +503,10 @@ def measure_c3(D, scales, videos_per_rank, steps, warmup, precision="fp16x3"):
         db = BatchPlan.build([vids[s][0] for s in sel]).to(dev)
         fwd_ms = median_ms(lambda: model._forward_nograd(xx, db))
     model.train()
-    rows = float(np.mean([vids[j % len(vids)][0] for j in range(warmup * k, (warmup + steps) * k)]))
+    rows = float(np.mean([vids[j % len(vids)][0] for j in range(n_warm * k, (n_warm + steps) * k)]))
     return {"ms_per_step": ms / steps, "videos_per_sec": D.world * k * steps / (ms * 1e-3), "videos_per_rank_per_step": k,
+            "e2e_ms_per_step": ms_e2e / steps, "e2e_videos_per_sec": D.world * k * steps / (ms_e2e * 1e-3),
+            "cuda_graph_replays": stepper.graph_replays,
             "host_label_ms_per_step": label_ms, "loss": loss,
             "allreduce_ms_per_step": t_ar, "allreduce_bytes_per_step": stepper.n_params * 4 if D.world > 1 else 0,
             "forward_only_ms": fwd_ms, "step_over_forward": (ms / steps) / fwd_ms, "mean_rows_per_video": rows,
@@ -579,9 +589,10 @@ def bench_c3(args, D):
                          "l2": "one video per step fits L2 (latency-bound step by nature of the config)", **res},
               # the features of the training split live on the device (as the reference keeps them after .to(device));
               # per step the host sends the labels and reads the loss back
-              "e2e": {"value": res["videos_per_sec"], "unit": "videos/s", "ms_per_step": res["ms_per_step"],
-                      "h2d_bytes_per_step": int(D.world * k * T * len(scales) * 9), "d2h_bytes_per_step": 4 * D.world,
-                      "note": "labels H2D and the loss read-back are inside the timed step; features are resident"},
+              "e2e": {"value": res["e2e_videos_per_sec"], "unit": "videos/s", "ms_per_step": res["e2e_ms_per_step"],
+                      "h2d_bytes_per_step": int(D.world * k * T * len(scales) * 12), "d2h_bytes_per_step": 4 * D.world,
+                      "note": "every step uploads its labels from pinned host memory and reads its loss back; the features "
+                              "of the training split are resident (the reference keeps them on the device as well)"},
               "gpu_launches": res["launches_per_step"] * steps,
               "roofline": {"kernel": "whole training step (launch / latency bound at one video per GPU)", "bound": "tensor",
                            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,

@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 8
+EDSNET_ABI_VERSION = 10
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -61,7 +61,7 @@ class Grads(C.Structure):
 
 TRAIN_LAYOUT_FIELDS = ("w_qkv16", "w_out16", "w_fc116", "w_fcb16", "qkv16", "qkv_inv", "q_land", "k_land", "attn2", "stats",
                        "a3v", "zmat", "wmat", "merged", "y", "yn", "uin", "hs", "u_last", "heads", "qkv_f32", "dqkv", "m3",
-                       "l3", "acc0", "acc_bytes", "dw_att", "dkl", "dql", "db_att", "da2", "dc_part", "zhist", "g", "d_logit",
+                       "l3", "acc0", "acc_bytes", "dw_att", "dkl", "dql", "db_att", "da2", "cmax", "dc_part", "zhist", "g", "d_logit",
                        "das", "du0", "dyn", "dy", "dmerged", "t_a", "t_b", "total")
 
 
@@ -105,7 +105,7 @@ SYMBOLS = {
     "edsnet_train_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int32, C.c_int32, C.POINTER(TrainLayout)]),
     "edsnet_train_launches": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "edsnet_train_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, C.c_int32, C.c_uint64,
-                                       C.c_uint64, _P, _P, _P, C.c_size_t, _P]),
+                                       C.c_uint64, _P, _P, _P, _P, C.c_size_t, _P]),
     "edsnet_dropout_mask": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, _P, _P]),
     "edsnet_loss_grad": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P,
                                    _P]),

@@ -745,6 +745,9 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
 // =====================================================================================================================
 namespace {
 
+// column-maximum slots of all transposed splits of one backward: 2 x 128 + 128 + 1024 + 1024 + 1024 + 512 + 512 + 1536 + 1024
+constexpr int kCmaxSlots = 8192;
+
 size_t round64(size_t x) { return (x + 63) & ~(size_t)63; }
 size_t planes_bytes(size_t rows, size_t cols) { return rows * cols * 4 + rows * 4; }
 
@@ -783,15 +786,16 @@ void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos
     L.dqkv = take(R * kQkvCols * sizeof(float));
     L.m3 = take(V * kHeads * 64 * sizeof(float));
     L.l3 = take(V * kHeads * 64 * sizeof(float));
-    L.acc0 = off;                                    // dW | dkl | dql: zeroed by one memset at the start of the backward
+    L.acc0 = off;                                    // dW | dkl | dql | column maxima: zeroed by one memset at the start of the backward
     L.dw_att = take(head_mat);
     L.dkl = take(head_mat);
     L.dql = take(head_mat);
+    L.cmax = take(kCmaxSlots * sizeof(unsigned));
     L.acc_bytes = off - L.acc0;
     L.db_att = take(head_mat);
     L.da2 = take(head_mat);
     L.dc_part = take(V * kHeads * sizeof(float));
-    L.zhist = take(head_mat * kPinvIters);
+    L.zhist = take(head_mat * kPinvIters * 4);
     L.g = take(R * 4 * sizeof(float));
     L.d_logit = take(R * S * sizeof(float));
     L.das = take(std::max<size_t>(D, 1) * R * kHidden * sizeof(float));
@@ -807,9 +811,11 @@ void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos
     *out = L;
 }
 
-SplitTJob split_t_job(const float* src, int rows, int cols, int ld, void* planes, int* cta) {
+SplitTJob split_t_job(const float* src, int rows, int cols, int ld, void* planes, int* cta, unsigned** cmax) {
     SplitTJob j;
     j.src = src;
+    j.cmax = *cmax;
+    *cmax += cols;
     j.rows = rows;
     j.cols = cols;
     j.ld = ld;
@@ -826,9 +832,16 @@ int launch_split_t(const SplitTJob* jobs, int n, int ctas, cudaStream_t st) {
     StageScope scope(ST_T_SPLIT, st);
     SplitTJobs js;
     js.n = n;
-    for (int i = 0; i < 4; ++i) js.j[i] = jobs[i < n ? i : 0];
-    split_t_kernel<<<ctas, 256, 0, st>>>(js);
-    CU_CHECK(cudaGetLastError(), "split_t_kernel");
+    int max_rows = 1, max_kp = 64;
+    for (int i = 0; i < 4; ++i) {
+        js.j[i] = jobs[i < n ? i : 0];
+        max_rows = std::max(max_rows, js.j[i].rows);
+        max_kp = std::max(max_kp, js.j[i].kp);
+    }
+    split_t_colmax_kernel<<<dim3(ctas, (max_rows + 255) / 256), 256, 0, st>>>(js);
+    CU_CHECK(cudaGetLastError(), "split_t_colmax_kernel");
+    split_t_tiles_kernel<<<dim3(ctas, max_kp / 64), 256, 0, st>>>(js);
+    CU_CHECK(cudaGetLastError(), "split_t_tiles_kernel");
     return EDSNET_OK;
 }
 
@@ -856,7 +869,7 @@ size_t edsnet_train_workspace_bytes(const edsnet_config* cfg, int32_t total_rows
 int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* backward) {
     if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
     if (forward) *forward = 4 + 1 + 1 + 6 + 1 + 1 + 1 + 1 + 1 + 1 + 1;       // weight planes, split, qkv, core, ..., roi
-    if (backward) *backward = 27;
+    if (backward) *backward = 36;
     return EDSNET_OK;
 }
 
@@ -870,14 +883,18 @@ int edsnet_dropout_mask(uint64_t seed, uint64_t offset, int32_t rows, int32_t de
 int edsnet_split_f16_t(const float* src, int64_t rows, int64_t cols, void* dst, void* stream) {
     if (!src || !dst || rows < 1 || cols < 1 || rows > (1 << 30) || cols > (1 << 24))
         return fail(EDSNET_E_ARG, "split_f16_t: bad argument");
+    // the column maxima are gathered in the cols x 4 scratch bytes behind the planes
+    const size_t kp = round64((size_t)rows);
+    unsigned* cm = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dst) + planes_bytes((size_t)cols, kp));
+    CU_CHECK(cudaMemsetAsync(cm, 0, (size_t)cols * sizeof(unsigned), static_cast<cudaStream_t>(stream)), "split_f16_t scratch");
     int cta = 0;
-    SplitTJob j = split_t_job(src, (int)rows, (int)cols, (int)cols, dst, &cta);
+    SplitTJob j = split_t_job(src, (int)rows, (int)cols, (int)cols, dst, &cta, &cm);
     return launch_split_t(&j, 1, cta, static_cast<cudaStream_t>(stream));
 }
 
 int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
-                         int32_t dropout, uint64_t seed, uint64_t offset, float* pred_cls, float* pred_loc,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         int32_t dropout, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* pred_cls,
+                         float* pred_loc, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_train_cfg(cfg);
     if (rc) return rc;
     rc = check_batch(batch);
@@ -932,7 +949,8 @@ int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, cons
         StageScope scope(ST_FC_STACK, st);
         CU_CHECK(launch_fc_stack_tc(F(L.uin), ws + L.w_fcb16, w->fcb_b, w->fcb_ln_w, w->fcb_ln_b, F(L.u_last), R,
                                     cfg->fc_depth, st, w->cls_w, w->loc_w, F(L.heads), F(L.hs), dropout ? 1 : 0, seed,
-                                    offset), "fc_stack_tc_kernel<train>");
+                                    offset, reinterpret_cast<const unsigned long long*>(offset_dev)),
+                 "fc_stack_tc_kernel<train>");
     }
     return roi_impl(cfg, w, batch, F(L.heads), pred_cls, pred_loc, st, true);
 }
@@ -1015,10 +1033,11 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     }
     SplitTJob jobs[4];
     int cta;
+    unsigned* cm = reinterpret_cast<unsigned*>(ws + L.cmax);
     // 4. d fc_block.0.weight = sum_l da_l^T u_l  (one product with K = D x rows)
     cta = 0;
-    jobs[0] = split_t_job(F(L.das), D * R, kHidden, kHidden, ws + L.t_a, &cta);
-    jobs[1] = split_t_job(F(L.uin), D * R, kHidden, kHidden, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(F(L.das), D * R, kHidden, kHidden, ws + L.t_a, &cta, &cm);
+    jobs[1] = split_t_job(F(L.uin), D * R, kHidden, kHidden, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 2, cta, st);
     if (rc) return rc;
     rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fcb_w, kHidden, kHidden, K5, nullptr,
@@ -1026,8 +1045,8 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     if (rc) return rc;
     // 5. d fc1.weight = du0^T LN(y)
     cta = 0;
-    jobs[0] = split_t_job(F(L.du0), R, kHidden, kHidden, ws + L.t_a, &cta);
-    jobs[1] = split_t_job(F(L.yn), R, kFeat, kFeat, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(F(L.du0), R, kHidden, kHidden, ws + L.t_a, &cta, &cm);
+    jobs[1] = split_t_job(F(L.yn), R, kFeat, kFeat, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 2, cta, st);
     if (rc) return rc;
     rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fc1_w, kHidden, kFeat, Rp, nullptr,
@@ -1039,7 +1058,7 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
         CU_CHECK(launch_split_f16(F(L.du0), ws + L.t_a, R, kHidden, st), "split du0");
     }
     cta = 0;
-    jobs[0] = split_t_job(w->fc1_w, kHidden, kFeat, kFeat, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(w->fc1_w, kHidden, kFeat, kFeat, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 1, cta, st);
     if (rc) return rc;
     rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, F(L.dyn), R, kFeat, kHidden, nullptr, nullptr,
@@ -1054,8 +1073,8 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     }
     // 8. d to_out.weight = dy^T merged
     cta = 0;
-    jobs[0] = split_t_job(F(L.dy), R, kFeat, kFeat, ws + L.t_a, &cta);
-    jobs[1] = split_t_job(F(L.merged), R, kInner, kInner, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(F(L.dy), R, kFeat, kFeat, ws + L.t_a, &cta, &cm);
+    jobs[1] = split_t_job(F(L.merged), R, kInner, kInner, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 2, cta, st);
     if (rc) return rc;
     rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_out_w, kFeat, kInner, Rp, nullptr,
@@ -1067,7 +1086,7 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
         CU_CHECK(launch_split_f16(F(L.dy), ws + L.t_a, R, kFeat, st), "split dy");
     }
     cta = 0;
-    jobs[0] = split_t_job(w->to_out_w, kFeat, kInner, kInner, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(w->to_out_w, kFeat, kInner, kInner, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 1, cta, st);
     if (rc) return rc;
     rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, F(L.dmerged), R, kInner, kFeat, nullptr,
@@ -1092,7 +1111,7 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     }
     {
         StageScope scope(ST_T_PINV_BWD, st);
-        pinv_bwd_kernel<<<dim3(kHeads, V), 256, kPinvBwdSmem, st>>>(F(L.attn2), F(L.stats), F(L.a3v), F(L.dw_att), F(L.zhist),
+        pinv_bwd_kernel<<<dim3(kHeads, V), kPinvBwdThreads, kPinvBwdSmem, st>>>(F(L.attn2), F(L.stats), F(L.a3v), F(L.dw_att), F(L.zhist),
                                                                    F(L.db_att), F(L.da2), F(L.dc_part), kPinvIters);
         CU_CHECK(cudaGetLastError(), "pinv_bwd_kernel");
     }
@@ -1110,13 +1129,13 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     }
     {
         StageScope scope(ST_T_FINISH, st);
-        dqkv_finish_kernel<<<batch->n_tiles64, 256, 0, st>>>(batch->cu_rows, t64, F(L.dql), F(L.dkl), F(L.dqkv));
+        dqkv_finish_kernel<<<dim3(batch->n_tiles64, kFinishSplit), 256, 0, st>>>(batch->cu_rows, t64, F(L.dql), F(L.dkl), F(L.dqkv));
         CU_CHECK(cudaGetLastError(), "dqkv_finish_kernel");
     }
     // 11. d to_qkv.weight = dqkv^T x
     cta = 0;
-    jobs[0] = split_t_job(F(L.dqkv), R, kQkvCols, kQkvCols, ws + L.t_a, &cta);
-    jobs[1] = split_t_job(x, R, kFeat, kFeat, ws + L.t_b, &cta);
+    jobs[0] = split_t_job(F(L.dqkv), R, kQkvCols, kQkvCols, ws + L.t_a, &cta, &cm);
+    jobs[1] = split_t_job(x, R, kFeat, kFeat, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 2, cta, st);
     if (rc) return rc;
     return gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_qkv_w, kQkvCols, kFeat, Rp, nullptr,

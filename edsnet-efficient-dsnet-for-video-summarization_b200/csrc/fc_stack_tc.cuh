@@ -49,7 +49,9 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ u_out, int rows, int depth, const float* __restrict__ w_cls,
                    const float* __restrict__ w_loc, float4* __restrict__ heads_out, float* __restrict__ h_save, int drop,
-                   unsigned long long seed, unsigned long long offset) {
+                   unsigned long long seed, unsigned long long offset,
+                   const unsigned long long* __restrict__ offset_dev) {
+    // offset_dev (optional, device memory): added to `offset` -- lets a captured CUDA graph draw a fresh mask per replay
     // heads_out != nullptr: the three head projections of every output row (u . w_cls, u . w_loc[0], u . w_loc[1]; the
     // ROI pooling and the heads are linear, so the pooling windows then run over these 3 channels) are emitted, 16 bytes
     // per row; u_out may then be nullptr and the 512-byte rows are never written.
@@ -182,7 +184,7 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
             uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;          // keep bits of this thread's 64 columns
             float keep_mul = 1.f;
             if (SAVE && drop) {
-                const uint4 dw = dropout_words(seed, offset, row, layer);
+                const uint4 dw = dropout_words(seed, offset + (offset_dev != nullptr ? __ldg(offset_dev) : 0ull), row, layer);
                 kw0 = half ? dw.z : dw.x;
                 kw1 = half ? dw.w : dw.y;
                 keep_mul = 2.f;
@@ -255,7 +257,8 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
                                       const float* beta, float* u_out, int rows, int depth, cudaStream_t st,
                                       const float* w_cls = nullptr, const float* w_loc = nullptr,
                                       float* heads_out = nullptr, float* h_save = nullptr, int drop = 0,
-                                      unsigned long long seed = 0, unsigned long long offset = 0) {
+                                      unsigned long long seed = 0, unsigned long long offset = 0,
+                                      const unsigned long long* offset_dev = nullptr) {
     static const char tag = 0;
     if (DeviceOnce once_{&tag}) {
         cudaError_t e = cudaFuncSetAttribute(tc::fc_stack_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -270,10 +273,10 @@ static cudaError_t launch_fc_stack_tc(const float* u_in, const void* w_planes, c
     if (h_save != nullptr)
         tc::fc_stack_tc_kernel<true><<<grid, 512, tc::kFcSmemBytes, st>>>(
             u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
-            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), h_save, drop, seed, offset);
+            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), h_save, drop, seed, offset, offset_dev);
     else
         tc::fc_stack_tc_kernel<false><<<grid, 512, tc::kFcSmemBytes, st>>>(
             u_in, static_cast<const __half*>(w_planes), split_scales(w_planes, 128, 128), bias, gamma, beta, u_out, rows,
-            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), nullptr, 0, 0ull, 0ull);
+            depth, w_cls, w_loc, reinterpret_cast<float4*>(heads_out), nullptr, 0, 0ull, 0ull, nullptr);
     return cudaGetLastError();
 }

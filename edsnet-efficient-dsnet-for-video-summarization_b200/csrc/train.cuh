@@ -47,18 +47,42 @@ enum MmMode : int { MM_NN = 0, MM_TN = 1, MM_NT = 2 };
 template <int MODE>
 __device__ __forceinline__ int mm_col(int tx, int j) { return MODE == MM_NT ? tx + 16 * j : tx * 4 + j; }
 
-template <int MODE>
-__device__ __forceinline__ void mm64(float (&acc)[4][4], const float* __restrict__ A, const float* __restrict__ B,
+// RT = rows per thread: 4 (256 threads, ty = tid >> 4 in 0..15) or 2 (512 threads, ty in 0..31); thread owns rows ty*RT+i
+template <int MODE, int RT = 4>
+__device__ __forceinline__ void mm64(float (&acc)[RT][4], const float* __restrict__ A, const float* __restrict__ B,
                                      int ty, int tx) {
     if (MODE == MM_NN) {
-        mm64_acc(acc, A, B, ty, tx);
+#pragma unroll 4
+        for (int k4 = 0; k4 < 64; k4 += 4) {
+            float4 a[RT], b[4];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) a[i] = lds4(A + (ty * RT + i) * kLd64 + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) b[kk] = lds4(B + (k4 + kk) * kLd64 + tx * 4);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]); acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
+                    acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]); acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+                }
+            }
+        }
     } else if (MODE == MM_TN) {
 #pragma unroll 8
         for (int k = 0; k < 64; ++k) {
-            const float4 a = lds4(A + k * kLd64 + ty * 4), b = lds4(B + k * kLd64 + tx * 4);
-            const float av[4] = {a.x, a.y, a.z, a.w};
+            float av[RT];
+            if (RT == 4) {
+                const float4 a = lds4(A + k * kLd64 + ty * 4);
+                av[0] = a.x; av[1] = a.y; av[RT - 2] = a.z; av[RT - 1] = a.w;
+            } else {
+                const float2 a = *reinterpret_cast<const float2*>(A + k * kLd64 + ty * 2);
+                av[0] = a.x; av[1] = a.y;
+            }
+            const float4 b = lds4(B + k * kLd64 + tx * 4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RT; ++i) {
                 acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
                 acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
             }
@@ -66,26 +90,33 @@ __device__ __forceinline__ void mm64(float (&acc)[4][4], const float* __restrict
     } else {
 #pragma unroll 4
         for (int k4 = 0; k4 < 64; k4 += 4) {
-            float4 a[4], b[4];
+            float4 a[RT], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = lds4(A + (ty * 4 + i) * kLd64 + k4);
+            for (int i = 0; i < RT; ++i) a[i] = lds4(A + (ty * RT + i) * kLd64 + k4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = lds4(B + (tx + 16 * j) * kLd64 + k4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < RT; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     acc[i][j] = fmaf(a[i].x, b[j].x, fmaf(a[i].y, b[j].y, fmaf(a[i].z, b[j].z, fmaf(a[i].w, b[j].w, acc[i][j]))));
         }
     }
 }
+template <int RT>
+__device__ __forceinline__ void zero_acc(float (&acc)[RT][4]) {
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
 // C = alpha * acc + beta * C (+ diag on the diagonal), in the ownership of MODE
-template <int MODE>
-__device__ __forceinline__ void mm64_store(float* __restrict__ C, const float (&acc)[4][4], float alpha, float beta,
+template <int MODE, int RT = 4>
+__device__ __forceinline__ void mm64_store(float* __restrict__ C, const float (&acc)[RT][4], float alpha, float beta,
                                            float diag, int ty, int tx) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = ty * 4 + i;
+    for (int i = 0; i < RT; ++i) {
+        const int r = ty * RT + i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = mm_col<MODE>(tx, j);
@@ -97,13 +128,20 @@ __device__ __forceinline__ void mm64_store(float* __restrict__ C, const float (&
     }
 }
 // C = alpha * op(A, B) + beta * C + diag I; the caller places the barriers
-template <int MODE>
+template <int MODE, int RT = 4>
 __device__ __forceinline__ void mm64_to(float* __restrict__ C, const float* __restrict__ A, const float* __restrict__ B,
                                         float alpha, float beta, float diag, int ty, int tx) {
-    float acc[4][4];
-    zero44(acc);
-    mm64<MODE>(acc, A, B, ty, tx);
-    mm64_store<MODE>(C, acc, alpha, beta, diag, ty, tx);
+    float acc[RT][4];
+    zero_acc<RT>(acc);
+    mm64<MODE, RT>(acc, A, B, ty, tx);
+    mm64_store<MODE, RT>(C, acc, alpha, beta, diag, ty, tx);
+}
+// dense 64 x 64 fp32 matrix in global memory <-> smem tile, any block size
+__device__ __forceinline__ void tile_load(float* __restrict__ S, const float* __restrict__ G, int tid, int nthr) {
+    for (int idx = tid; idx < 1024; idx += nthr) st4(S + (idx >> 4) * kLd64 + (idx & 15) * 4, ldg4(G + idx * 4));
+}
+__device__ __forceinline__ void tile_store(float* __restrict__ G, const float* __restrict__ S, int tid, int nthr) {
+    for (int idx = tid; idx < 1024; idx += nthr) st4(G + idx * 4, lds4(S + (idx >> 4) * kLd64 + (idx & 15) * 4));
 }
 // 64 x 64 global tile (row stride ld_g, rows >= n_valid read as zero) -> smem
 __device__ __forceinline__ void load64_rows(float* __restrict__ S, const float* __restrict__ G, int ld_g, int n_valid, int tid) {
@@ -125,69 +163,84 @@ __device__ __forceinline__ void atomic_add64(float* __restrict__ G, const float*
 // split_t: fp32 src [rows][cols] (row stride ld) -> planes of the TRANSPOSE, hi [cols][kp] | lo [cols][kp] fp16 and
 // inv [cols] fp32 (kp = rows rounded up to 64, the padding is zero; layout of edsnet_split_f16 with rows <-> cols): every
 // output row (= source column) is scaled by a power of two that puts its largest magnitude into [2^14, 2^15).
-// Up to four independent jobs per launch; one CTA per 32 source columns.
+// Up to four independent jobs per launch, two passes (column maxima, then 32-column x 64-row tiles), both spread over the
+// whole GPU whatever the shape (a [rows][128] operand has only four column blocks).
 // ---------------------------------------------------------------------------------------------------------
 struct SplitTJob {
     const float* src;
     __half* hi;
     __half* lo;
     float* inv;
+    unsigned* cmax;                // [cols] bit patterns of max|column| (non-negative floats order like unsigned), ZERO on entry
     int rows, cols, ld, kp;
-    int cta0;                      // first CTA of this job
+    int cta0;                      // first column block (32 columns) of this job in the launch
 };
 struct SplitTJobs { int n; SplitTJob j[4]; };
 
-__global__ void __launch_bounds__(256)
-split_t_kernel(const SplitTJobs jobs) {
-    __shared__ float tile[32][65];
-    __shared__ float cmax[8][32];
-    __shared__ float csc[32];
+__device__ __forceinline__ const SplitTJob& split_t_pick(const SplitTJobs& jobs, int block) {
     int ji = 0;
 #pragma unroll
     for (int q = 1; q < 4; ++q)
-        if (q < jobs.n && (int)blockIdx.x >= jobs.j[q].cta0) ji = q;
-    const SplitTJob& jb = jobs.j[ji];
+        if (q < jobs.n && block >= jobs.j[q].cta0) ji = q;
+    return jobs.j[ji];
+}
+
+// pass 1: column maxima.  grid (column blocks of all jobs, row chunks of 256), 256 threads.
+__global__ void __launch_bounds__(256)
+split_t_colmax_kernel(const SplitTJobs jobs) {
+    __shared__ float cmax[8][32];
+    const SplitTJob& jb = split_t_pick(jobs, (int)blockIdx.x);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = ((int)blockIdx.x - jb.cta0) * 32;
-    const int c = c0 + lane;
-    const bool cin = c < jb.cols;
+    const int c = ((int)blockIdx.x - jb.cta0) * 32 + lane;
+    const int r0 = (int)blockIdx.y * 256, r1 = min(jb.rows, r0 + 256);
+    if (r0 >= jb.rows) return;
     float mx = 0.f;
-    if (cin)
-        for (int r = warp; r < jb.rows; r += 8) mx = fmaxf(mx, fabsf(__ldg(jb.src + (size_t)r * jb.ld + c)));
+    if (c < jb.cols)
+        for (int r = r0 + warp; r < r1; r += 8) mx = fmaxf(mx, fabsf(__ldg(jb.src + (size_t)r * jb.ld + c)));
     cmax[warp][lane] = mx;
     __syncthreads();
-    if (tid < 32) {
+    if (tid < 32 && c < jb.cols) {
         float m = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) m = fmaxf(m, cmax[w][lane]);
-        const int e = tc::scale_exp(m);
-        csc[lane] = ldexpf(1.f, e);
-        if (cin) jb.inv[c] = ldexpf(1.f, -e);
+        if (m > 0.f && m < INFINITY) atomicMax(jb.cmax + c, __float_as_uint(m));
+    }
+}
+
+// pass 2: one CTA per (32 source columns, 64 source rows): scale, transpose through shared memory, write both planes.
+// grid (column blocks of all jobs, largest kp / 64), 256 threads.
+__global__ void __launch_bounds__(256)
+split_t_tiles_kernel(const SplitTJobs jobs) {
+    __shared__ float tile[32][65];
+    const SplitTJob& jb = split_t_pick(jobs, (int)blockIdx.x);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = ((int)blockIdx.x - jb.cta0) * 32;
+    const int c = c0 + lane;
+    const int k0 = (int)blockIdx.y * 64;
+    if (k0 >= jb.kp) return;
+    const bool cin = c < jb.cols;
+    const int e = tc::scale_exp(cin ? __uint_as_float(jb.cmax[c]) : 0.f);
+    const float sc = ldexpf(1.f, e);
+    if (blockIdx.y == 0 && warp == 0 && cin) jb.inv[c] = ldexpf(1.f, -e);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = k0 + warp * 8 + rr;
+        float v = 0.f;
+        if (cin && r < jb.rows) v = __ldg(jb.src + (size_t)r * jb.ld + c) * sc;
+        tile[lane][warp * 8 + rr] = v;
     }
     __syncthreads();
-    const float sc = csc[lane];
-    for (int k0 = 0; k0 < jb.kp; k0 += 64) {
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = k0 + warp * 8 + rr;
-            float v = 0.f;
-            if (cin && r < jb.rows) v = __ldg(jb.src + (size_t)r * jb.ld + c) * sc;
-            tile[lane][warp * 8 + rr] = v;
+    for (int q = 0; q < 4; ++q) {
+        const int cc = warp * 4 + q;
+        if (c0 + cc < jb.cols) {
+            const float v0 = tile[cc][2 * lane], v1 = tile[cc][2 * lane + 1];
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const size_t o = (size_t)(c0 + cc) * jb.kp + k0 + 2 * lane;
+            *reinterpret_cast<__half2*>(jb.hi + o) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(jb.lo + o) =
+                __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
         }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int cc = warp * 4 + q;
-            if (c0 + cc < jb.cols) {
-                const float v0 = tile[cc][2 * lane], v1 = tile[cc][2 * lane + 1];
-                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-                const size_t o = (size_t)(c0 + cc) * jb.kp + k0 + 2 * lane;
-                *reinterpret_cast<__half2*>(jb.hi + o) = __halves2half2(h0, h1);
-                *reinterpret_cast<__half2*>(jb.lo + o) =
-                    __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -875,14 +928,17 @@ attn_bwd_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ dm
     }
 }
 
-// pinv kernel: one CTA per (video, head); grid (8, V).  attn2 = A, a3v = B, stats as attn2_kernel wrote them.
-// zhist [V][8][6][64][64]: the inputs Z_0 .. Z_5 of the six iterations (recomputed here in fp32).
+// pinv kernel: one CTA per (video, head); grid (8, V), 512 threads (two rows per thread: a dependent chain of 64^3 products
+// on ONE SM is bound by how well the FFMA latency is hidden).  attn2 = A, a3v = B, stats as attn2_kernel wrote them.
+// hist [V][8][iters][4][64][64]: Z_k (input of iteration k), P_k = A Z_k, T2_k, T3_k of the forward chain, which is
+// recomputed here in fp32; the reverse sweep reads them back (L2) instead of recomputing three products per iteration.
 // Outputs: dB [V][8][64][64], dA2 (without the start-scale term) [V][8][64][64], dc_part [V][8].
+constexpr int kPinvBwdThreads = 512;
 constexpr int kPinvBwdSmem = (11 * 64 * kLd64 + 16) * (int)sizeof(float);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPinvBwdThreads)
 pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
-                const float* __restrict__ dW, float* __restrict__ zhist, float* __restrict__ dB, float* __restrict__ dA2,
+                const float* __restrict__ dW, float* __restrict__ hist, float* __restrict__ dB, float* __restrict__ dA2,
                 float* __restrict__ dc_part, int iters) {
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
@@ -897,9 +953,10 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
     float* Vs = Us + 64 * kLd64;
     float* DP = Vs + 64 * kLd64;
     float* red = DP + 64 * kLd64;
+    constexpr int RT = 2, NT = kPinvBwdThreads;
     const int h = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const size_t off = ((size_t)v * kHeads + h) * 4096;
-    float* zh = zhist + off * iters;
+    float* hs = hist + off * iters * 4;
 
     float mrow = 0.f, mcol = 0.f;
 #pragma unroll
@@ -908,9 +965,7 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
         mcol = fmaxf(mcol, __ldg(stats + ((size_t)v * kHeads + hh) * 2 + 1));
     }
     const float denom = mrow * mcol;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int idx = tid + it * 256;
+    for (int idx = tid; idx < 1024; idx += NT) {
         const int r = idx >> 4, c4 = (idx & 15) * 4;
         const float4 a = ldg4(attn2 + off + r * 64 + c4);
         st4(As + r * kLd64 + c4, a);
@@ -918,76 +973,78 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
         Zs[(c4 + 2) * kLd64 + r] = a.z / denom; Zs[(c4 + 3) * kLd64 + r] = a.w / denom;
     }
     __syncthreads();
-    // ---- forward chain, keeping the input of every iteration ----
+    // ---- forward chain, keeping Z_k, P_k, T2_k, T3_k ----
     for (int k = 0; k < iters; ++k) {
-        for (int idx = tid; idx < 4096; idx += 256) zh[(size_t)k * 4096 + idx] = Zs[(idx >> 6) * kLd64 + (idx & 63)];
-        mm64_to<MM_NN>(Pz, As, Zs, 1.f, 0.f, 0.f, ty, tx);
+        float* hk = hs + (size_t)k * 4 * 4096;
+        tile_store(hk, Zs, tid, NT);
+        mm64_to<MM_NN, RT>(Pz, As, Zs, 1.f, 0.f, 0.f, ty, tx);
         __syncthreads();
-        for (int idx = tid; idx < 4096; idx += 256) {
+        tile_store(hk + 4096, Pz, tid, NT);
+        for (int idx = tid; idx < 4096; idx += NT) {
             const int r = idx >> 6, c = idx & 63;
             T1[r * kLd64 + c] = (r == c ? 7.f : 0.f) - Pz[r * kLd64 + c];
         }
         __syncthreads();
-        mm64_to<MM_NN>(T2, Pz, T1, -1.f, 0.f, 15.f, ty, tx);
+        mm64_to<MM_NN, RT>(T2, Pz, T1, -1.f, 0.f, 15.f, ty, tx);
         __syncthreads();
-        mm64_to<MM_NN>(T3, Pz, T2, -1.f, 0.f, 13.f, ty, tx);
+        tile_store(hk + 2 * 4096, T2, tid, NT);
+        mm64_to<MM_NN, RT>(T3, Pz, T2, -1.f, 0.f, 13.f, ty, tx);
         __syncthreads();
-        mm64_to<MM_NN>(Zn, Zs, T3, 0.25f, 0.f, 0.f, ty, tx);
+        tile_store(hk + 3 * 4096, T3, tid, NT);
+        mm64_to<MM_NN, RT>(Zn, Zs, T3, 0.25f, 0.f, 0.f, ty, tx);
         __syncthreads();
         float* t = Zs; Zs = Zn; Zn = t;
     }
     // ---- W = Z B:  dZ = dW B^T,  dB = Z^T dW ----
-    load64_rowmajor(Us, a3v + off, 64, tid);
-    load64_rowmajor(Vs, dW + off, 64, tid);
+    tile_load(Us, a3v + off, tid, NT);
+    tile_load(Vs, dW + off, tid, NT);
     __syncthreads();
-    mm64_to<MM_NT>(dZ, Vs, Us, 1.f, 0.f, 0.f, ty, tx);
-    mm64_to<MM_TN>(DP, Zs, Vs, 1.f, 0.f, 0.f, ty, tx);
+    mm64_to<MM_NT, RT>(dZ, Vs, Us, 1.f, 0.f, 0.f, ty, tx);
+    mm64_to<MM_TN, RT>(DP, Zs, Vs, 1.f, 0.f, 0.f, ty, tx);
     __syncthreads();
-    for (int idx = tid; idx < 4096; idx += 256) dB[off + idx] = DP[(idx >> 6) * kLd64 + (idx & 63)];
-    float dA[4][4];                                   // NT ownership: rows ty*4+i, cols tx+16j
-    zero44(dA);
+    tile_store(dB + off, DP, tid, NT);
+    float dA[RT][4];                                  // NT ownership: rows ty*2+i, cols tx+16j
+    zero_acc<RT>(dA);
     // ---- the iterations in reverse ----
     for (int k = iters - 1; k >= 0; --k) {
+        const float* hk = hs + (size_t)k * 4 * 4096;
+        __syncthreads();                              // everything of the previous round (and the dB store) has read its tiles
+        tile_load(Zs, hk, tid, NT);
+        tile_load(Pz, hk + 4096, tid, NT);
+        tile_load(T2, hk + 2 * 4096, tid, NT);
+        tile_load(T3, hk + 3 * 4096, tid, NT);
         __syncthreads();
-        for (int idx = tid; idx < 4096; idx += 256) Zs[(idx >> 6) * kLd64 + (idx & 63)] = zh[(size_t)k * 4096 + idx];
-        __syncthreads();
-        mm64_to<MM_NN>(Pz, As, Zs, 1.f, 0.f, 0.f, ty, tx);
-        __syncthreads();
-        for (int idx = tid; idx < 4096; idx += 256) {
+        for (int idx = tid; idx < 4096; idx += NT) {
             const int r = idx >> 6, c = idx & 63;
             T1[r * kLd64 + c] = (r == c ? 7.f : 0.f) - Pz[r * kLd64 + c];
         }
+        mm64_to<MM_TN, RT>(Us, Zs, dZ, 0.25f, 0.f, 0.f, ty, tx);          // dT3 = 0.25 Z^T dZ
         __syncthreads();
-        mm64_to<MM_NN>(T2, Pz, T1, -1.f, 0.f, 15.f, ty, tx);
+        mm64_to<MM_NT, RT>(Zn, dZ, T3, 0.25f, 0.f, 0.f, ty, tx);          // dZ' = 0.25 dZ T3^T
+        mm64_to<MM_NT, RT>(DP, Us, T2, -1.f, 0.f, 0.f, ty, tx);           // dP  = -dT3 T2^T
+        mm64_to<MM_TN, RT>(Vs, Pz, Us, -1.f, 0.f, 0.f, ty, tx);           // dT2 = -P^T dT3
         __syncthreads();
-        mm64_to<MM_NN>(T3, Pz, T2, -1.f, 0.f, 13.f, ty, tx);
-        mm64_to<MM_TN>(Us, Zs, dZ, 0.25f, 0.f, 0.f, ty, tx);          // dT3 = 0.25 Z^T dZ
+        mm64_to<MM_NT, RT>(DP, Vs, T1, -1.f, 1.f, 0.f, ty, tx);           // dP -= dT2 T1^T      (same ownership as above)
+        __syncthreads();                                                  // Us (dT3) no longer read
+        mm64_to<MM_TN, RT>(Us, Pz, Vs, -1.f, 0.f, 0.f, ty, tx);           // dT1 = -P^T dT2
         __syncthreads();
-        mm64_to<MM_NT>(Zn, dZ, T3, 0.25f, 0.f, 0.f, ty, tx);          // dZ' = 0.25 dZ T3^T
-        mm64_to<MM_NT>(DP, Us, T2, -1.f, 0.f, 0.f, ty, tx);           // dP  = -dT3 T2^T
-        mm64_to<MM_TN>(Vs, Pz, Us, -1.f, 0.f, 0.f, ty, tx);           // dT2 = -P^T dT3
-        __syncthreads();
-        mm64_to<MM_NT>(DP, Vs, T1, -1.f, 1.f, 0.f, ty, tx);           // dP -= dT2 T1^T      (same ownership as above)
-        __syncthreads();                                              // Us (dT3) no longer read
-        mm64_to<MM_TN>(Us, Pz, Vs, -1.f, 0.f, 0.f, ty, tx);           // dT1 = -P^T dT2
-        __syncthreads();
-        for (int idx = tid; idx < 4096; idx += 256) {
+        for (int idx = tid; idx < 4096; idx += NT) {
             const int r = idx >> 6, c = idx & 63;
-            DP[r * kLd64 + c] -= Us[r * kLd64 + c];                   // dP -= dT1
+            DP[r * kLd64 + c] -= Us[r * kLd64 + c];                       // dP -= dT1
         }
         __syncthreads();
-        mm64<MM_NT>(dA, DP, Zs, ty, tx);                              // dA += dP Z^T
-        mm64_to<MM_TN>(Zn, As, DP, 1.f, 1.f, 0.f, ty, tx);            // dZ' += A^T dP
+        mm64<MM_NT, RT>(dA, DP, Zs, ty, tx);                              // dA += dP Z^T
+        mm64_to<MM_TN, RT>(Zn, As, DP, 1.f, 1.f, 0.f, ty, tx);            // dZ' += A^T dP
         __syncthreads();
         float* t = dZ; dZ = Zn; Zn = t;
     }
     // Z_0 = A^T / c:  dA += dZ^T / c,  dc = - sum dZ o A^T / c^2
     float part = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int r = ty * 4 + i, c = tx + 16 * j;
+            const int r = ty * RT + i, c = tx + 16 * j;
             const float dzt = dZ[c * kLd64 + r];
             dA[i][j] += dzt / denom;
             part = fmaf(dzt, As[r * kLd64 + c], part);
@@ -997,10 +1054,10 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
     if ((tid & 31) == 0) red[tid >> 5] = part;
     __syncthreads();
     if (tid == 0) {
-        float s = 0.f;
+        float sum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w];
-        dc_part[v * kHeads + h] = -s / (denom * denom);
+        for (int w = 0; w < NT / 32; ++w) sum += red[w];
+        dc_part[v * kHeads + h] = -sum / (denom * denom);
     }
 }
 
@@ -1172,11 +1229,12 @@ attn_bwd_keys_kernel(const float* __restrict__ qkv, const int* __restrict__ cu_r
 
 // finish: dq = (dq_part + dql[landmark of the row] / seg) / 8,  dk = dk_part + dkl[landmark] / seg; in place.
 // One CTA per 64-row tile; thread <-> 4 of the 1024 q|k columns.
+constexpr int kFinishSplit = 8;                       // grid.y: a 64-row tile is finished by 8 CTAs of 8 rows each
 __global__ void __launch_bounds__(256)
 dqkv_finish_kernel(const int* __restrict__ cu_rows, const int2* __restrict__ tiles, const float* __restrict__ dql,
                    const float* __restrict__ dkl, float* __restrict__ dqkv) {
     const int2 tile = tiles[blockIdx.x];
-    const int v = tile.x, r0 = tile.y;
+    const int v = tile.x, r0 = tile.y + (int)blockIdx.y * (64 / kFinishSplit);
     const VidInfo vi = vid_info(cu_rows, v);
     const int c4 = threadIdx.x * 4;
     const bool is_k = c4 >= kInner;
@@ -1184,7 +1242,7 @@ dqkv_finish_kernel(const int* __restrict__ cu_rows, const int2* __restrict__ til
     const int hd = cc >> 6, d = cc & 63;
     const float* land = (is_k ? dkl : dql) + ((size_t)v * kHeads + hd) * 4096 + d;
     const float inv_seg = 1.f / (float)vi.seg, mul = is_k ? 1.f : 0.125f;
-    const int rend = min(r0 + 64, vi.T);
+    const int rend = min(r0 + 64 / kFinishSplit, vi.T);
     for (int r = r0; r < rend; ++r) {
         const int j = (r + vi.pad) / vi.seg;
         const float4 l = ldg4(land + j * 64);

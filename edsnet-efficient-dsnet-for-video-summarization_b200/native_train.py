@@ -15,6 +15,7 @@ No torch op computes any part of the model here; torch provides device memory, s
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
@@ -67,8 +68,10 @@ def _as_batch(batch, device) -> DeviceBatch:
     return plan.to(device)
 
 
-def train_forward(model, x: torch.Tensor, batch, dropout: bool, seed: int, offset: int) -> TrainContext:
-    """x: packed [rows, 1024] float32 CUDA.  Runs edsnet_train_forward; returns the context (ctx.pred_cls, ctx.pred_loc)."""
+def train_forward(model, x: torch.Tensor, batch, dropout: bool, seed: int, offset: int,
+                  offset_dev: Optional[torch.Tensor] = None) -> TrainContext:
+    """x: packed [rows, 1024] float32 CUDA.  Runs edsnet_train_forward; returns the context (ctx.pred_cls, ctx.pred_loc).
+    offset_dev: optional int64 device scalar added to `offset` at run time (fresh dropout masks under graph replay)."""
     model._check_input(x)
     if model.base_model_type != "nystromformer":
         raise RuntimeError("the native training kernels cover base_model='nystromformer' (the hot path)")
@@ -89,8 +92,9 @@ def train_forward(model, x: torch.Tensor, batch, dropout: bool, seed: int, offse
         pred_cls = torch.empty((x.shape[0], S), dtype=torch.float32, device=x.device)
         pred_loc = torch.empty((x.shape[0], S, 2), dtype=torch.float32, device=x.device)
         _capi.check(lib.edsnet_train_forward(cfg, w, batch.struct, x.data_ptr(), 1 if dropout else 0,
-                                             seed & _SEED_MASK, offset & _SEED_MASK, pred_cls.data_ptr(),
-                                             pred_loc.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                             seed & _SEED_MASK, offset & _SEED_MASK,
+                                             offset_dev.data_ptr() if offset_dev is not None else None,
+                                             pred_cls.data_ptr(), pred_loc.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     ctx.cfg, ctx.batch, ctx.x, ctx.pred_cls, ctx.pred_loc = cfg, batch, x, pred_cls, pred_loc
     ctx.workspace, ctx.dropout, ctx.weights, ctx.keep = ws, bool(dropout), w, keep
     return ctx
@@ -212,10 +216,17 @@ class NativeDataParallelStep:
     Adam on the flat parameter buffer with the 1 / world factor folded in.  loss = mean over the step's videos of
     cls_loss + lambda_reg * loc_loss (anchor_based/train.py:119-123); lr 5e-5, weight decay 1e-5 as train.py:53-55.
 
-    The parameters become views of one flat buffer (so do their .grad), in the order of edsnet_grads."""
+    The parameters become views of one flat buffer (so do their .grad), in the order of edsnet_grads.
+
+    use_graphs: the forward + loss + backward launch sequence (about 45 kernels of a few microseconds each for one
+    TVSum-sized video: launch bound from the host) is captured into a CUDA graph per tuple of video lengths the second
+    time that tuple is seen and replayed afterwards; features and labels are copied into the graph's static buffers, the
+    dropout mask still changes every step (the Philox offset lives in device memory).  At most `max_graphs` graphs are
+    kept (least recently used first out); a dataset of N videos taken k at a time in a fixed order needs N / k."""
 
     def __init__(self, model, lr: float = 5e-5, weight_decay: float = 1e-5, lambda_reg: float = 1.0, world_size: int = 1,
-                 group=None, betas=(0.9, 0.999), eps: float = 1e-8, dropout: bool = True, seed: Optional[int] = None):
+                 group=None, betas=(0.9, 0.999), eps: float = 1e-8, dropout: bool = True, seed: Optional[int] = None,
+                 use_graphs: bool = True, max_graphs: int = 64):
         named = model._named_weights()
         params = [named[k] for k in _capi.GRAD_FIELDS]
         dev = params[0].device
@@ -242,40 +253,100 @@ class NativeDataParallelStep:
             o += n
         self.step_count = 0
         self.skip_allreduce = False
+        self.use_graphs, self.max_graphs = bool(use_graphs), int(max_graphs)
         self._loss = None
-        self._plans = {}
+        self._graphs = collections.OrderedDict()
+        self._seen = set()
+        self._offset_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._side = torch.cuda.Stream(dev)
+        self.graph_replays = 0
         fwd, bwd = C.c_int32(0), C.c_int32(0)
         _capi.check(_capi.lib().edsnet_train_launches(model._config(), C.byref(fwd), C.byref(bwd)))
         self.launches_per_step = int(fwd.value) + int(bwd.value) + 3          # + gradient memset, loss gradient, Adam
 
-    def _plan(self, lengths: Tuple[int, ...]) -> DeviceBatch:
-        b = self._plans.get(lengths)
-        if b is None:
-            if len(self._plans) > 256:
-                self._plans.clear()
-            b = BatchPlan.build(lengths).to(self.device)
-            self._plans[lengths] = b
-        return b
+    # ---- labels: host NumPy (anchor_labels / LabelCache) or tensors -> one int32 and one float32 array per step ----
+    @staticmethod
+    def _host_labels(cls_labels, loc_labels):
+        def to_np(a):
+            return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+        cl = np.ascontiguousarray(np.concatenate([to_np(c) for c in cls_labels]), dtype=np.int32)
+        ll = np.ascontiguousarray(np.concatenate([to_np(l) for l in loc_labels]), dtype=np.float32)
+        return cl, ll
+
+    def _forward_backward(self, x, batch, cl, ll, k, offset, offset_dev):
+        """zero gradient, train-mode forward, loss gradient (scaled by 1 / local videos), backward -> flat_grad."""
+        self.flat_grad.zero_()
+        ctx = train_forward(self.model, x, batch, self.dropout, self.seed, offset, offset_dev)
+        loss, d_logit, d_loc = loss_and_grad(ctx, cl, ll, self.lambda_reg, 1.0 / k)
+        train_backward(ctx, d_logit, d_loc, self.grad_views, logit_grad=True)
+        return ctx, loss, d_logit, d_loc
 
     def backward_only(self, seqs: Sequence[torch.Tensor], cls_labels, loc_labels) -> torch.Tensor:
         """Forward + loss + backward of this rank's videos into flat_grad (already divided by the local video count);
-        returns the per-video losses [k, 3] (device).  No collective, no update."""
-        dev = self.device
+        returns the per-video losses [k, 3] (device).  No collective, no update, no graph."""
         lengths = tuple(int(s.shape[0]) for s in seqs)
         x = seqs[0] if len(seqs) == 1 else torch.cat(list(seqs))
-        batch = self._plan(lengths)
-        cl = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.asarray(c) for c in cls_labels]), dtype=np.int32))
-        ll = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.asarray(l) for l in loc_labels]), dtype=np.float32))
-        cl, ll = cl.to(dev, non_blocking=True), ll.to(dev, non_blocking=True)
-        self.flat_grad.zero_()
-        ctx = train_forward(self.model, x, batch, self.dropout, self.seed, self.step_count)
-        loss, d_logit, d_loc = loss_and_grad(ctx, cl, ll, self.lambda_reg, 1.0 / len(seqs))
-        train_backward(ctx, d_logit, d_loc, self.grad_views, logit_grad=True)
+        batch = self.model._device_batch(lengths, self.device)
+        cl, ll = self._host_labels(cls_labels, loc_labels)
+        cl, ll = torch.from_numpy(cl).to(self.device), torch.from_numpy(ll).to(self.device)
+        _, loss, _, _ = self._forward_backward(x, batch, cl.reshape(x.shape[0], -1), ll.reshape(x.shape[0], -1, 2),
+                                               len(seqs), self.step_count, None)
         return loss
 
+    def _capture(self, lengths, k):
+        dev, S = self.device, self.model.num_scales
+        R = int(sum(lengths))
+        e = {"x": torch.zeros((R, 1024), dtype=torch.float32, device=dev),
+             "cl": torch.zeros((R, S), dtype=torch.int32, device=dev),
+             "ll": torch.zeros((R, S, 2), dtype=torch.float32, device=dev),
+             "cl_pin": torch.zeros((R, S), dtype=torch.int32).pin_memory(),
+             "ll_pin": torch.zeros((R, S, 2), dtype=torch.float32).pin_memory(),
+             "copied": torch.cuda.Event()}
+        batch = self.model._device_batch(lengths, dev)
+        graph = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            with torch.cuda.graph(graph, stream=self._side):
+                e["keep"] = self._forward_backward(e["x"], batch, e["cl"], e["ll"], k, 0, self._offset_dev)
+        cur.wait_stream(self._side)
+        e["graph"], e["batch"], e["loss"] = graph, batch, e["keep"][1]
+        e["copied"].record(cur)
+        return e
+
     def step(self, seqs: Sequence[torch.Tensor], cls_labels, loc_labels) -> torch.Tensor:
+        """Returns the per-video losses [k, 3] of this rank (device tensor, overwritten by a later step on the same
+        length tuple when graphs are in use)."""
         self.model.train()
-        self._loss = self.backward_only(seqs, cls_labels, loc_labels)
+        lengths = tuple(int(s.shape[0]) for s in seqs)
+        entry = None
+        if self.use_graphs:
+            entry = self._graphs.get(lengths)
+            if entry is None and lengths in self._seen:
+                entry = self._capture(lengths, len(seqs))          # second sighting: everything lazy has run once
+                self._graphs[lengths] = entry
+                if len(self._graphs) > self.max_graphs:
+                    self._graphs.popitem(last=False)
+            self._seen.add(lengths)
+        if entry is not None:
+            self._graphs.move_to_end(lengths)
+            cl, ll = self._host_labels(cls_labels, loc_labels)
+            entry["copied"].synchronize()                          # the previous upload out of the pinned buffers is done
+            entry["cl_pin"].numpy().reshape(-1)[:] = cl.reshape(-1)
+            entry["ll_pin"].numpy().reshape(-1)[:] = ll.reshape(-1)
+            entry["cl"].copy_(entry["cl_pin"], non_blocking=True)
+            entry["ll"].copy_(entry["ll_pin"], non_blocking=True)
+            entry["copied"].record(torch.cuda.current_stream(self.device))
+            if len(seqs) == 1:
+                entry["x"].copy_(seqs[0])
+            else:
+                torch.cat(list(seqs), out=entry["x"])
+            self._offset_dev.fill_(self.step_count)
+            entry["graph"].replay()
+            self.graph_replays += 1
+            self._loss = entry["loss"]
+        else:
+            self._loss = self.backward_only(seqs, cls_labels, loc_labels)
         if self.world_size > 1 and not self.skip_allreduce:
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)

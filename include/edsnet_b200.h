@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 8
+#define EDSNET_ABI_VERSION 10
 
 enum {
     EDSNET_OK = 0,
@@ -288,10 +288,11 @@ typedef struct {
     size_t qkv_f32;                              /* [rows][1536] fp32 copy of q/8 | k | v (backward)                     */
     size_t dqkv;                                 /* [rows][1536] gradient of the to_qkv output                           */
     size_t m3, l3;                               /* [videos][8][64] row maximum / normaliser of softmax(q_land k^T)      */
-    size_t acc0, acc_bytes;                      /* dw_att | dkl | dql, zeroed at the start of the backward             */
+    size_t acc0, acc_bytes;                      /* dw_att | dkl | dql | cmax, zeroed at the start of the backward      */
     size_t dw_att, dkl, dql, db_att, da2;        /* [videos][8][64][64] each                                            */
+    size_t cmax;                                 /* column maxima of the transposed operand splits (uint bit patterns)   */
     size_t dc_part;                              /* [videos][8] gradient of the pseudo-inverse start scale, per head     */
-    size_t zhist;                                /* [videos][8][6][64][64] inputs of the six pinv iterations             */
+    size_t zhist;                                /* [videos][8][6][4][64][64] Z_k, A Z_k, T2_k, T3_k of the pinv chain   */
     size_t g;                                    /* [rows][4] gradient of the head projections                           */
     size_t d_logit;                              /* [rows][S]                                                            */
     size_t das;                                  /* [depth][rows][128] gradient of every Linear output of the fc block   */
@@ -308,10 +309,12 @@ int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* b
 /* DSNet.forward in train() mode (anchor_based/dsnet.py:100-115 with the Dropout(0.5) of the shared fc block, :91-95,
  * active when dropout != 0) keeping every activation the backward needs.  The mask is Philox4x32-10 with counter
  * (row, layer, offset) and key seed: bit c of the 128 output bits keeps hidden column c; edsnet_dropout_mask writes it
- * out ([depth][rows][128] bytes, 1 = kept) for tests.  Only the fp32 weight pointers of `w` are read. */
+ * out ([depth][rows][128] bytes, 1 = kept) for tests.  offset_dev (may be NULL): one uint64 in DEVICE memory that is added
+ * to `offset` when the kernel runs, so that a captured CUDA graph draws a fresh mask on every replay.  Only the fp32 weight
+ * pointers of `w` are read. */
 int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
-                         int32_t dropout, uint64_t seed, uint64_t offset, float* pred_cls, float* pred_loc,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int32_t dropout, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float* pred_cls,
+                         float* pred_loc, void* workspace, size_t workspace_bytes, void* stream);
 int edsnet_dropout_mask(uint64_t seed, uint64_t offset, int32_t rows, int32_t depth, uint8_t* out, void* stream);
 
 /* anchor_based/losses.py:5-57 combined as anchor_based/train.py:119-123, per video of the batch:
@@ -338,7 +341,8 @@ int edsnet_adam_step(float* params, const float* grads, float* exp_avg, float* e
 
 /* fp32 (rows, cols) -> operand planes of the TRANSPOSE: hi [cols][kp] fp16 | lo [cols][kp] fp16 | inverse scales [cols]
  * fp32, kp = rows rounded up to 64 (zero padded), every output row scaled like edsnet_split_f16 does.  The operand format
- * of every dW = dY^T X product of the backward.  dst needs edsnet_split_f16_bytes(cols, kp) bytes. */
+ * of every dW = dY^T X product of the backward.  dst needs edsnet_split_f16_bytes(cols, kp) + 4 * cols bytes (the last
+ * 4 * cols are scratch for the column maxima). */
 int edsnet_split_f16_t(const float* src, int64_t rows, int64_t cols, void* dst, void* stream);
 
 /* ---- stage-level entry points (tests, per-kernel timing, ncu) ---- */

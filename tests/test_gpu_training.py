@@ -92,12 +92,12 @@ def test_split_t_planes(rows, cols):
     g = torch.Generator().manual_seed(rows + cols)
     src = (torch.randn(rows, cols, generator=g) * torch.logspace(-6, 2, cols)[None, :]).to(DEV)
     kp = (rows + 63) // 64 * 64
-    dst = torch.zeros(lib.edsnet_split_f16_bytes(cols, kp), dtype=torch.uint8, device=DEV)
+    dst = torch.zeros(lib.edsnet_split_f16_bytes(cols, kp) + 4 * cols, dtype=torch.uint8, device=DEV)
     capi.check(lib.edsnet_split_f16_t(src.data_ptr(), rows, cols, dst.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     hi = dst[:cols * kp * 2].view(torch.float16).reshape(cols, kp).double().cpu()
     lo = dst[cols * kp * 2:cols * kp * 4].view(torch.float16).reshape(cols, kp).double().cpu()
-    inv = dst[cols * kp * 4:].view(torch.float32).double().cpu()
+    inv = dst[cols * kp * 4:cols * kp * 4 + cols * 4].view(torch.float32).double().cpu()
     want = src.t().double().cpu()
     rec = (hi + lo) * inv[:, None]
     assert torch.equal(rec[:, rows:], torch.zeros(cols, kp - rows, dtype=torch.float64))
@@ -117,8 +117,8 @@ def test_dw_product_on_tensor_cores(M, N, K):
     X = (torch.randn(K, N, generator=g) * 0.05).to(DEV)
     kp = (K + 63) // 64 * 64
     st = torch.cuda.current_stream().cuda_stream
-    A16 = torch.empty(lib.edsnet_split_f16_bytes(M, kp), dtype=torch.uint8, device=DEV)
-    B16 = torch.empty(lib.edsnet_split_f16_bytes(N, kp), dtype=torch.uint8, device=DEV)
+    A16 = torch.empty(lib.edsnet_split_f16_bytes(M, kp) + 4 * M, dtype=torch.uint8, device=DEV)
+    B16 = torch.empty(lib.edsnet_split_f16_bytes(N, kp) + 4 * N, dtype=torch.uint8, device=DEV)
     capi.check(lib.edsnet_split_f16_t(dY.data_ptr(), K, M, A16.data_ptr(), st))
     capi.check(lib.edsnet_split_f16_t(X.data_ptr(), K, N, B16.data_ptr(), st))
     Cd = torch.full((M, N), float("nan"), device=DEV)
