@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 10
+EDSNET_ABI_VERSION = 11
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -44,7 +44,7 @@ class Batch(C.Structure):
 
 
 LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",
-                 "u0", "u1", "x16", "zeros", "zstat", "xstat", "total")
+                 "u0", "u1", "x16", "zeros", "a3_part", "zstat", "xstat", "total")
 
 
 class WorkspaceLayout(C.Structure):
@@ -60,7 +60,7 @@ class Grads(C.Structure):
 
 
 TRAIN_LAYOUT_FIELDS = ("w_qkv16", "w_out16", "w_fc116", "w_fcb16", "qkv16", "qkv_inv", "q_land", "k_land", "attn2", "stats",
-                       "a3v", "zmat", "wmat", "merged", "y", "yn", "uin", "hs", "u_last", "heads", "qkv_f32", "dqkv", "m3",
+                       "a3v", "zmat", "wmat", "a3_part", "merged", "y", "yn", "uin", "hs", "u_last", "heads", "qkv_f32", "dqkv", "m3",
                        "l3", "acc0", "acc_bytes", "dw_att", "dkl", "dql", "db_att", "da2", "cmax", "dc_part", "zhist", "g", "d_logit",
                        "das", "du0", "dyn", "dy", "dmerged", "t_a", "t_b", "total")
 

@@ -180,10 +180,14 @@ constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 
 // 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
 // 32..63), warp 8 = TMA producer, warp 9 = MMA issuer (told by mbarriers when S has been read out / P is in place, so
 // the row warps never wait for an issue loop).
+// gridDim.z > 1 (few, long videos: one video would otherwise keep 4 of 148 SMs busy): CTA z streams the z-th contiguous
+// range of key tiles and leaves its un-normalised output rows and (running max, sum) in `part` [V][8][Z][64][66];
+// a3v_merge_kernel combines the ranges (flash-decoding style).  The zero pad keys belong to range 0.
+constexpr int kA3PartLd = 66;
 __global__ void __launch_bounds__(320, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
-              float* __restrict__ a3v) {
+              float* __restrict__ a3v, float* __restrict__ part) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
@@ -198,7 +202,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pair = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
-    const int n_tiles = (vi.T + 63) / 64;
+    const int tiles_all = (vi.T + 63) / 64;
+    const int zsplit = (int)gridDim.z, zi = (int)blockIdx.z;
+    const int per = (tiles_all + zsplit - 1) / zsplit;
+    const int tile0 = zi * per;                                             // first key tile of this CTA's range
+    const int n_tiles = max(0, min(per, tiles_all - tile0));
     const int h0 = pair * 2;
 
     if (tid == 0) {
@@ -222,13 +230,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         inv_ql = ldexpf(1.f, -e);
         s_pair[tid] = inv_ql;
         store_row64(g + oQl, g + oQl + 16384, tid, q, ldexpf(1.f, e));
-        // scales of tile 0: thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
-        const int key = tid & 63, part = 1 + (tid >> 6);
+        // scales of the first tile: thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
+        const int key = tile0 * 64 + (tid & 63), qkv_part = 1 + (tid >> 6);
         const bool in = key < vi.T;
-        const float* ip = inv + (size_t)(vi.row0 + (in ? key : 0)) * 24 + part * 8 + h0;
+        const float* ip = inv + (size_t)(vi.row0 + (in ? key : 0)) * 24 + qkv_part * 8 + h0;
         const float sc0 = in ? __ldg(ip) : 0.f, sc1 = in ? __ldg(ip + 1) : 0.f;
-        sc_vec[((tid >> 6) * 2 + 0) * 64 + key] = sc0;
-        sc_vec[((tid >> 6) * 2 + 1) * 64 + key] = sc1;
+        sc_vec[((tid >> 6) * 2 + 0) * 64 + (tid & 63)] = sc0;
+        sc_vec[((tid >> 6) * 2 + 1) * 64 + (tid & 63)] = sc1;
         if (tid >= 64) {                                   // warps 2, 3 hold the v scales: their maxima per head
             const float m0 = warp_max(sc0), m1 = warp_max(sc1);
             if (lane == 0) { s_vmx[0 * 2 + (warp - 2)] = m0; s_vmx[1 * 2 + (warp - 2)] = m1; }
@@ -249,7 +257,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 const int s = i & 1;
                 const uint32_t ph = ((uint32_t)(i >> 1) & 1u) ^ 1u;
                 const uint32_t st = base + oKV + s * kA3Stage;
-                const int row = vi.row0 + i * 64;
+                const int row = vi.row0 + (tile0 + i) * 64;
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv) {                            // 0: k_h0 k_h1, 1: v_h0 v_h1
                     const uint32_t full = bars + (kv ? 48 : 0) + 8 * s, empty = bars + (kv ? 64 : 16) + 8 * s;
@@ -308,7 +316,8 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 #pragma unroll
         for (int d = 0; d < 32; ++d) o[d] = 0.f;
         // running max is shared by the two threads of a row; the running sum is per thread (its keys) and merged at the end
-        float run_max = vi.pad > 0 ? 0.f : -INFINITY, run_sum = half == 0 ? (float)vi.pad : 0.f;
+        const bool pads_here = vi.pad > 0 && zi == 0;                       // the zero pad keys: logit 0, value 0
+        float run_max = pads_here ? 0.f : -INFINITY, run_sum = (half == 0 && pads_here) ? (float)vi.pad : 0.f;
         // Software pipeline over the key tiles: S(i+1) is issued as soon as every thread has pulled S(i) out of TMEM,
         // so it runs under the softmax of tile i; the P.V product of tile i is only collected in iteration i+1, after
         // that tile's softmax arithmetic, so it runs under the S read-out and the exponentials of tile i+1.
@@ -330,9 +339,9 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             // prefetch the next tile's scales (written to the other stage's slot below)
             float nsc0 = 0.f, nsc1 = 0.f;
             if (tid < 128) {
-                const int key = (i + 1) * 64 + (tid & 63), part = 1 + (tid >> 6);
+                const int key = (tile0 + i + 1) * 64 + (tid & 63), qkv_part = 1 + (tid >> 6);
                 if (key < vi.T) {
-                    const float* ip = inv + (size_t)(vi.row0 + key) * 24 + part * 8 + h0;
+                    const float* ip = inv + (size_t)(vi.row0 + key) * 24 + qkv_part * 8 + h0;
                     nsc0 = __ldg(ip); nsc1 = __ldg(ip + 1);
                 }
             }
@@ -345,7 +354,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             tmem_read32_sum(tS, tS + 64u, p);
             const float* isk = sc_vec + (s * 4 + hh) * 64 + half * 32;
             const float* isv = sc_vec + (s * 4 + 2 + hh) * 64 + half * 32;
-            const int kvalid = vi.T - i * 64 - half * 32;
+            const int kvalid = vi.T - (tile0 + i) * 64 - half * 32;
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -396,16 +405,51 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         // merge the two partial sums of the row
         s_pair[half * 128 + row] = run_sum;
         named_bar_sync(1, 256);
-        const float rs = 1.f / (run_sum + s_pair[(half ^ 1) * 128 + row]);
-        if (ok) {
+        const float tot = run_sum + s_pair[(half ^ 1) * 128 + row];
+        if (ok && zsplit == 1) {
+            const float rs = 1.f / tot;
             float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kDimHead + half * 32;
 #pragma unroll
             for (int d = 0; d < 32; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
+        } else if (ok) {
+            float* dst = part + ((((size_t)v * kHeads + h0 + hh) * zsplit + zi) * kLandmark + (row & 63)) * kA3PartLd;
+#pragma unroll
+            for (int d = 0; d < 32; d += 2) *reinterpret_cast<float2*>(dst + half * 32 + d) = make_float2(o[d], o[d + 1]);
+            if (half == 0) *reinterpret_cast<float2*>(dst + 64) = make_float2(run_max, tot);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// Combine the key ranges of a3v_tc_kernel: a3v[j][d] = sum_z o_z[j][d] e^(m_z - m) / sum_z l_z e^(m_z - m), m = max_z m_z
+// (an empty range leaves m_z = -inf, l_z = 0).  grid (8, V), 256 threads: thread <-> (landmark row, 16 columns).
+__global__ void __launch_bounds__(256)
+a3v_merge_kernel(const float* __restrict__ part, int zsplit, float* __restrict__ a3v) {
+    const int h = blockIdx.x, v = blockIdx.y;
+    const int j = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16;
+    const float* p0 = part + (((size_t)v * kHeads + h) * zsplit) * kLandmark * kA3PartLd + (size_t)j * kA3PartLd;
+    float m = -INFINITY;
+    for (int z = 0; z < zsplit; ++z) m = fmaxf(m, p0[(size_t)z * kLandmark * kA3PartLd + 64]);
+    float acc[16], den = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+    for (int z = 0; z < zsplit; ++z) {
+        const float* pz = p0 + (size_t)z * kLandmark * kA3PartLd;
+        const float w = expf(pz[64] - m);                                    // exp(-inf) = 0 for an empty range
+        den = fmaf(pz[65], w, den);
+#pragma unroll
+        for (int d = 0; d < 16; d += 2) {
+            const float2 o = *reinterpret_cast<const float2*>(pz + c0 + d);
+            acc[d] = fmaf(o.x, w, acc[d]);
+            acc[d + 1] = fmaf(o.y, w, acc[d + 1]);
+        }
+    }
+    const float rs = 1.f / den;
+    float* dst = a3v + (((size_t)v * kHeads + h) * kLandmark + j) * kDimHead + c0;
+#pragma unroll
+    for (int d = 0; d < 16; d += 4) st4(dst + d, make_float4(acc[d] * rs, acc[d + 1] * rs, acc[d + 2] * rs, acc[d + 3] * rs));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -441,7 +485,12 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, v = blockIdx.y;
     const VidInfo vi = vid_info(cu_rows, v);
-    const int n_tiles = (vi.T + 127) / 128;
+    // gridDim.z > 1 (few, long videos): CTA z takes the z-th contiguous range of 128-row tiles (rows are independent)
+    const int tiles_all = (vi.T + 127) / 128;
+    const int per = (tiles_all + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int tile0 = (int)blockIdx.z * per;
+    const int n_tiles = max(0, min(per, tiles_all - tile0));
+    const int rbase = tile0 * 128;                                          // first row of this CTA's range
     const size_t hoff = ((size_t)v * kHeads + h) * 4096;
 
     if (tid == 0) {
@@ -470,7 +519,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     if (tid >= 64 && tid < 128) store_row64(g + oW, g + oW + 8192, tid - 64, wrow, ldexpf(1.f, ew));
     // max|W| of this (video, head): every output row is a convex combination of W's rows, so this bounds the
     // attention part of `merged` (value_conv_kernel derives the operand-plane scale from it)
-    if (tid == 0 && w_max_out != nullptr) w_max_out[((size_t)v * kHeads + h) * 2] = __uint_as_float(*s_wmax);
+    if (tid == 0 && w_max_out != nullptr && blockIdx.z == 0) w_max_out[((size_t)v * kHeads + h) * 2] = __uint_as_float(*s_wmax);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -484,7 +533,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 if (!mbar_wait(bars + 16 + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u)) break;
                 const uint32_t st = base + oQ + s * 32768;
                 mbar_expect_tx(bars + 8 * s, 32768);
-                const int row = vi.row0 + i * 128, col = h * kDimHead;
+                const int row = vi.row0 + rbase + i * 128, col = h * kDimHead;
                 tma_load_2d(st, &map_hi, bars + 8 * s, col, row);
                 tma_load_2d(st + 8192, &map_hi, bars + 8 * s, col, row + 64);
                 tma_load_2d(st + 16384, &map_lo, bars + 8 * s, col, row);
@@ -533,7 +582,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         const float o_scale = ldexpf(1.f, -ew) * (1.f / 16384.f);
         uint32_t s_phase = 0, pv_phase = 0;
         bool ok = true;
-        float inv_q = trow < vi.T ? __ldg(inv + (size_t)(vi.row0 + trow) * 24 + h) : 0.f;
+        float inv_q = rbase + trow < vi.T ? __ldg(inv + (size_t)(vi.row0 + rbase + trow) * 24 + h) : 0.f;
         float rs_prev = 0.f;
         // P.V product of tile j: read out, scale by the row's 1 / sum, store
         // Stored straight from the accumulator layout a warp instruction would touch 32 rows x 16 bytes (32 L1 tag
@@ -553,7 +602,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int row = j * 128 + wrow0 + rr + 16 * i;
+                    const int row = rbase + j * 128 + wrow0 + rr + 16 * i;
                     const float4 o4 = lds4(scr + (rr + 16 * i) * 12 + cc * 4);
                     if (row < vi.T)
                         st4(attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32 + q * 8 + cc * 4, o4);
@@ -563,7 +612,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
-            const int row = i * 128 + trow;
+            const int row = rbase + i * 128 + trow;
             const float inv_q_next = (row + 128 < vi.T) ? __ldg(inv + (size_t)(vi.row0 + row + 128) * 24 + h) : 0.f;
             unsigned char* stp = g + oQ + s * 32768;
             ok = mbar_wait(bars + 32, s_phase) && ok;

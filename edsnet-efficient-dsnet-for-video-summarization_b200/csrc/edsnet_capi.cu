@@ -174,9 +174,21 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
 
 // qkv: fp32 [R][1536] for EDSNET_PREC_FP32; for the tcgen05 precisions the hi plane [R][1536] fp16 followed by the lo
 // plane, with qkv_inv [R][24] (gemm_tc.cuh EPI_QKV_PLANES).
+// Key-range / row-range splits of the per-(video, head) attention kernels: with few videos in the batch (one long
+// video: BASELINE config 5) a grid of (heads, videos) CTAs would leave most of the 148 SMs idle.
+int a3v_split_cap(int n_videos) {                   // capacity the workspace is sized for
+    return 4 * n_videos >= 74 ? 1 : (148 + 4 * n_videos - 1) / (4 * n_videos);
+}
+int a3v_splits(int n_videos, int max_rows) { return std::max(1, std::min(a3v_split_cap(n_videos), (max_rows + 63) / 64)); }
+int attn_out_splits(int n_videos, int max_rows) {
+    if (8 * n_videos >= 148) return 1;
+    return std::max(1, std::min((296 + 8 * n_videos - 1) / (8 * n_videos), (max_rows + 127) / 128));
+}
+
 int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, const float* qkv_inv,
                       const float* conv_w, float* q_land, float* k_land, float* attn2, float* stats, float* a3v,
-                      float* zmat, float* wmat, float* merged, cudaStream_t st, void* merged16 = nullptr) {
+                      float* zmat, float* wmat, float* merged, cudaStream_t st, void* merged16 = nullptr,
+                      float* a3_part = nullptr) {
     // merged16 != nullptr (tcgen05 precisions, edsnet_forward): `merged` only carries the attention part and the sum
     // with the value convolution leaves as the to_out operand planes in merged16 (edsnet_split_f16 layout, 512 columns)
     const bool tcp = precision != EDSNET_PREC_FP32;
@@ -218,8 +230,18 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     }
     {
         StageScope scope(ST_A3V, st);
-        if (tcp) tc::a3v_tc_kernel<<<dim3(kHeads / 2, V), 320, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v);
-        else a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
+        if (tcp) {
+            // a3_part (edsnet_forward / edsnet_train_forward pass it): room for a3v_split_cap(V) key ranges per (video, head)
+            const int z = a3_part ? a3v_splits(V, b->max_rows) : 1;
+            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), 320, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+                                                                                   q_land, a3v, a3_part);
+            if (z > 1) {
+                CU_CHECK(cudaGetLastError(), "a3v_tc_kernel");
+                tc::a3v_merge_kernel<<<dim3(kHeads, V), 256, 0, st>>>(a3_part, z, a3v);
+            }
+        } else {
+            a3v_kernel<<<dim3(kHeads, V), 256, kA3vSmem, st>>>(qkv, b->cu_rows, q_land, a3v);
+        }
         CU_CHECK(cudaGetLastError(), "a3v_kernel");
     }
     {
@@ -231,7 +253,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     if (tcp) {
         {
             StageScope scope(ST_ATTN_OUT, st);
-            tc::attn_out_tc_kernel<<<dim3(kHeads, V), 320, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+            tc::attn_out_tc_kernel<<<dim3(kHeads, V, attn_out_splits(V, b->max_rows)), 320, tc::kAoSmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
                                                                                   k_land, wmat, merged,
                                                                                   merged16 ? stats : nullptr);
             CU_CHECK(cudaGetLastError(), "attn_out_tc_kernel");
@@ -341,6 +363,8 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.x16 = off;
     if (cfg && cfg->precision != EDSNET_PREC_FP32) take(split_f16_bytes(R, kFeat));
     L.zeros = take(kFeat * sizeof(float));
+    L.a3_part = off;
+    if (tcp && !mha) L.a3_part = take(V * kHeads * (size_t)a3v_split_cap((int)V) * kLandmark * tc::kA3PartLd * sizeof(float));
     L.zstat = off;
     L.xstat = off;
     if (tcp && !mha) {
@@ -523,7 +547,8 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         // (tcgen05: the x16 planes are dead after step 1; the front of that region takes merged (R x 512) as planes)
         void* merged16_out = prec != EDSNET_PREC_FP32 ? static_cast<void*>(ws + L.x16) : nullptr;
         rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
-                               F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, merged16_out);
+                               F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, merged16_out,
+                               prec != EDSNET_PREC_FP32 ? F(L.a3_part) : nullptr);
         if (rc) return rc;
         // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
         //    (fp16x3: z = y - mean(x row) - mean(bias) leaves as the fc1 operand planes with the row sums LayerNorm needs; step 4
@@ -774,6 +799,7 @@ void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos
     L.a3v = take(head_mat);
     L.zmat = take(head_mat);
     L.wmat = take(head_mat);
+    L.a3_part = take(V * kHeads * (size_t)a3v_split_cap((int)V) * kLandmark * tc::kA3PartLd * sizeof(float));
     L.merged = take(R * kInner * sizeof(float));
     L.y = take(R * kFeat * sizeof(float));
     L.yn = take(R * kFeat * sizeof(float));
@@ -924,7 +950,7 @@ int edsnet_train_forward(const edsnet_config* cfg, const edsnet_weights* w, cons
                        nullptr, nullptr, kInner, st, ST_QKV, F(L.qkv_inv));
     if (rc) return rc;
     rc = nystrom_core_impl(P3, batch, F(L.qkv16), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2),
-                           F(L.stats), F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, nullptr);
+                           F(L.stats), F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, nullptr, F(L.a3_part));
     if (rc) return rc;
     {
         StageScope scope(ST_SPLIT, st);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 10
+#define EDSNET_ABI_VERSION 11
 
 enum {
     EDSNET_OK = 0,
@@ -142,6 +142,8 @@ typedef struct {
                         * (u . w_cls, u . w_loc[0], u . w_loc[1], 0), the hidden rows are not written */
     size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
     size_t zeros;      /* [1024] zero bias (attention base: its projections have no bias) */
+    size_t a3_part;    /* tcgen05 precisions, few videos: per (video, head, key range) un-normalised rows of
+                        * softmax(q_land k^T) v with their running max / sum, [..][64][66], merged into a3v */
     size_t zstat;      /* EDSNET_PREC_FP16X3, Nystrom base: [rows][16][2] (sum z, sum z^2) per 64-column slot */
     size_t xstat;      /* EDSNET_PREC_FP16X3, Nystrom base: [rows][2] (mean, max|.|) of the input rows */
     size_t total;
@@ -278,6 +280,7 @@ typedef struct {
     size_t w_qkv16, w_out16, w_fc116, w_fcb16;   /* operand planes of the step's weights (edsnet_split_f16 layout)       */
     size_t qkv16, qkv_inv;                       /* q | k | v operand planes [rows][1536] hi, lo; scales [rows][24]      */
     size_t q_land, k_land, attn2, stats, a3v, zmat, wmat;   /* as in edsnet_workspace_layout                             */
+    size_t a3_part;                              /* key-range partials of a3v (few, long videos), as in the forward     */
     size_t merged;                               /* [rows][512] fp32: attention + value convolution, head-merged         */
     size_t y;                                    /* [rows][1024] to_out + bias + x                                      */
     size_t yn;                                   /* [rows][1024] LayerNorm(y)                                           */

@@ -265,6 +265,28 @@ def test_long_video_forward_c5_shape():
         assert max(e) < 5e-5, e       # fp32 reference itself sits ~1e-5 from fp64 at this length
 
 
+def test_few_long_videos_use_key_and_row_range_splits():
+    """A batch of few videos makes a3v stream its keys in several ranges per (video, head) (partials merged flash-decoding
+    style) and attn_out take row ranges: ragged lengths, a range count that does not divide the tile count, a video
+    shorter than one range.  Same rows as the one-video-per-call path, and the oracle."""
+    from edsnet_b200 import BatchPlan
+    scales = [4, 8]
+    p = orc.synth_params(33, "xavier")
+    lengths = [5000, 130, 64, 1999]
+    xs = [orc.synth_features(t, 700 + i) for i, t in enumerate(lengths)]
+    model = make_model(p, scales, 5, "fp16x3", DEV)
+    with torch.no_grad():
+        cls, loc = model.forward_packed(torch.cat(xs).to(DEV), BatchPlan.build(lengths).to(DEV))
+    _no_tc_timeout()
+    o = 0
+    for x, t in zip(xs, lengths):
+        with torch.no_grad():
+            rc, rl = orc.dsnet_forward(x, p, scales, 5)
+        e = max(orc.rel_l2(cls[o:o + t].cpu().numpy(), rc.numpy()), orc.rel_l2(loc[o:o + t].cpu().numpy(), rl.numpy()))
+        assert e < 3e-5, (t, e)          # fp32 reference itself is ~1e-5 from float64 at T = 5000
+        o += t
+
+
 # ------------------------------------------------------------------------------------------------ decode + NMS
 @pytest.mark.parametrize("name", list(DN["cases"]))
 def test_decode_nms_bit_exact_vs_reference_golden(name):
