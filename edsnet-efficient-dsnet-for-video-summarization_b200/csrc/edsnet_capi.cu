@@ -179,9 +179,15 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
 int a3v_split_cap(int n_videos) {                   // capacity the workspace is sized for
     return 4 * n_videos >= 74 ? 1 : (148 + 4 * n_videos - 1) / (4 * n_videos);
 }
-int a3v_splits(int n_videos, int max_rows) { return std::max(1, std::min(a3v_split_cap(n_videos), (max_rows + 63) / 64)); }
+// Only when the longest video has at least kSplitMinRows rows: below that every video is summed in ONE fixed order
+// whatever batch it travels in, which is what keeps a packed batch bit-identical to one-video-per-call scoring.
+constexpr int kSplitMinRows = 2048;
+int a3v_splits(int n_videos, int max_rows) {
+    if (max_rows < kSplitMinRows) return 1;
+    return std::max(1, std::min(a3v_split_cap(n_videos), (max_rows + 63) / 64));
+}
 int attn_out_splits(int n_videos, int max_rows) {
-    if (8 * n_videos >= 148) return 1;
+    if (8 * n_videos >= 148 || max_rows < kSplitMinRows) return 1;
     return std::max(1, std::min((296 + 8 * n_videos - 1) / (8 * n_videos), (max_rows + 127) / 128));
 }
 
