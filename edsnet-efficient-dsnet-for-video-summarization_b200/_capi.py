@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 11
+EDSNET_ABI_VERSION = 12
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -44,7 +44,7 @@ class Batch(C.Structure):
 
 
 LAYOUT_FIELDS = ("qkv", "q_land", "k_land", "attn2", "stats", "qkv_inv", "a3v", "zmat", "wmat", "merged", "y", "yn",
-                 "u0", "u1", "x16", "zeros", "a3_part", "zstat", "xstat", "total")
+                 "u0", "u1", "x16", "zeros", "mha16", "a3_part", "zstat", "xstat", "total")
 
 
 class WorkspaceLayout(C.Structure):

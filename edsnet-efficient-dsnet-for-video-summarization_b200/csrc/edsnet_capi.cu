@@ -15,6 +15,7 @@
 #include "fc_stack_tc.cuh"
 #include "attn_tc.cuh"
 #include "mha.cuh"
+#include "mha_tc.cuh"
 #include "nystrom.cuh"
 #include "tail.cuh"
 #include "decode_nms.cuh"
@@ -369,6 +370,8 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
     L.x16 = off;
     if (cfg && cfg->precision != EDSNET_PREC_FP32) take(split_f16_bytes(R, kFeat));
     L.zeros = take(kFeat * sizeof(float));
+    L.mha16 = off;
+    if (tcp && mha) L.mha16 = take(R * kMhaQkvCols * 4);           // q | k | v operand planes of the attention base (hi, lo)
     L.a3_part = off;
     if (tcp && !mha) L.a3_part = take(V * kHeads * (size_t)a3v_split_cap((int)V) * kLandmark * tc::kA3PartLd * sizeof(float));
     L.zstat = off;
@@ -525,13 +528,37 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         rc = gemm_dispatch(prec, EPI_NONE, x, x16, w->mha_qkv_w, w->mha_qkv_w16, F(L.qkv), R, kMhaQkvCols, kFeat,
                            nullptr, nullptr, 0, st);
         if (rc) return rc;
-        {
+        if (prec == EDSNET_PREC_FP32) {
             static const char mha_tag = 0;
             if (DeviceOnce once_{&mha_tag}) CU_CHECK(opt_in_smem(mha_flash_kernel, kMhaSmem), "smem opt-in mha_flash");
             StageScope scope(ST_A3V, st);
             mha_flash_kernel<<<dim3(batch->n_tiles64, kHeads), 256, kMhaSmem, st>>>(
                 F(L.qkv), batch->cu_rows, reinterpret_cast<const int2*>(batch->tiles64), F(L.merged));
             CU_CHECK(cudaGetLastError(), "mha_flash_kernel");
+        } else {
+            // tensor-core attention core: Q | K | V as operand planes (one scale per row and 128-column head slice), then
+            // flash attention with both contractions on tcgen05 (mha_tc.cuh)
+            static const char mhat_tag = 0;
+            if (DeviceOnce once_{&mhat_tag}) CU_CHECK(opt_in_smem(tc::mha_tc_kernel, tc::kMtSmemBytes), "smem opt-in mha_tc");
+            __half* p_hi = reinterpret_cast<__half*>(ws + L.mha16);
+            __half* p_lo = p_hi + (size_t)R * kMhaQkvCols;
+            {
+                StageScope scope(ST_LANDMARKS, st);
+                tc::mha_planes_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(L.qkv), p_hi, p_lo, F(L.qkv_inv), R);
+                CU_CHECK(cudaGetLastError(), "mha_planes_kernel");
+            }
+            CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo;
+            std::string msg;
+            if (!tc::make_map(&mq_hi, p_hi, (uint64_t)R, kMhaQkvCols, 64, 128, &msg) ||
+                !tc::make_map(&mq_lo, p_lo, (uint64_t)R, kMhaQkvCols, 64, 128, &msg) ||
+                !tc::make_map(&mk_hi, p_hi, (uint64_t)R, kMhaQkvCols, 64, 64, &msg) ||
+                !tc::make_map(&mk_lo, p_lo, (uint64_t)R, kMhaQkvCols, 64, 64, &msg))
+                return fail(EDSNET_E_CUDA, "mha: " + msg);
+            StageScope scope(ST_A3V, st);
+            tc::mha_tc_kernel<<<dim3(batch->n_tiles128, kHeads), 320, tc::kMtSmemBytes, st>>>(
+                mq_hi, mq_lo, mk_hi, mk_lo, F(L.qkv_inv), batch->cu_rows, reinterpret_cast<const int2*>(batch->tiles128),
+                F(L.merged));
+            CU_CHECK(cudaGetLastError(), "mha_tc_kernel");
         }
         const void* m16 = nullptr;
         if (prec != EDSNET_PREC_FP32) {
@@ -690,7 +717,7 @@ int edsnet_forward_launches(const edsnet_config* cfg) {
     // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add the operand split of x
     // (and of merged for the attention base) and run the value convolution as its own kernel; fp16x3 with the Nystrom
     // base has no LayerNorm kernel (folded into to_out's and fc1's epilogues)
-    if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 9;
+    if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 10;
     return cfg->precision == EDSNET_PREC_FP32 ? 11 : (cfg->precision == EDSNET_PREC_FP16 ? 13 : 12);
 }
 

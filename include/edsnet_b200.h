@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 11
+#define EDSNET_ABI_VERSION 12
 
 enum {
     EDSNET_OK = 0,
@@ -142,6 +142,7 @@ typedef struct {
                         * (u . w_cls, u . w_loc[0], u . w_loc[1], 0), the hidden rows are not written */
     size_t x16;        /* tcgen05 precisions: operand planes of the current GEMM's A   */
     size_t zeros;      /* [1024] zero bias (attention base: its projections have no bias) */
+    size_t mha16;      /* attention base, tcgen05 precisions: Q | K | V operand planes [rows][3072] hi, lo (scales in qkv_inv) */
     size_t a3_part;    /* tcgen05 precisions, few videos: per (video, head, key range) un-normalised rows of
                         * softmax(q_land k^T) v with their running max / sum, [..][64][66], merged into a3v */
     size_t zstat;      /* EDSNET_PREC_FP16X3, Nystrom base: [rows][16][2] (sum z, sum z^2) per 64-column slot */
