@@ -777,7 +777,7 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
         CU_CHECK(cudaGetLastError(), "nms_kernel");
         if (skip_large) {
             // videos with more than 4096 anchors: multi-CTA sort + blocked suppression, one video after the other;
-            // scratch offsets follow the same rule as the caller's table (32 bytes per anchor, power of two)
+            // scratch offsets follow the same rule as the caller's table (48 bytes per anchor, power of two)
             size_t off = 0;
             for (int v = 0; v < batch->n_videos; ++v) {
                 const long long row0 = batch->cu_rows_host[v];
@@ -786,10 +786,10 @@ int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const
                 size_t P = kNmsTile;
                 while ((long long)P < n) P <<= 1;
                 const size_t g0 = (size_t)row0 * cfg->n_scales;
-                CU_CHECK(launch_nms_large(pred_cls + g0, boxes_i32 + 2 * g0, (int)n, nms_thresh,
+                CU_CHECK(launch_nms_large(pred_cls + g0, boxes_i32 + 2 * g0, (int)n, (int)(n / cfg->n_scales), nms_thresh,
                                           static_cast<unsigned char*>(nms_scratch) + off, keep_count + v, keep_idx + g0,
                                           keep_scores + g0, keep_boxes + 2 * g0, st), "nms_large");
-                off += 32 * P;
+                off += (size_t)kNmsScratchPerAnchor * P;
             }
         }
     }

@@ -67,10 +67,10 @@ class BatchPlan:
 
     def nms_scratch(self, n_scales: int):
         """Byte offsets (int64 [V]) and total bytes of the global NMS scratch, needed only by videos with more than
-        4096 anchors (edsnet_decode_nms contract: 32 bytes per anchor rounded up to a power of two)."""
+        4096 anchors (edsnet_decode_nms contract: 48 bytes per anchor rounded up to a power of two)."""
         n = self.lengths * int(n_scales)
         p = np.where(n > 4096, 2 ** np.ceil(np.log2(np.maximum(n, 1))).astype(np.int64), 0)
-        sizes = p * 32
+        sizes = p * 48
         off = np.cumsum(sizes) - sizes
         return off.astype(np.int64), int(sizes.sum())
 

@@ -169,7 +169,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
  *   keep_count [dev][n_videos]; keep_idx / keep_scores / keep_boxes are [dev] arrays of total_rows*S entries,
  *   the kept proposals of video v (descending score) start at entry cu_rows[v]*S; keep_idx is the flat
  *   anchor index t*S+s inside the video.
- *   Videos with more than 4096 anchors need scratch: 32 bytes per anchor, anchors rounded up to a power of two,
+ *   Videos with more than 4096 anchors need scratch: 48 bytes per anchor, anchors rounded up to a power of two,
  *   video after video in batch order; nms_scratch_off [dev][n_videos] are those byte offsets (only read when
  *   batch->cu_rows_host is NULL).  Both may be NULL when no video is that long. */
 int edsnet_decode_nms(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_cls,

@@ -389,6 +389,27 @@ def test_nms_packed_many_videos_vs_oracle():
         o += t
 
 
+def test_nms_large_deep_suppression_chain():
+    """Worst case for the fixpoint NMS of the > 4096-anchor path: identical boxes shifted by one position with scores that
+    fall along the timeline form ONE suppression chain thousands of levels deep (box t is decided only after box t - 1 ...),
+    far beyond the fixed number of parallel rounds -- the ordered clean-up pass must finish it, bit-exact."""
+    from edsnet_b200 import BatchPlan
+    T, scales = 6000, [10]
+    p = orc.synth_params(1, "default")
+    model = make_model(p, scales, 5, "fp32", DEV)
+    batch = BatchPlan.build([T]).to(DEV)
+    loc = np.zeros((T, 1, 2), dtype=np.float32)                      # every box = its anchor: [t - 5, t + 5) clipped
+    scores = np.linspace(0.99, 0.01, T).astype(np.float32)
+    for thresh in (0.5, 0.3):
+        r = model.nms_packed(torch.from_numpy(scores).to(DEV).reshape(T, 1), torch.from_numpy(loc).to(DEV), batch, thresh)
+        k = int(r["keep_count"].cpu()[0])
+        boxes = orc.clip_round(orc.decode_boxes(loc, T, scales, exp_mode="cr"), T)
+        rs, rb, ridx = orc.nms_1d(scores, boxes, thresh)
+        assert k == len(rs) and k > 500
+        assert np.array_equal(r["keep_idx"][:k].cpu().numpy(), ridx.astype(np.int32))
+        assert np.array_equal(r["keep_boxes"][:k].cpu().numpy(), rb) and np.array_equal(r["keep_scores"][:k].cpu().numpy(), rs)
+
+
 def test_nms_properties_at_full_size():
     """C5-size NMS (65536 anchors): kept boxes are mutually below the threshold, scores descend, every dropped
     valid box is suppressed by some kept box of higher-or-equal score, and NMS of the kept set is the identity."""

@@ -70,7 +70,7 @@ def test_batch_plan_tables():
     assert plan.tiles128.tolist() == [[0, 0], [1, 0], [2, 0], [3, 0], [3, 128], [3, 256]]
     assert plan.n_videos == 4 and plan.total_rows == 430 and plan.max_rows == 300
     off, total = BatchPlan.build([100, 2000, 5000]).nms_scratch(4)
-    assert off.tolist() == [0, 0, 8192 * 32] and total == (8192 + 32768) * 32
+    assert off.tolist() == [0, 0, 8192 * 48] and total == (8192 + 32768) * 48
     with pytest.raises(ValueError):
         BatchPlan.build([])
     with pytest.raises(ValueError):
