@@ -1,5 +1,5 @@
 """One forward + decode + NMS of a bench-shaped packed batch between cudaProfilerStart/Stop, for
-`ncu --profile-from-start off --set full --import-source on -o ... python tools/profile_forward.py [videos]`
+`ncu --profile-from-start off --set full --import-source on -o ... python tools/profile_forward.py [videos] [precision]`
 (the kernel list is then exactly one forward, independent of how many launches the weight preparation needs)."""
 import os
 import sys
@@ -19,7 +19,7 @@ def main():
     lengths = bench.workload_lengths(0, videos)
     R = int(sum(lengths))
     model = bench.xavier_state([12]).to(dev).eval()
-    model.precision = "fp16x3"
+    model.precision = sys.argv[2] if len(sys.argv) > 2 else "fp16x2"
     x = bench.synth_features_device(R, dev, bench.SEED + 1000)
     plan = BatchPlan.build(lengths).to(dev)
     with torch.no_grad():
@@ -32,7 +32,7 @@ def main():
         model.nms_packed(cls, loc, plan, bench.NMS_THRESH)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-    print(f"profiled one forward of {videos} videos, {R} rows")
+    print(f"profiled one forward of {videos} videos, {R} rows, precision {model.precision}")
 
 
 if __name__ == "__main__":
