@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 12
+EDSNET_ABI_VERSION = 13
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -62,7 +62,7 @@ class Grads(C.Structure):
 TRAIN_LAYOUT_FIELDS = ("w_qkv16", "w_out16", "w_fc116", "w_fcb16", "qkv16", "qkv_inv", "q_land", "k_land", "attn2", "stats",
                        "a3v", "zmat", "wmat", "a3_part", "merged", "y", "yn", "uin", "hs", "u_last", "heads", "qkv_f32", "dqkv", "m3",
                        "l3", "acc0", "acc_bytes", "dw_att", "dkl", "dql", "db_att", "da2", "cmax", "dc_part", "zhist", "g", "d_logit",
-                       "das", "du0", "dyn", "dy", "dmerged", "t_a", "t_b", "total")
+                       "das", "du0", "dyn", "dy", "dmerged", "t_a", "t_b", "t_c", "t_d", "total")
 
 
 class TrainLayout(C.Structure):
@@ -110,7 +110,7 @@ SYMBOLS = {
     "edsnet_loss_grad": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P,
                                    _P]),
     "edsnet_train_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(Batch), _P, _P, _P, _P, C.c_int32,
-                                        C.c_int32, C.POINTER(Grads), _P, C.c_size_t, _P]),
+                                        C.c_int32, C.POINTER(Grads), _P, C.c_size_t, _P, _P]),
     "edsnet_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int64, C.c_float, _P]),
     "edsnet_split_f16_t": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),

@@ -956,7 +956,8 @@ __global__ void __launch_bounds__(320, 1)
 value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                      const float* __restrict__ inv, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
                      const float* __restrict__ conv_w, const float* __restrict__ attn, const float* __restrict__ w_max,
-                     __half* __restrict__ m_hi, __half* __restrict__ m_lo, float* __restrict__ m_inv) {
+                     __half* __restrict__ m_hi, __half* __restrict__ m_lo, float* __restrict__ m_inv, int write_lo) {
+    // write_lo == 0: the to_out product that follows runs two passes (A_hi only): the lo plane is not written
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
@@ -1154,7 +1155,7 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
                     if (rw < vi.T) {
                         const size_t oo = (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + half * 32 + q * 16 + cc * 4;
                         *reinterpret_cast<uint2*>(m_hi + oo) = *reinterpret_cast<uint2*>(hh);
-                        *reinterpret_cast<uint2*>(m_lo + oo) = *reinterpret_cast<uint2*>(ll);
+                        if (write_lo) *reinterpret_cast<uint2*>(m_lo + oo) = *reinterpret_cast<uint2*>(ll);
                     }
                 }
                 __syncwarp();

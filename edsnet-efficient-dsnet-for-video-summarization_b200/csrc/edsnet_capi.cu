@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -195,7 +197,7 @@ int attn_out_splits(int n_videos, int max_rows) {
 int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, const float* qkv_inv,
                       const float* conv_w, float* q_land, float* k_land, float* attn2, float* stats, float* a3v,
                       float* zmat, float* wmat, float* merged, cudaStream_t st, void* merged16 = nullptr,
-                      float* a3_part = nullptr) {
+                      float* a3_part = nullptr, bool merged_lo = true) {
     // merged16 != nullptr (tcgen05 precisions, edsnet_forward): `merged` only carries the attention part and the sum
     // with the value convolution leaves as the to_out operand planes in merged16 (edsnet_split_f16 layout, 512 columns)
     const bool tcp = precision != EDSNET_PREC_FP32;
@@ -280,7 +282,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
                     return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
                 tc::value_conv_tc_kernel<<<b->n_tiles128, 320, tc::kCvSmemBytes, st>>>(
                     map32_hi, map32_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged,
-                    stats, m_hi, m_lo, m_inv);
+                    stats, m_hi, m_lo, m_inv, merged_lo ? 1 : 0);
             }
         } else {
             tc::value_conv_kernel<<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
@@ -581,7 +583,7 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
         void* merged16_out = prec != EDSNET_PREC_FP32 ? static_cast<void*>(ws + L.x16) : nullptr;
         rc = nystrom_core_impl(prec, batch, F(L.qkv), F(L.qkv_inv), w->res_conv_w, F(L.q_land), F(L.k_land), F(L.attn2), F(L.stats),
                                F(L.a3v), F(L.zmat), F(L.wmat), F(L.merged), st, merged16_out,
-                               prec != EDSNET_PREC_FP32 ? F(L.a3_part) : nullptr);
+                               prec != EDSNET_PREC_FP32 ? F(L.a3_part) : nullptr, /*merged_lo=*/prec != EDSNET_PREC_FP16X2);
         if (rc) return rc;
         // 3. y = merged Wout^T + b + x                                              (nystroformer.py:143, dsnet.py:105)
         //    (fp16x3: z = y - mean(x row) - mean(bias) leaves as the fc1 operand planes with the row sums LayerNorm needs; step 4
@@ -854,7 +856,7 @@ void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos
     L.db_att = take(head_mat);
     L.da2 = take(head_mat);
     L.dc_part = take(V * kHeads * sizeof(float));
-    L.zhist = take(head_mat * kPinvIters * 4);
+    L.zhist = take(head_mat * (kPinvIters * 4 + 1));
     L.g = take(R * 4 * sizeof(float));
     L.d_logit = take(R * S * sizeof(float));
     L.das = take(std::max<size_t>(D, 1) * R * kHidden * sizeof(float));
@@ -866,8 +868,30 @@ void train_layout(const edsnet_config* cfg, int32_t total_rows, int32_t n_videos
     L.t_a = take(std::max(std::max(planes_bytes(kQkvCols, Rp), planes_bytes(kHidden, K5)), planes_bytes(R, kFeat)));
     L.t_b = take(std::max(std::max(planes_bytes(kFeat, Rp), planes_bytes(kHidden, K5)),
                           std::max(planes_bytes(kFeat, kHidden), planes_bytes(kInner, kFeat))));
+    // second pair for the weight-gradient products that run on the side stream next to the dX chain
+    L.t_c = take(std::max(std::max(planes_bytes(kHidden, K5), planes_bytes(kHidden, Rp)), planes_bytes(kFeat, Rp)));
+    L.t_d = take(std::max(std::max(planes_bytes(kHidden, K5), planes_bytes(kFeat, Rp)), planes_bytes(kInner, Rp)));
     L.total = off;
     *out = L;
+}
+
+// events that fork / join the backward's side stream: one set per device, created on first use
+struct SideEvents { cudaEvent_t fork, fc, ln, hist, done; };
+SideEvents* side_events() {
+    static std::mutex m;
+    static std::map<int, SideEvents> pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(m);
+    auto it = pool.find(dev);
+    if (it == pool.end()) {
+        SideEvents ev;
+        cudaEvent_t* e[5] = {&ev.fork, &ev.fc, &ev.ln, &ev.hist, &ev.done};
+        for (auto* p : e)
+            if (cudaEventCreateWithFlags(p, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        it = pool.emplace(dev, ev).first;
+    }
+    return &it->second;
 }
 
 SplitTJob split_t_job(const float* src, int rows, int cols, int ld, void* planes, int* cta, unsigned** cmax) {
@@ -928,7 +952,7 @@ size_t edsnet_train_workspace_bytes(const edsnet_config* cfg, int32_t total_rows
 int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* backward) {
     if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
     if (forward) *forward = 4 + 1 + 1 + 6 + 1 + 1 + 1 + 1 + 1 + 1 + 1;       // weight planes, split, qkv, core, ..., roi
-    if (backward) *backward = 36;
+    if (backward) *backward = 37;
     return EDSNET_OK;
 }
 
@@ -1034,7 +1058,7 @@ int edsnet_loss_grad(const edsnet_config* cfg, const edsnet_batch* batch, const 
 int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
                           const float* pred_cls, const float* d_cls, const float* d_loc, int32_t d_cls_is_logit_grad,
                           int32_t dropout, const edsnet_grads* grads, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+                          void* stream, void* side_stream) {
     int rc = check_train_cfg(cfg);
     if (rc) return rc;
     rc = check_batch(batch);
@@ -1060,10 +1084,27 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
         CU_CHECK(opt_in_smem(fc_stack_bwd_kernel, kFcBwdSmem), "smem opt-in fc_stack_bwd");
         CU_CHECK(opt_in_smem(attn_bwd_rows_kernel, kAttnBwdRowsSmem), "smem opt-in attn_bwd_rows");
         CU_CHECK(opt_in_smem(pinv_bwd_kernel, kPinvBwdSmem), "smem opt-in pinv_bwd");
+        CU_CHECK(opt_in_smem(pinv_hist_kernel, kPinvHistSmem), "smem opt-in pinv_hist");
         CU_CHECK(opt_in_smem(attn2_bwd_kernel, 4 * 64 * kLd64 * (int)sizeof(float)), "smem opt-in attn2_bwd");
         CU_CHECK(opt_in_smem(attn_bwd_keys_kernel, kAttnBwdKeysSmem), "smem opt-in attn_bwd_keys");
     }
     CU_CHECK(cudaMemsetAsync(ws + L.acc0, 0, L.acc_bytes, st), "zero attention accumulators");
+    // Side stream (optional): what nothing downstream of the dX chain waits for -- the forward chain of the pseudo-inverse
+    // (needed only by pinv_bwd) and the three weight-gradient products of the tail -- runs next to the chain.
+    cudaStream_t ss = side_stream ? static_cast<cudaStream_t>(side_stream) : st;
+    const bool par = ss != st;
+    SideEvents* ev = par ? side_events() : nullptr;
+    if (par && !ev) return fail(EDSNET_E_CUDA, "train_backward: could not create the side-stream events");
+    if (par) {
+        CU_CHECK(cudaEventRecord(ev->fork, st), "fork event");
+        CU_CHECK(cudaStreamWaitEvent(ss, ev->fork, 0), "fork wait");
+    }
+    {
+        StageScope scope(ST_T_PINV_BWD, ss);
+        pinv_hist_kernel<<<dim3(kHeads, V), kPinvBwdThreads, kPinvHistSmem, ss>>>(F(L.attn2), F(L.stats), F(L.zhist), kPinvIters);
+        CU_CHECK(cudaGetLastError(), "pinv_hist_kernel");
+    }
+    if (par) CU_CHECK(cudaEventRecord(ev->hist, ss), "hist event");
     // 1. d logits
     const float* d_logit = d_cls;
     if (!d_cls_is_logit_grad) {
@@ -1093,23 +1134,27 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     SplitTJob jobs[4];
     int cta;
     unsigned* cm = reinterpret_cast<unsigned*>(ws + L.cmax);
-    // 4. d fc_block.0.weight = sum_l da_l^T u_l  (one product with K = D x rows)
+    if (par) {
+        CU_CHECK(cudaEventRecord(ev->fc, st), "fc event");
+        CU_CHECK(cudaStreamWaitEvent(ss, ev->fc, 0), "fc wait");
+    }
+    // 4. d fc_block.0.weight = sum_l da_l^T u_l  (one product with K = D x rows)                      [side stream]
     cta = 0;
-    jobs[0] = split_t_job(F(L.das), D * R, kHidden, kHidden, ws + L.t_a, &cta, &cm);
-    jobs[1] = split_t_job(F(L.uin), D * R, kHidden, kHidden, ws + L.t_b, &cta, &cm);
-    rc = launch_split_t(jobs, 2, cta, st);
+    jobs[0] = split_t_job(F(L.das), D * R, kHidden, kHidden, ws + L.t_c, &cta, &cm);
+    jobs[1] = split_t_job(F(L.uin), D * R, kHidden, kHidden, ws + L.t_d, &cta, &cm);
+    rc = launch_split_t(jobs, 2, cta, ss);
     if (rc) return rc;
-    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fcb_w, kHidden, kHidden, K5, nullptr,
-                       nullptr, 0, st, ST_T_GEMM_DW);
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_c, nullptr, ws + L.t_d, grads->fcb_w, kHidden, kHidden, K5, nullptr,
+                       nullptr, 0, ss, ST_T_GEMM_DW);
     if (rc) return rc;
-    // 5. d fc1.weight = du0^T LN(y)
+    // 5. d fc1.weight = du0^T LN(y)                                                                    [side stream]
     cta = 0;
-    jobs[0] = split_t_job(F(L.du0), R, kHidden, kHidden, ws + L.t_a, &cta, &cm);
-    jobs[1] = split_t_job(F(L.yn), R, kFeat, kFeat, ws + L.t_b, &cta, &cm);
-    rc = launch_split_t(jobs, 2, cta, st);
+    jobs[0] = split_t_job(F(L.du0), R, kHidden, kHidden, ws + L.t_c, &cta, &cm);
+    jobs[1] = split_t_job(F(L.yn), R, kFeat, kFeat, ws + L.t_d, &cta, &cm);
+    rc = launch_split_t(jobs, 2, cta, ss);
     if (rc) return rc;
-    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->fc1_w, kHidden, kFeat, Rp, nullptr,
-                       nullptr, 0, st, ST_T_GEMM_DW);
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_c, nullptr, ws + L.t_d, grads->fc1_w, kHidden, kFeat, Rp, nullptr,
+                       nullptr, 0, ss, ST_T_GEMM_DW);
     if (rc) return rc;
     // 6. d LN(y) = du0 W1
     {
@@ -1130,15 +1175,20 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
                                                         grads->to_out_b);
         CU_CHECK(cudaGetLastError(), "ln1024_bwd_kernel");
     }
-    // 8. d to_out.weight = dy^T merged
+    if (par) {
+        CU_CHECK(cudaEventRecord(ev->ln, st), "ln event");
+        CU_CHECK(cudaStreamWaitEvent(ss, ev->ln, 0), "ln wait");
+    }
+    // 8. d to_out.weight = dy^T merged                                                                 [side stream]
     cta = 0;
-    jobs[0] = split_t_job(F(L.dy), R, kFeat, kFeat, ws + L.t_a, &cta, &cm);
-    jobs[1] = split_t_job(F(L.merged), R, kInner, kInner, ws + L.t_b, &cta, &cm);
-    rc = launch_split_t(jobs, 2, cta, st);
+    jobs[0] = split_t_job(F(L.dy), R, kFeat, kFeat, ws + L.t_c, &cta, &cm);
+    jobs[1] = split_t_job(F(L.merged), R, kInner, kInner, ws + L.t_d, &cta, &cm);
+    rc = launch_split_t(jobs, 2, cta, ss);
     if (rc) return rc;
-    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_out_w, kFeat, kInner, Rp, nullptr,
-                       nullptr, 0, st, ST_T_GEMM_DW);
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_c, nullptr, ws + L.t_d, grads->to_out_w, kFeat, kInner, Rp, nullptr,
+                       nullptr, 0, ss, ST_T_GEMM_DW);
     if (rc) return rc;
+    if (par) CU_CHECK(cudaEventRecord(ev->done, ss), "side done event");
     // 9. d merged = dy Wout
     {
         StageScope scope(ST_T_SPLIT, st);
@@ -1168,6 +1218,7 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
             F(L.dkl), grads->res_conv_w);
         CU_CHECK(cudaGetLastError(), "attn_bwd_rows_kernel");
     }
+    if (par) CU_CHECK(cudaStreamWaitEvent(st, ev->hist, 0), "hist wait");
     {
         StageScope scope(ST_T_PINV_BWD, st);
         pinv_bwd_kernel<<<dim3(kHeads, V), kPinvBwdThreads, kPinvBwdSmem, st>>>(F(L.attn2), F(L.stats), F(L.a3v), F(L.dw_att), F(L.zhist),
@@ -1197,8 +1248,11 @@ int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, con
     jobs[1] = split_t_job(x, R, kFeat, kFeat, ws + L.t_b, &cta, &cm);
     rc = launch_split_t(jobs, 2, cta, st);
     if (rc) return rc;
-    return gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_qkv_w, kQkvCols, kFeat, Rp, nullptr,
-                         nullptr, 0, st, ST_T_GEMM_DW);
+    rc = gemm_dispatch(P3, EPI_NONE, nullptr, ws + L.t_a, nullptr, ws + L.t_b, grads->to_qkv_w, kQkvCols, kFeat, Rp, nullptr,
+                       nullptr, 0, st, ST_T_GEMM_DW);
+    if (rc) return rc;
+    if (par) CU_CHECK(cudaStreamWaitEvent(st, ev->done, 0), "side join");
+    return EDSNET_OK;
 }
 
 int edsnet_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

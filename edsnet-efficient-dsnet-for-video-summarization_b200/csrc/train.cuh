@@ -928,18 +928,30 @@ attn_bwd_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ dm
     }
 }
 
-// pinv kernel: one CTA per (video, head); grid (8, V), 512 threads (two rows per thread: a dependent chain of 64^3 products
+// pinv kernels: one CTA per (video, head); grid (8, V), 512 threads (two rows per thread: a dependent chain of 64^3 products
 // on ONE SM is bound by how well the FFMA latency is hidden).  attn2 = A, a3v = B, stats as attn2_kernel wrote them.
-// hist [V][8][iters][4][64][64]: Z_k (input of iteration k), P_k = A Z_k, T2_k, T3_k of the forward chain, which is
-// recomputed here in fp32; the reverse sweep reads them back (L2) instead of recomputing three products per iteration.
+//   pinv_hist_kernel  recomputes the forward chain in fp32 and keeps Z_k (input of iteration k), P_k = A Z_k, T2_k, T3_k
+//                     and the final Z: hist [V][8][iters * 4 + 1][64][64].  It depends on the forward only, so the
+//                     backward runs it on its side stream under the kernels in front of the attention block.
+//   pinv_bwd_kernel   dZ = dW B^T, dB = Z^T dW, then the iterations in reverse, reading the kept tiles back (L2) instead of
+//                     recomputing three products per iteration.
 // Outputs: dB [V][8][64][64], dA2 (without the start-scale term) [V][8][64][64], dc_part [V][8].
 constexpr int kPinvBwdThreads = 512;
+constexpr int kPinvHistSmem = 7 * 64 * kLd64 * (int)sizeof(float);
 constexpr int kPinvBwdSmem = (11 * 64 * kLd64 + 16) * (int)sizeof(float);
 
+__device__ __forceinline__ float pinv_start_scale(const float* __restrict__ stats, int v) {
+    float mrow = 0.f, mcol = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < kHeads; ++hh) {
+        mrow = fmaxf(mrow, __ldg(stats + ((size_t)v * kHeads + hh) * 2 + 0));
+        mcol = fmaxf(mcol, __ldg(stats + ((size_t)v * kHeads + hh) * 2 + 1));
+    }
+    return mrow * mcol;
+}
+
 __global__ void __launch_bounds__(kPinvBwdThreads)
-pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
-                const float* __restrict__ dW, float* __restrict__ hist, float* __restrict__ dB, float* __restrict__ dA2,
-                float* __restrict__ dc_part, int iters) {
+pinv_hist_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, float* __restrict__ hist, int iters) {
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Zs = As + 64 * kLd64;
@@ -947,24 +959,12 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
     float* T1 = Pz + 64 * kLd64;
     float* T2 = T1 + 64 * kLd64;
     float* T3 = T2 + 64 * kLd64;
-    float* dZ = T3 + 64 * kLd64;
-    float* Zn = dZ + 64 * kLd64;
-    float* Us = Zn + 64 * kLd64;
-    float* Vs = Us + 64 * kLd64;
-    float* DP = Vs + 64 * kLd64;
-    float* red = DP + 64 * kLd64;
+    float* Zn = T3 + 64 * kLd64;
     constexpr int RT = 2, NT = kPinvBwdThreads;
     const int h = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const size_t off = ((size_t)v * kHeads + h) * 4096;
-    float* hs = hist + off * iters * 4;
-
-    float mrow = 0.f, mcol = 0.f;
-#pragma unroll
-    for (int hh = 0; hh < kHeads; ++hh) {
-        mrow = fmaxf(mrow, __ldg(stats + ((size_t)v * kHeads + hh) * 2 + 0));
-        mcol = fmaxf(mcol, __ldg(stats + ((size_t)v * kHeads + hh) * 2 + 1));
-    }
-    const float denom = mrow * mcol;
+    float* hs = hist + off * (iters * 4 + 1);
+    const float denom = pinv_start_scale(stats, v);
     for (int idx = tid; idx < 1024; idx += NT) {
         const int r = idx >> 4, c4 = (idx & 15) * 4;
         const float4 a = ldg4(attn2 + off + r * 64 + c4);
@@ -973,7 +973,6 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
         Zs[(c4 + 2) * kLd64 + r] = a.z / denom; Zs[(c4 + 3) * kLd64 + r] = a.w / denom;
     }
     __syncthreads();
-    // ---- forward chain, keeping Z_k, P_k, T2_k, T3_k ----
     for (int k = 0; k < iters; ++k) {
         float* hk = hs + (size_t)k * 4 * 4096;
         tile_store(hk, Zs, tid, NT);
@@ -995,7 +994,34 @@ pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats
         __syncthreads();
         float* t = Zs; Zs = Zn; Zn = t;
     }
+    tile_store(hs + (size_t)iters * 4 * 4096, Zs, tid, NT);
+}
+
+__global__ void __launch_bounds__(kPinvBwdThreads)
+pinv_bwd_kernel(const float* __restrict__ attn2, const float* __restrict__ stats, const float* __restrict__ a3v,
+                const float* __restrict__ dW, const float* __restrict__ hist, float* __restrict__ dB,
+                float* __restrict__ dA2, float* __restrict__ dc_part, int iters) {
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;
+    float* Zs = As + 64 * kLd64;
+    float* Pz = Zs + 64 * kLd64;
+    float* T1 = Pz + 64 * kLd64;
+    float* T2 = T1 + 64 * kLd64;
+    float* T3 = T2 + 64 * kLd64;
+    float* dZ = T3 + 64 * kLd64;
+    float* Zn = dZ + 64 * kLd64;
+    float* Us = Zn + 64 * kLd64;
+    float* Vs = Us + 64 * kLd64;
+    float* DP = Vs + 64 * kLd64;
+    float* red = DP + 64 * kLd64;
+    constexpr int RT = 2, NT = kPinvBwdThreads;
+    const int h = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const size_t off = ((size_t)v * kHeads + h) * 4096;
+    const float* hs = hist + off * (iters * 4 + 1);
+    const float denom = pinv_start_scale(stats, v);
     // ---- W = Z B:  dZ = dW B^T,  dB = Z^T dW ----
+    tile_load(As, attn2 + off, tid, NT);
+    tile_load(Zs, hs + (size_t)iters * 4 * 4096, tid, NT);
     tile_load(Us, a3v + off, tid, NT);
     tile_load(Vs, dW + off, tid, NT);
     __syncthreads();

@@ -122,8 +122,10 @@ def loss_and_grad(ctx: TrainContext, cls_label: torch.Tensor, loc_label: torch.T
     return loss, d_logit, d_loc
 
 
-def train_backward(ctx: TrainContext, d_cls: torch.Tensor, d_loc: torch.Tensor, grads: dict, logit_grad: bool) -> None:
-    """grads: {edsnet_weights field name: ZERO-filled float32 tensor of the parameter's shape}; filled on return."""
+def train_backward(ctx: TrainContext, d_cls: torch.Tensor, d_loc: torch.Tensor, grads: dict, logit_grad: bool,
+                   side_stream: Optional[torch.cuda.Stream] = None) -> None:
+    """grads: {edsnet_weights field name: ZERO-filled float32 tensor of the parameter's shape}; filled on return.
+    side_stream: second stream for the independent part of the backward (forked / joined inside the call)."""
     dev = ctx.x.device
     d_cls, d_loc = d_cls.contiguous(), d_loc.contiguous()
     if d_cls.dtype != torch.float32 or d_loc.dtype != torch.float32:
@@ -134,7 +136,10 @@ def train_backward(ctx: TrainContext, d_cls: torch.Tensor, d_loc: torch.Tensor, 
         _capi.check(_capi.lib().edsnet_train_backward(ctx.cfg, ctx.weights, ctx.batch.struct, ctx.x.data_ptr(),
                                                       ctx.pred_cls.data_ptr(), d_cls.data_ptr(), d_loc.data_ptr(),
                                                       1 if logit_grad else 0, 1 if ctx.dropout else 0, g,
-                                                      ctx.workspace.data_ptr(), ctx.workspace.numel(), stream))
+                                                      ctx.workspace.data_ptr(), ctx.workspace.numel(), stream,
+                                                      side_stream.cuda_stream if side_stream is not None else None))
+        # (the call joins the side stream back into `stream` before it returns: stream order on `stream` alone keeps the
+        # workspace and the gradient buffers safe)
 
 
 class _NativeScoring(torch.autograd.Function):
@@ -259,6 +264,7 @@ class NativeDataParallelStep:
         self._seen = set()
         self._offset_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._side = torch.cuda.Stream(dev)
+        self._bwd_side = torch.cuda.Stream(dev)        # independent part of the backward (pinv chain re-run, dW products)
         self.graph_replays = 0
         fwd, bwd = C.c_int32(0), C.c_int32(0)
         _capi.check(_capi.lib().edsnet_train_launches(model._config(), C.byref(fwd), C.byref(bwd)))
@@ -278,7 +284,7 @@ class NativeDataParallelStep:
         self.flat_grad.zero_()
         ctx = train_forward(self.model, x, batch, self.dropout, self.seed, offset, offset_dev)
         loss, d_logit, d_loc = loss_and_grad(ctx, cl, ll, self.lambda_reg, 1.0 / k)
-        train_backward(ctx, d_logit, d_loc, self.grad_views, logit_grad=True)
+        train_backward(ctx, d_logit, d_loc, self.grad_views, logit_grad=True, side_stream=self._bwd_side)
         return ctx, loss, d_logit, d_loc
 
     def backward_only(self, seqs: Sequence[torch.Tensor], cls_labels, loc_labels) -> torch.Tensor:

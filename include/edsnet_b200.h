@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 12
+#define EDSNET_ABI_VERSION 13
 
 enum {
     EDSNET_OK = 0,
@@ -296,12 +296,13 @@ typedef struct {
     size_t dw_att, dkl, dql, db_att, da2;        /* [videos][8][64][64] each                                            */
     size_t cmax;                                 /* column maxima of the transposed operand splits (uint bit patterns)   */
     size_t dc_part;                              /* [videos][8] gradient of the pseudo-inverse start scale, per head     */
-    size_t zhist;                                /* [videos][8][6][4][64][64] Z_k, A Z_k, T2_k, T3_k of the pinv chain   */
+    size_t zhist;                                /* [videos][8][6 * 4 + 1][64][64] Z_k, A Z_k, T2_k, T3_k of the pinv chain, Z */
     size_t g;                                    /* [rows][4] gradient of the head projections                           */
     size_t d_logit;                              /* [rows][S]                                                            */
     size_t das;                                  /* [depth][rows][128] gradient of every Linear output of the fc block   */
     size_t du0, dyn, dy, dmerged;                /* [rows][128], [rows][1024], [rows][1024], [rows][512]                 */
     size_t t_a, t_b;                             /* operand-plane scratch of the backward GEMMs                          */
+    size_t t_c, t_d;                             /* the same for the weight-gradient products on the side stream         */
     size_t total;
 } edsnet_train_layout;
 
@@ -332,11 +333,15 @@ int edsnet_loss_grad(const edsnet_config* cfg, const edsnet_batch* batch, const 
 
 /* loss.backward(): parameter gradients from d loss / d outputs.  d_cls is either the gradient with respect to the
  * logits (d_cls_is_logit_grad != 0, what edsnet_loss_grad writes) or with respect to pred_cls after the sigmoid (what
- * torch.autograd hands over); pred_cls = the forward's output; dropout = the forward's flag; workspace = the forward's. */
+ * torch.autograd hands over); pred_cls = the forward's output; dropout = the forward's flag; workspace = the forward's.
+ * side_stream (may be NULL): a second stream of the same device on which the work nothing else waits for -- the fp32
+ * re-run of the pseudo-inverse chain and the three weight-gradient products of the tail -- runs next to the dX chain;
+ * it is forked from and joined back into `stream` with events inside the call (capturable into a CUDA graph), so the
+ * caller never synchronises it.  The events are per device: one call at a time per device when a side stream is given. */
 int edsnet_train_backward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch, const float* x,
                           const float* pred_cls, const float* d_cls, const float* d_loc, int32_t d_cls_is_logit_grad,
                           int32_t dropout, const edsnet_grads* grads, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          void* stream, void* side_stream);
 
 /* torch.optim.Adam(lr, betas, eps, weight_decay) (anchor_based/train.py:53-55) on flat fp32 buffers of n values; the
  * gradient is multiplied by grad_scale first (1 / world size after a summing all-reduce); step counts from 1. */
