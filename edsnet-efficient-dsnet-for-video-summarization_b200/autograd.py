@@ -1,10 +1,11 @@
-"""Differentiable path of the scoring model (used when gradients are required or the module is in train() mode).
+"""Torch-op graph of the scoring model, kept for the two cases that are NOT on the hot path.
 
-The inference path is hand-written CUDA behind the C ABI and is not differentiable.  Training (SURVEY.md §8 f /
-config 3) is the next row to be built natively; until then gradients come from this torch-op graph, which runs on
-the GPU, is numerically the same function (same parameter tensors, same operation order as
-src/transformer/nystroformer.py:67-150 and src/anchor_based/dsnet.py:100-115) and supports the train-mode
-Dropout(0.5) of the shared fc block.  It is never used when `torch.no_grad()` + `eval()` hold (evaluate.py:15-17).
+Training of the Nystrom model runs on the native kernels (native_train.py,
+csrc/train.cuh).  This graph remains for (i) the comparison base ('attention', BASELINE config 4) in train() mode and
+(ii) gradients with respect to the INPUT features.  It runs on the GPU, is numerically the same function (same
+parameter tensors, same operation order as src/transformer/nystroformer.py:67-150 and
+src/anchor_based/dsnet.py:100-115) and supports the train-mode Dropout(0.5) of the shared fc block.  It is never used
+when `torch.no_grad()` + `eval()` hold (evaluate.py:15-17).
 """
 from __future__ import annotations
 
