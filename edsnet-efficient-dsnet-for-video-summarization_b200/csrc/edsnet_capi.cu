@@ -16,6 +16,7 @@
 #include "gemm_tc2.cuh"
 #include "fc_stack_tc.cuh"
 #include "attn_tc.cuh"
+#include "pinv_tc.cuh"
 #include "mha.cuh"
 #include "mha_tc.cuh"
 #include "nystrom.cuh"
@@ -217,6 +218,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
             CU_CHECK(opt_in_smem(tc::value_conv_kernel, tc::kConvSmemBytes), "smem opt-in value_conv");
             CU_CHECK(opt_in_smem(tc::value_conv_tc_kernel, tc::kCvSmemBytes), "smem opt-in value_conv_tc");
             CU_CHECK(opt_in_smem(tc::pinv_w_tc_kernel, tc::kPinvTcSmemBytes), "smem opt-in pinv_w_tc");
+            CU_CHECK(opt_in_smem(tc::pinv_w_tc2_kernel, tc::kPinv2SmemBytes), "smem opt-in pinv_w_tc2");
         }
     }
     static const char f32_tag = 0;
@@ -255,7 +257,10 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     }
     {
         StageScope scope(ST_PINV, st);
-        if (tcp) tc::pinv_w_tc_kernel<<<dim3(kHeads / 2, V), 256, tc::kPinvTcSmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        // EDSNET_PINV_VARIANT=1: the round-1 chain (two heads per CTA, four products per iteration), kept as a cross-check
+        static const int pinv_variant = [] { const char* e = getenv("EDSNET_PINV_VARIANT"); return e ? atoi(e) : 0; }();
+        if (tcp && pinv_variant == 1) tc::pinv_w_tc_kernel<<<dim3(kHeads / 2, V), 256, tc::kPinvTcSmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
+        else if (tcp) tc::pinv_w_tc2_kernel<<<dim3(kHeads, V), 256, tc::kPinv2SmemBytes, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         else pinv_w_kernel<<<dim3(kHeads, V), 256, kPinvSmem, st>>>(attn2, stats, a3v, wmat, zmat, kPinvIters);
         CU_CHECK(cudaGetLastError(), "pinv_w_kernel");
     }
