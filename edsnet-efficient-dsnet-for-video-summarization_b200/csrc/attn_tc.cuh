@@ -113,20 +113,29 @@ __device__ __forceinline__ void tmem_read64_sum(uint32_t t_main, uint32_t t_lo, 
         for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
     }
 }
-// three-pass product of [M=128][K=64] (K-major A planes) with a [N=64][K=64] K-major or [K=64][N=64] MN-major B
+__device__ __forceinline__ uint64_t make_smem_desc_mn2(uint32_t addr) {      // two MN atoms (64 columns each), 8 KB apart
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// three-pass product of [M=128][K=64] (K-major A planes) with a [N=64][K=64] K-major or [K=64][N=64] MN-major B.
+// B's hi and lo planes lie 8 KB apart (b_lo == b_hi + 8192) and the accumulators side by side (acc_lo == acc_main + 64),
+// so A_hi [B_hi | B_lo] is ONE N = 128 instruction whose halves land in (main | cross); A_lo B_hi follows into the cross
+// half: 8 instead of 12 tcgen05.mma per product, same accumulation order per accumulator (bit-identical results).  The
+// issuing thread needs ~90 cycles per instruction (clock64 probe in the pinv chain), and in these latency-bound kernels
+// that issue time is on the critical path.
 template <bool B_MN>
 __device__ __forceinline__ void issue_split_mma64(uint32_t acc_main, uint32_t acc_lo, uint32_t a_hi, uint32_t a_lo,
                                                   uint32_t b_hi, uint32_t b_lo) {
-    constexpr uint32_t idesc = B_MN ? make_idesc_bmn(128, 64) : make_idesc(128, 64);
+    constexpr uint32_t idesc2 = B_MN ? make_idesc_bmn(128, 128) : make_idesc(128, 128);
+    constexpr uint32_t idesc1 = B_MN ? make_idesc_bmn(128, 64) : make_idesc(128, 64);
+    (void)acc_lo; (void)b_lo;                                   // fixed by the layout: acc_main + 64, b_hi + 8192
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t ka = (uint32_t)k * 32u, kb = B_MN ? (uint32_t)k * 2048u : (uint32_t)k * 32u;
         const uint64_t dah = make_smem_desc<64>(a_hi + ka), dal = make_smem_desc<64>(a_lo + ka);
-        const uint64_t dbh = B_MN ? make_smem_desc_mn(b_hi + kb) : make_smem_desc<64>(b_hi + kb);
-        const uint64_t dbl = B_MN ? make_smem_desc_mn(b_lo + kb) : make_smem_desc<64>(b_lo + kb);
-        umma_f16(acc_main, dah, dbh, idesc, k != 0 ? 1u : 0u);
-        umma_f16(acc_lo, dah, dbl, idesc, k != 0 ? 1u : 0u);
-        umma_f16(acc_lo, dal, dbh, idesc, 1u);
+        const uint64_t db2 = B_MN ? make_smem_desc_mn2(b_hi + kb) : make_smem_desc<64>(b_hi + kb);
+        const uint64_t db1 = B_MN ? make_smem_desc_mn(b_hi + kb) : make_smem_desc<64>(b_hi + kb);
+        umma_f16(acc_main, dah, db2, idesc2, k != 0 ? 1u : 0u);
+        umma_f16(acc_main + 64u, dal, db1, idesc1, 1u);
     }
 }
 
@@ -177,14 +186,17 @@ constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32;              // k
                                                                             // + largest v scale [2 stages][2 heads][2 warps]
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
-// 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
-// 32..63), warp 8 = TMA producer, warp 9 = MMA issuer (told by mbarriers when S has been read out / P is in place, so
-// the row warps never wait for an issue loop).
+// 352 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
+// 32..63), warp 8 = TMA producer, warps 9 and 10 = MMA issuers, one per head of the pair (told by mbarriers when S has
+// been read out / P is in place, so the row warps never wait for an issue loop).  The two heads' products go to
+// different accumulators, so two threads may issue them concurrently: a thread needs ~90 cycles per tcgen05.mma, and a
+// tile's 32 instructions issued by one thread alone took longer than the tile's softmax.
 // gridDim.z > 1 (few, long videos: one video would otherwise keep 4 of 148 SMs busy): CTA z streams the z-th contiguous
 // range of key tiles and leaves its un-normalised output rows and (running max, sum) in `part` [V][8][Z][64][66];
 // a3v_merge_kernel combines the ranges (flash-decoding style).  The zero pad keys belong to range 0.
 constexpr int kA3PartLd = 66;
-__global__ void __launch_bounds__(320, 1)
+constexpr int kA3Threads = 352;
+__global__ void __launch_bounds__(kA3Threads, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
               float* __restrict__ a3v, float* __restrict__ part) {
@@ -211,11 +223,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 
     if (tid == 0) {
         mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
-        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // K empty
-        mbar_init(bars + 32, 1);                                            // S products done
-        mbar_init(bars + 40, 1);                                            // P.V products done
+        mbar_init(bars + 16, 2); mbar_init(bars + 24, 2);                   // K empty (one commit per issuer)
+        mbar_init(bars + 32, 2);                                            // S products done
+        mbar_init(bars + 40, 2);                                            // P.V products done
         mbar_init(bars + 48, 1); mbar_init(bars + 56, 1);                   // V full
-        mbar_init(bars + 64, 1); mbar_init(bars + 72, 1);                   // V empty
+        mbar_init(bars + 64, 2); mbar_init(bars + 72, 2);                   // V empty
         mbar_init(bars + 80, 256);                                          // every row thread has read S
         mbar_init(bars + 88, 256);                                          // every row thread has stored P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -272,18 +284,18 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 9 || warp == 10) {
         if (lane == 0) {
-            // ---- MMA issuer: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
+            // ---- MMA issuer of head ih: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
+            const uint32_t ih = (uint32_t)(warp - 9);
             bool mok = true;
             auto issue_s = [&](int i) {
                 const int s1 = i & 1;
                 mok = mbar_wait(bars + 8 * s1, (uint32_t)(i >> 1) & 1u) && mok;         // K of that tile has landed
                 tc_fence_after();
-                const uint32_t st1 = base + oKV + s1 * kA3Stage;
-                issue_split_mma64<false>(tmem_base, tmem_base + 64u, base + oQl, base + oQl + 16384, st1, st1 + 8192);
-                issue_split_mma64<false>(tmem_base + 128u, tmem_base + 192u, base + oQl, base + oQl + 16384,
-                                         st1 + 16384, st1 + 16384 + 8192);
+                const uint32_t st1 = base + oKV + s1 * kA3Stage + ih * 16384u;
+                issue_split_mma64<false>(tmem_base + ih * 128u, tmem_base + ih * 128u + 64u, base + oQl, base + oQl + 16384,
+                                         st1, st1 + 8192);
                 umma_commit(bars + 32);
                 umma_commit(bars + 16 + 8 * s1);                            // K half of the stage free after the S products
             };
@@ -298,10 +310,8 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 mok = mbar_wait(bars + 48 + 8 * s, (uint32_t)(i >> 1) & 1u) && mok;     // V of this tile has landed
                 mok = mbar_wait(bars + 88, (uint32_t)i & 1u) && mok;        // P(i) stored, O(i-1) read by everyone
                 tc_fence_after();
-                issue_split_mma64<true>(tmem_base + 256u, tmem_base + 320u, base + oP, base + oP + 16384,
-                                        st + 32768, st + 32768 + 8192);
-                issue_split_mma64<true>(tmem_base + 384u, tmem_base + 448u, base + oP, base + oP + 16384,
-                                        st + 49152, st + 49152 + 8192);
+                issue_split_mma64<true>(tmem_base + 256u + ih * 128u, tmem_base + 320u + ih * 128u, base + oP, base + oP + 16384,
+                                        st + 32768 + ih * 16384u, st + 32768 + ih * 16384u + 8192);
                 umma_commit(bars + 40);
                 umma_commit(bars + 64 + 8 * s);                             // V half of the stage free after P.V
             }
@@ -667,9 +677,6 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 constexpr int kPinvTile = 32768;
 constexpr int kPinvTcSmemBytes = 3 * kPinvTile + 256 + 1024;
 
-__device__ __forceinline__ uint64_t make_smem_desc_mn2(uint32_t addr) {      // two MN atoms, 8 KB apart
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 __device__ __forceinline__ void issue_pinv_product(uint32_t tmem_base, uint32_t left, uint32_t right) {
     constexpr uint32_t idesc = make_idesc_bmn(128, 128);
 #pragma unroll

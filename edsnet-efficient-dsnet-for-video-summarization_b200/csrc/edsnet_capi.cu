@@ -244,7 +244,7 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (tcp) {
             // a3_part (edsnet_forward / edsnet_train_forward pass it): room for a3v_split_cap(V) key ranges per (video, head)
             const int z = a3_part ? a3v_splits(V, b->max_rows) : 1;
-            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), 320, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
+            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), tc::kA3Threads, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
                                                                                    q_land, a3v, a3_part);
             if (z > 1) {
                 CU_CHECK(cudaGetLastError(), "a3v_tc_kernel");
