@@ -8,6 +8,7 @@ Public surface:
   ShotPlan / keyshot_summaries   kept proposals -> keyshot summaries on the device (bbox2summary)
   TruthPlan / eval_metrics / evaluate   F-score and diversity of the summaries on the device (evaluate.py)
   kts_change_points / kts_shots   kernel temporal segmentation (shot boundaries) on the device
+  GoogLeNetPool5   pool5 frame features (the reference's FeatureExtractor('google-net')) on the tcgen05 GEMM
   summarize        infer.py's chain from the sampled features on: segmentation -> scores -> NMS -> keyshot summary
   training         anchor labels, cls/loc losses, data-parallel step with one flat gradient all-reduce
 """
@@ -19,5 +20,6 @@ from .summary import ShotPlan, keyshot_summaries, keyshot_from_scores, training_
 from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
 from .kts import kts_change_points, kts_shots                      # noqa: F401
 from .infer import summarize                                       # noqa: F401
+from .features import GoogLeNetPool5                               # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

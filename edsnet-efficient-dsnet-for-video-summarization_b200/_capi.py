@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libedsnet_b200.so")
 
-EDSNET_ABI_VERSION = 13
+EDSNET_ABI_VERSION = 14
 EDSNET_MAX_SCALES = 8
 
 OK, E_ARG, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, 1, 2, 3, 4
@@ -77,6 +77,15 @@ class EvalTruth(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("cu_users", "user_off", "user_frames", "user_summ", "metric")]
 
 
+class CnnSrc(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("image_stride", C.c_int64), ("pixel_stride", C.c_int32),
+                ("channel_stride", C.c_int32), ("col0", C.c_int32), ("channels", C.c_int32)]
+
+
+class CnnInput(C.Structure):
+    _fields_ = [("src", CnnSrc * 4), ("n_src", C.c_int32), ("relu", C.c_int32)]
+
+
 # every symbol include/edsnet_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -93,6 +102,11 @@ SYMBOLS = {
     "edsnet_kts_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "edsnet_kts": (C.c_int, [C.POINTER(Batch), _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                              _P, _P, _P, _P, _P]),
+    "edsnet_cnn_im2col": (C.c_int, [C.POINTER(CnnInput), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, _P, _P]),
+    "edsnet_cnn_maxpool": (C.c_int, [C.POINTER(CnnInput), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     _P, _P]),
+    "edsnet_cnn_avgpool_l2norm": (C.c_int, [C.POINTER(CnnInput), C.c_int32, C.c_int32, _P, _P]),
     "edsnet_decode_boxes": (C.c_int, [C.POINTER(Config), C.POINTER(Batch), _P, _P, _P, _P]),
     "edsnet_forward_launches": (C.c_int, [C.POINTER(Config)]),
     "edsnet_split_f16_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

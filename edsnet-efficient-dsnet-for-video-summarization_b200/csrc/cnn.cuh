@@ -1,0 +1,133 @@
+// GoogLeNet pool5 feature extraction (second half): the frame features the scoring path consumes,
+// helpers/video_helper.py:27-73 -- torchvision's googlenet without its last two children (dropout, fc), eval mode, then
+// feat / (|feat| + 1e-10).  Every convolution (conv + folded BatchNorm(eps 1e-3) + bias) is a product on the tcgen05
+// GEMM of gemm_tc.cuh; this file holds what surrounds the products:
+//
+//   cnn_im2col_planes_kernel   patch gather (kh x kw x C, channel fastest, zero padding) over a VIRTUAL channel concat of
+//                              up to four source buffers, ReLU of the producing layer applied on the way, straight into
+//                              the GEMM's operand format: fp16 hi / lo planes with one power-of-two scale per row.  The
+//                              four branch outputs of an inception module are therefore never concatenated in memory,
+//                              and no activation is ever written back "activated".
+//   cnn_maxpool_kernel         MaxPool2d(k, stride, pad, ceil_mode=True) over the same kind of input -> dense NHWC fp32
+//   cnn_avgpool_l2norm_kernel  AdaptiveAvgPool2d(1) + the reference's L2 normalisation, one CTA per frame
+//
+// Activations are [pixels][ld] fp32 (NHWC, ld >= channels: GEMM outputs are padded to 128 columns); the input frames may
+// be NCHW (general image / pixel / channel strides).
+#pragma once
+#include "common.cuh"
+
+struct CnnSrc {
+    const float* p;
+    long long sn;        // stride between images
+    int sp, sc;          // stride between pixels / channels
+    int col0, ch;        // first column, channels taken from this source
+};
+struct CnnInput {
+    CnnSrc s[4];
+    int n_src, relu;
+};
+
+__device__ __forceinline__ float cnn_fetch(const CnnInput& in, int img, int pix, int c) {
+    int s = 0;
+    while (s + 1 < in.n_src && c >= in.s[s].ch) { c -= in.s[s].ch; ++s; }
+    const CnnSrc& q = in.s[s];
+    const float v = __ldg(q.p + (size_t)img * q.sn + (size_t)pix * q.sp + (size_t)(q.col0 + c) * q.sc);
+    return in.relu ? fmaxf(v, 0.f) : v;
+}
+
+// one warp per output pixel; K = kh * kw * C (k = (ky * kw + kx) * C + c), zero padded to kpad (multiple of 64)
+__global__ void __launch_bounds__(256)
+cnn_im2col_planes_kernel(CnnInput in, int C, int n_img, int H, int W, int kh, int kw, int stride, int pad, int OH, int OW,
+                         int kpad, __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ inv) {
+    const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long M = (long long)n_img * OH * OW;
+    if (m >= M) return;
+    const int img = (int)(m / (OH * OW)), r = (int)(m % (OH * OW));
+    const int oy = r / OW, ox = r % OW;
+    float mx = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+            const int ix = ox * stride - pad + kx;
+            if (ix < 0 || ix >= W) continue;
+            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, fabsf(cnn_fetch(in, img, iy * W + ix, c)));
+        }
+    }
+    mx = warp_max(mx);
+    int e = 0;
+    if (mx > 0.f && mx < INFINITY) e = 14 - ilogbf(mx);
+    e = max(-100, min(100, e));
+    const float sc = ldexpf(1.f, e);
+    if (lane == 0) inv[m] = ldexpf(1.f, -e);
+    __half* ph = hi + (size_t)m * kpad;
+    __half* pl = lo + (size_t)m * kpad;
+    int k0 = 0;
+    for (int ky = 0; ky < kh; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        for (int kx = 0; kx < kw; ++kx, k0 += C) {
+            const int ix = ox * stride - pad + kx;
+            const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
+            for (int c = lane; c < C; c += 32) {
+                const float v = inside ? cnn_fetch(in, img, iy * W + ix, c) * sc : 0.f;
+                const __half h = __float2half_rn(v);
+                ph[k0 + c] = h;
+                pl[k0 + c] = __float2half_rn(v - __half2float(h));
+            }
+        }
+    }
+    for (int k = k0 + lane; k < kpad; k += 32) { ph[k] = __float2half_rn(0.f); pl[k] = __float2half_rn(0.f); }
+}
+
+// MaxPool2d(k, stride, pad, ceil_mode=True): thread per (output pixel, channel), channel fastest; windows are clipped to
+// the image (the padding never wins a maximum)
+__global__ void __launch_bounds__(256)
+cnn_maxpool_kernel(CnnInput in, int C, int n_img, int H, int W, int k, int stride, int pad, int OH, int OW,
+                   float* __restrict__ out) {
+    const long long total = (long long)n_img * OH * OW * C;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int c = (int)(idx % C);
+        const long long m = idx / C;
+        const int img = (int)(m / (OH * OW)), r = (int)(m % (OH * OW));
+        const int oy = r / OW, ox = r % OW;
+        const int y0 = max(0, oy * stride - pad), y1 = min(H, oy * stride - pad + k);
+        const int x0 = max(0, ox * stride - pad), x1 = min(W, ox * stride - pad + k);
+        float best = -INFINITY;
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) best = fmaxf(best, cnn_fetch(in, img, y * W + x, c));
+        out[idx] = best;
+    }
+}
+
+// mean over the HW pixels of every channel, then feat / (|feat|_2 + 1e-10) (video_helper.py:66-72); C <= 1024, one CTA
+// per frame, thread <-> channels tid, tid + 256, ...
+__global__ void __launch_bounds__(256)
+cnn_avgpool_l2norm_kernel(CnnInput in, int C, int HW, float* __restrict__ out) {
+    __shared__ float s_part[8];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = tid + 256 * q;
+        if (c < C) {
+            float a = 0.f;
+            for (int p = 0; p < HW; ++p) a += cnn_fetch(in, img, p, c);
+            f[q] = a / (float)HW;
+            ss = fmaf(f[q], f[q], ss);
+        }
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w];
+    const float d = sqrtf(tot) + 1e-10f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = tid + 256 * q;
+        if (c < C) out[(size_t)img * C + c] = f[q] / d;
+    }
+}

@@ -27,6 +27,7 @@
 #include "eval.cuh"
 #include "kts.cuh"
 #include "train.cuh"
+#include "cnn.cuh"
 
 namespace {
 
@@ -716,6 +717,80 @@ int edsnet_keyshot_summary(const edsnet_config* cfg, const edsnet_batch* batch, 
                                                            keep_boxes, pos_scores, frame_scores, seg_scores, picked,
                                                            summary, static_cast<unsigned char*>(dp_scratch));
     CU_CHECK(cudaGetLastError(), "keyshot_summary_kernel");
+    return EDSNET_OK;
+}
+
+// ---- GoogLeNet pool5 feature extraction: what surrounds the convolution products (cnn.cuh) ----
+namespace {
+int cnn_input(const edsnet_cnn_input* in, CnnInput* out, int* channels) {
+    if (!in) return fail(EDSNET_E_ARG, "cnn: input is NULL");
+    if (in->n_src < 1 || in->n_src > 4) return fail(EDSNET_E_ARG, "cnn: 1..4 source buffers");
+    int C = 0;
+    for (int i = 0; i < in->n_src; ++i) {
+        const edsnet_cnn_src& q = in->src[i];
+        if (!q.p || q.channels < 1 || q.col0 < 0) return fail(EDSNET_E_ARG, "cnn: bad source buffer");
+        out->s[i] = CnnSrc{q.p, (long long)q.image_stride, q.pixel_stride, q.channel_stride, q.col0, q.channels};
+        C += q.channels;
+    }
+    for (int i = in->n_src; i < 4; ++i) out->s[i] = CnnSrc{nullptr, 0, 0, 0, 0, 0};
+    out->n_src = in->n_src;
+    out->relu = in->relu ? 1 : 0;
+    *channels = C;
+    return EDSNET_OK;
+}
+int pool_out(int H, int k, int stride, int pad) {           // torch, ceil_mode=True
+    int o = (H + 2 * pad - k + stride - 1) / stride + 1;
+    if ((o - 1) * stride >= H + pad) --o;                   // the last window must start inside the image or its left padding
+    return o;
+}
+}  // namespace
+
+int edsnet_cnn_im2col(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                      int32_t stride, int32_t pad, int32_t kpad, void* planes, void* stream) {
+    CnnInput ci;
+    int C = 0;
+    int rc = cnn_input(in, &ci, &C);
+    if (rc) return rc;
+    if (n_img < 1 || H < 1 || W < 1 || kh < 1 || kw < 1 || stride < 1 || pad < 0 || !planes)
+        return fail(EDSNET_E_ARG, "cnn_im2col: bad geometry");
+    if (kpad % 64 != 0 || kpad < kh * kw * C) return fail(EDSNET_E_ARG, "cnn_im2col: kpad must be a multiple of 64 >= kh * kw * C");
+    const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
+    if (OH < 1 || OW < 1) return fail(EDSNET_E_ARG, "cnn_im2col: empty output");
+    const long long M = (long long)n_img * OH * OW;
+    if (M > 0x7fffffffLL) return fail(EDSNET_E_ARG, "cnn_im2col: too many output pixels");
+    __half* hi = static_cast<__half*>(planes);
+    __half* lo = hi + (size_t)M * kpad;
+    float* inv = reinterpret_cast<float*>(lo + (size_t)M * kpad);
+    cnn_im2col_planes_kernel<<<(unsigned)((M + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+    CU_CHECK(cudaGetLastError(), "cnn_im2col_planes_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_cnn_maxpool(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int32_t W, int32_t k, int32_t stride,
+                       int32_t pad, float* out, void* stream) {
+    CnnInput ci;
+    int C = 0;
+    int rc = cnn_input(in, &ci, &C);
+    if (rc) return rc;
+    if (n_img < 1 || H < 1 || W < 1 || k < 1 || stride < 1 || pad < 0 || 2 * pad > k || !out)
+        return fail(EDSNET_E_ARG, "cnn_maxpool: bad geometry");
+    const int OH = pool_out(H, k, stride, pad), OW = pool_out(W, k, stride, pad);
+    const long long total = (long long)n_img * OH * OW * C;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+    cnn_maxpool_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(ci, C, n_img, H, W, k, stride, pad, OH, OW, out);
+    CU_CHECK(cudaGetLastError(), "cnn_maxpool_kernel");
+    return EDSNET_OK;
+}
+
+int edsnet_cnn_avgpool_l2norm(const edsnet_cnn_input* in, int32_t n_img, int32_t HW, float* out, void* stream) {
+    CnnInput ci;
+    int C = 0;
+    int rc = cnn_input(in, &ci, &C);
+    if (rc) return rc;
+    if (n_img < 1 || HW < 1 || C > 1024 || !out) return fail(EDSNET_E_ARG, "cnn_avgpool_l2norm: bad geometry (C <= 1024)");
+    cnn_avgpool_l2norm_kernel<<<n_img, 256, 0, static_cast<cudaStream_t>(stream)>>>(ci, C, HW, out);
+    CU_CHECK(cudaGetLastError(), "cnn_avgpool_l2norm_kernel");
     return EDSNET_OK;
 }
 

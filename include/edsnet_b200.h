@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EDSNET_ABI_VERSION 13
+#define EDSNET_ABI_VERSION 14
 
 enum {
     EDSNET_OK = 0,
@@ -243,6 +243,38 @@ size_t edsnet_kts_scratch_bytes(int32_t n);
 int edsnet_kts(const edsnet_batch* batch, const edsnet_kts_video* videos, const float* x, int32_t ncp_cap,
                int32_t m_fixed, double vmax, int32_t desc_rate, int32_t lmin, int32_t lmax, int32_t* n_cps,
                int32_t* cps, double* objective, void* scratch, void* stream);
+
+/* ---- GoogLeNet pool5 feature extraction (helpers/video_helper.py:27-73), the step in front of the scoring path ----
+ * The convolutions are products on the tcgen05 GEMM (edsnet_gemm, epilogue 2 = + bias, with BatchNorm folded into
+ * weights and bias by the host); the entry points below are what surrounds them.  Activations are fp32
+ * [pixels][ld] buffers (NHWC; ld >= channels); an input is a VIRTUAL channel concatenation of up to four such
+ * buffers (the four branches of an inception module are never concatenated in memory) with the producing layers'
+ * ReLU applied while reading.  General strides, so the network input may be NCHW. */
+typedef struct {
+    const float* p;            /* [dev] first element                                                       */
+    int64_t image_stride;      /* elements between images                                                   */
+    int32_t pixel_stride;      /* elements between pixels (row-major y * W + x)                             */
+    int32_t channel_stride;    /* elements between channels                                                 */
+    int32_t col0;              /* first channel column taken from this buffer                               */
+    int32_t channels;          /* channels taken                                                            */
+} edsnet_cnn_src;
+typedef struct {
+    edsnet_cnn_src src[4];
+    int32_t n_src;             /* 1..4                                                                      */
+    int32_t relu;              /* 1: max(x, 0) applied to every value read                                  */
+} edsnet_cnn_input;
+
+/* Patch gather of a kh x kw convolution (stride, zero padding `pad`) into the GEMM operand format: row m = output
+ * pixel (image, oy, ox), column k = (ky * kw + kx) * C + c with C = the input's total channels, zero padded to kpad (a
+ * multiple of 64).  planes: hi [M][kpad] fp16 | lo [M][kpad] fp16 | inverse row scales [M] fp32 =
+ * edsnet_split_f16_bytes(M, kpad) bytes, M = n_img * OH * OW, OH = (H + 2 pad - kh) / stride + 1. */
+int edsnet_cnn_im2col(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                      int32_t stride, int32_t pad, int32_t kpad, void* planes, void* stream);
+/* MaxPool2d(k, stride, pad, ceil_mode=True) -> out [dev][n_img * OH * OW][C] fp32; OH as torch computes it. */
+int edsnet_cnn_maxpool(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int32_t W, int32_t k, int32_t stride,
+                       int32_t pad, float* out, void* stream);
+/* AdaptiveAvgPool2d(1) over HW pixels, then feat / (|feat|_2 + 1e-10) -> out [dev][n_img][C] fp32, C <= 1024. */
+int edsnet_cnn_avgpool_l2norm(const edsnet_cnn_input* in, int32_t n_img, int32_t HW, float* out, void* stream);
 
 /* decode only (what DSNet.predict returns, dsnet.py:146-153, plus the evaluate.py:26 clip/round):
  * boxes_f32 [dev][total_rows*S][2] (may be NULL), boxes_i32 [dev][total_rows*S][2] (may be NULL). */

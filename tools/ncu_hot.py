@@ -7,8 +7,8 @@ import sys
 def main():
     path, rx = sys.argv[1], sys.argv[2]
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", "regex:" + rx],
-                         capture_output=True, text=True).stdout
+    sel = ["--kernel-id", ":::" + rx[3:]] if rx.startswith("id:") else ["--kernel-name", "regex:" + rx]
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     si = hdr.index("Warp Stall Sampling (All Samples)")

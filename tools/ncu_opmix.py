@@ -1,5 +1,5 @@
 """Executed-instruction mix of one kernel of an ncu report (source page), weighted by execution count:
-    python tools/ncu_opmix.py report.ncu-rep kernel_regex [n]
+    python tools/ncu_opmix.py report.ncu-rep kernel_regex|id:N [n]   (id:N = N-th launch, 1-based)
 Also prints the share of mbarrier try_wait spin loops (SYNCS ... TRYWAIT) in the executed instructions."""
 import collections
 import csv
@@ -10,8 +10,8 @@ import sys
 def main():
     path, rx = sys.argv[1], sys.argv[2]
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", "regex:" + rx],
-                         capture_output=True, text=True).stdout
+    sel = ["--kernel-id", ":::" + rx[3:]] if rx.startswith("id:") else ["--kernel-name", "regex:" + rx]
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     si = hdr.index("Warp Stall Sampling (All Samples)")
