@@ -19,7 +19,7 @@ from . import training                                           # noqa: F401
 from .summary import ShotPlan, keyshot_summaries, keyshot_from_scores, training_targets, split_summaries  # noqa: F401
 from .evaluate import TruthPlan, eval_metrics, evaluate            # noqa: F401
 from .kts import kts_change_points, kts_shots                      # noqa: F401
-from .infer import summarize                                       # noqa: F401
+from .infer import summarize, summarize_frames                                       # noqa: F401
 from .features import GoogLeNetPool5                               # noqa: F401
 
 __all__ = ["DSNet", "NystromAttention", "BatchPlan", "DeviceBatch", "shard_videos", "ScoringPipeline"]

@@ -146,17 +146,17 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap mapq_hi, const __grid_constant
                 mok = mbar_wait(bars + 8 * s1, (uint32_t)(i >> 1) & 1u) && mok;          // K of that tile has landed
                 tc_fence_after();
                 const uint32_t kst = base + oK + s1 * kMtKStage;
-                constexpr uint32_t idesc = make_idesc(128, 64);
+                // K's hi and lo planes of a 64-column block are contiguous (8 KB each) and the accumulators adjacent
+                // (main | cross): Q_hi [K_hi | K_lo]^T is one N = 128 instruction, Q_lo K_hi^T follows into the cross half
+                constexpr uint32_t idesc = make_idesc(128, 64), idesc2 = make_idesc(128, 128);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t a0 = base + oQ + kb * 32768 + k * 32, b0 = kst + kb * 16384 + k * 32;
                         const uint64_t dah = make_smem_desc<64>(a0), dal = make_smem_desc<64>(a0 + 16384);
-                        const uint64_t dbh = make_smem_desc<64>(b0), dbl = make_smem_desc<64>(b0 + 8192);
-                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        umma_f16(tmem_base, dah, dbh, idesc, acc);
-                        umma_f16(tmem_base + 64u, dah, dbl, idesc, acc);
+                        const uint64_t dbh = make_smem_desc<64>(b0);
+                        umma_f16(tmem_base, dah, dbh, idesc2, (kb | k) != 0 ? 1u : 0u);
                         umma_f16(tmem_base + 64u, dal, dbh, idesc, 1u);
                     }
                 umma_commit(bars + 32);
@@ -179,10 +179,10 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap mapq_hi, const __grid_constant
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t a0 = base + oP + k * 32, b0 = base + oV + k * 2048;
                     const uint64_t dah = make_smem_desc<64>(a0), dal = make_smem_desc<64>(a0 + 16384);
-                    const uint64_t dbh = make_smem_desc_mn2(b0), dbl = make_smem_desc_mn2(b0 + 16384);
-                    const uint32_t acc = k != 0 ? 1u : 0u;
-                    umma_f16(tmem_base + 128u, dah, dbh, idesc_o, acc);
-                    umma_f16(tmem_base + 256u, dah, dbl, idesc_o, acc);
+                    // V_hi (two MN atoms) and V_lo (two more) are four atoms 8 KB apart: P_hi [V_hi | V_lo] is one N = 256
+                    // instruction over the adjacent (main | cross) output accumulators
+                    const uint64_t dbh = make_smem_desc_mn2(b0);
+                    umma_f16(tmem_base + 128u, dah, dbh, make_idesc_bmn(128, 256), k != 0 ? 1u : 0u);
                     umma_f16(tmem_base + 256u, dal, dbh, idesc_o, 1u);
                 }
                 umma_commit(bars + 40);

@@ -152,3 +152,31 @@ def test_pool5_other_resolution():
     dev = torch.device("cuda", 0)
     got = GoogLeNetPool5(p, dev)(x.to(dev)).cpu().numpy()
     assert rel_l2(got, ref) < 2e-5
+
+
+@pytest.mark.gpu
+def test_frames_to_summary_chain_vs_oracle():
+    """VideoPreprocessor.run + infer.py:26-36 from the sampled frames on: pool5 features -> segmentation -> scores -> NMS
+    -> keyshot summary on the device; checked against the oracle's features (tolerance) and, from the device's own
+    features on, against the oracle's host chain (exact: change points, shots, summary)."""
+    from edsnet_b200 import GoogLeNetPool5, summarize_frames
+    from oracle import dsnet_oracle as orc
+    from tests.util import make_model
+    dev = torch.device("cuda", 0)
+    p = gno.synth_googlenet_params(11)
+    lengths, sample_rate = [40, 25], 15
+    n_frames = [40 * 15 - 7, 25 * 15 - 3]
+    frames = [F.interpolate(gno.synth_frames(t, 100 + t), size=(96, 128), mode="bilinear", align_corners=False).contiguous()
+              for t in lengths]
+    scales = [4, 8]
+    model = make_model(orc.synth_params(9, "xavier"), scales, 5, "fp16x3", dev)
+    res = summarize_frames(model, GoogLeNetPool5(p, dev), [f.to(dev) for f in frames], n_frames, 0.5, sample_rate,
+                           frame_batch=16)
+    for f, t, nf, r in zip(frames, lengths, n_frames, res):
+        with torch.no_grad():
+            want_feat = gno.pool5_features(f, p).numpy()
+        feat = r["features"].cpu().numpy()
+        assert rel_l2(feat, want_feat) < 2e-5
+        cps, nfps, picks = orc.kts_shots(nf, feat, sample_rate)
+        assert np.array_equal(r["change_points"], cps) and np.array_equal(r["nfps"], nfps) and np.array_equal(r["picks"], picks)
+        assert r["summary"].shape == (nf,) and r["summary"].sum() <= int(nf * 0.15)
