@@ -16,12 +16,40 @@ from .plan import BatchPlan
 _VIDEO_DT = np.dtype([("scratch_off", np.int64), ("row0", np.int32), ("n", np.int32)])
 
 
+def gram_tensor_core(xv: torch.Tensor, out: torch.Tensor) -> None:
+    """out (n x n float32 view, row-major) <- X X^T of one video's features (video_helper.py:117) on the tcgen05 GEMM:
+    the rows go through the operand-plane gather (`edsnet_cnn_im2col` as a 1 x 1 gather: fp16 hi / lo planes, one
+    power-of-two scale per row) and ONE product with A = B = those planes, three split-fp16 passes (fp32-grade: the
+    entries agree with a float32 matmul to ~5e-7, which is also what two BLAS libraries differ by).  Rows are padded to
+    the GEMM's 128-column granularity; torch only moves data here."""
+    import ctypes as C
+    from .features import _Act
+    lib = _capi.lib()
+    n, f = int(xv.shape[0]), int(xv.shape[1])
+    npad = (n + 127) // 128 * 128
+    dev = xv.device
+    xp = torch.zeros((npad, f), dtype=torch.float32, device=dev)
+    xp[:n] = xv
+    planes = torch.empty(int(lib.edsnet_split_f16_bytes(npad, f)), dtype=torch.uint8, device=dev)
+    cpad = torch.empty((npad, npad), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ci = _Act([(xp, f, 0, f)], 1, npad, 1, relu=False).struct()
+    _capi.check(lib.edsnet_cnn_im2col(C.byref(ci), 1, npad, 1, 1, 1, 1, 0, f, planes.data_ptr(), st))
+    _capi.check(lib.edsnet_gemm(_capi.PREC_FP16X3, 0, None, planes.data_ptr(), None, planes.data_ptr(), cpad.data_ptr(),
+                                npad, npad, f, None, None, 0, st))
+    out.copy_(cpad[:n, :n])
+
+
 def kts_change_points(x: torch.Tensor, lengths: Sequence[int], kernels: Optional[Sequence[np.ndarray]] = None,
                       ncp_cap: int = -1, m_fixed: int = -1, vmax: float = 1.0, desc_rate: int = 1, lmin: int = 1,
-                      lmax: int = 100000, scratch_budget: int = 4 << 30) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                      lmax: int = 100000, scratch_budget: int = 4 << 30, gram: str = "tensor"
+                      ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """x: packed float32 [sum(lengths), 1024] features on a CUDA device.  kernels: optional per-video float32 n x n
     kernel matrices to segment instead of X X^T (bit-exact comparison against the reference needs the reference's own
-    np.matmul result).  Returns (change points per video, objective values for 0..len(cps) change points per video)."""
+    np.matmul result).  gram: 'tensor' = X X^T on the tcgen05 GEMM (gram_tensor_core), 'fp32' = the CUDA-core kernel inside
+    edsnet_kts.  Returns (change points per video, objective values for 0..len(cps) change points per video)."""
+    if gram not in ("tensor", "fp32"):
+        raise ValueError("gram must be 'tensor' or 'fp32'")
     if not x.is_cuda:
         raise RuntimeError("kts_change_points needs CUDA tensors (there is no CPU fallback)")
     lengths = [int(t) for t in lengths]
@@ -60,6 +88,14 @@ def kts_change_points(x: torch.Tensor, lengths: Sequence[int], kernels: Optional
                 k = torch.from_numpy(np.ascontiguousarray(kernels[start + i], dtype=np.float32)).to(dev)
                 o = int(vids[i]["scratch_off"])
                 scratch[o:o + n * n * 4].view(torch.float32).copy_(k.reshape(-1))
+        x_arg = None
+        if kernels is None and gram == "tensor" and x.shape[1] % 64 == 0:
+            with torch.cuda.device(dev):
+                for i, n in enumerate(sub):
+                    o, r0 = int(vids[i]["scratch_off"]), int(cu[start]) + int(plan.cu_rows[i])
+                    gram_tensor_core(x[r0:r0 + n], scratch[o:o + n * n * 4].view(torch.float32).view(n, n))
+        elif kernels is None:
+            x_arg = "features"
         vids_dev = torch.from_numpy(vids.view(np.uint8)).to(dev)
         R = int(sum(sub))
         n_cps = torch.zeros(len(sub), dtype=torch.int32, device=dev)
@@ -68,7 +104,7 @@ def kts_change_points(x: torch.Tensor, lengths: Sequence[int], kernels: Optional
         xs = x[int(cu[start]):int(cu[end])]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _capi.check(lib.edsnet_kts(batch.struct, vids_dev.data_ptr(), None if kernels is not None else xs.data_ptr(),
+            _capi.check(lib.edsnet_kts(batch.struct, vids_dev.data_ptr(), xs.data_ptr() if x_arg else None,
                                        ncp_cap, m_fixed, float(vmax), desc_rate, lmin, lmax, n_cps.data_ptr(),
                                        cps.data_ptr(), obj.data_ptr(), scratch.data_ptr(), stream))
         nc, cp, ob = n_cps.cpu().numpy(), cps.cpu().numpy(), obj.cpu().numpy()

@@ -911,15 +911,31 @@ def test_kts_from_features_and_shot_tables():
     for n, f in zip(names, feats):
         assert orc.rel_l2(np.matmul(f, f.T), KTS[f"{n}/K"]) < 1e-6          # the committed generator reproduces the inputs
     x = torch.from_numpy(np.concatenate(feats)).to(DEV)
-    cps, obj = kts_change_points(x, [len(f) for f in feats])
-    for n, c, o in zip(names, cps, obj):
-        assert np.array_equal(c, KTS[f"{n}/cps"]), (n, c, KTS[f"{n}/cps"])
-        assert np.allclose(o, KTS[f"{n}/scores"], rtol=1e-4, atol=1e-4)
+    for gram in ("tensor", "fp32"):                                # X X^T on the tcgen05 GEMM / on CUDA cores
+        cps, obj = kts_change_points(x, [len(f) for f in feats], gram=gram)
+        for n, c, o in zip(names, cps, obj):
+            assert np.array_equal(c, KTS[f"{n}/cps"]), (gram, n, c, KTS[f"{n}/cps"])
+            # the objective is a difference of float32 prefix sums of K: last-bit differences of K (summation order /
+            # split-fp16 products) show up at ~1e-6 of the LARGEST objective value
+            assert np.allclose(o, KTS[f"{n}/scores"], rtol=1e-4, atol=5e-6 * float(np.max(KTS[f"{n}/scores"])) + 1e-4)
     n = "t150"
     f = feats[names.index(n)]
     cp, nfps, picks = kts_shots(int(KTS[f"{n}/n_frames"]), torch.from_numpy(f).to(DEV), int(KTS[f"{n}/rate"]))
     assert np.array_equal(cp, KTS[f"{n}/change_points"]) and np.array_equal(nfps, KTS[f"{n}/nfps"])
     assert np.array_equal(picks, np.arange(len(f)) * 15)
+
+
+def test_gram_on_tensor_cores_matches_float32_matmul():
+    """K = X X^T of video_helper.py:117 on the tcgen05 GEMM (three split-fp16 passes): float32-matmul grade."""
+    from edsnet_b200.kts import gram_tensor_core
+    for n in (7, 128, 333):
+        f = orc.synth_features(n, 50 + n)
+        out = torch.empty((n, n), dtype=torch.float32, device=DEV)
+        gram_tensor_core(f.to(DEV), out)
+        ref = f.double() @ f.double().t()
+        assert orc.rel_l2(out.cpu().numpy(), ref.numpy()) < 1e-6
+    from edsnet_b200 import _capi
+    assert _capi.lib().edsnet_debug_tc_status(0) == 0
 
 
 def test_infer_chain_vs_oracle():
