@@ -35,7 +35,22 @@ __device__ __forceinline__ float cnn_fetch(const CnnInput& in, int img, int pix,
     return in.relu ? fmaxf(v, 0.f) : v;
 }
 
-// one warp per output pixel; K = kh * kw * C (k = (ky * kw + kx) * C + c), zero padded to kpad (multiple of 64)
+// four consecutive channels c .. c + 3 (host-checked: every source has channel stride 1, 4-aligned columns / counts /
+// strides and a 16-byte aligned base, so a vector never straddles two sources)
+__device__ __forceinline__ float4 cnn_fetch4(const CnnInput& in, int img, int pix, int c) {
+    int s = 0;
+    while (s + 1 < in.n_src && c >= in.s[s].ch) { c -= in.s[s].ch; ++s; }
+    const CnnSrc& q = in.s[s];
+    float4 v = ldg4(q.p + (size_t)img * q.sn + (size_t)pix * q.sp + (size_t)(q.col0 + c));
+    if (in.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+}
+
+// One warp per output pixel; K = kh * kw * C (k = (ky * kw + kx) * C + c), zero padded to kpad (multiple of 64).
+// VEC = 4: lanes walk the flattened (tap, channel / 4) index with 16-byte loads and 8-byte plane stores; NCACHE > 0: the
+// row has at most 32 * NCACHE vectors and stays in registers between the maximum and the conversion (one read of the
+// input instead of two).  VEC = 1: the general scalar form (the network input: 3 channels, NCHW).
+template <int VEC, int NCACHE>
 __global__ void __launch_bounds__(256)
 cnn_im2col_planes_kernel(CnnInput in, int C, int n_img, int H, int W, int kh, int kw, int stride, int pad, int OH, int OW,
                          int kpad, __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ inv) {
@@ -45,14 +60,28 @@ cnn_im2col_planes_kernel(CnnInput in, int C, int n_img, int H, int W, int kh, in
     if (m >= M) return;
     const int img = (int)(m / (OH * OW)), r = (int)(m % (OH * OW));
     const int oy = r / OW, ox = r % OW;
+    const int CV = C / VEC, KV = kh * kw * CV;                      // vectors per tap / per row
+    auto fetch = [&](int v) -> float4 {                             // vector v of the row (zero outside the image)
+        const int tap = v / CV, c = (v - tap * CV) * VEC;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC == 4) return cnn_fetch4(in, img, iy * W + ix, c);
+        return make_float4(cnn_fetch(in, img, iy * W + ix, c), 0.f, 0.f, 0.f);
+    };
+    float4 cache[NCACHE > 0 ? NCACHE : 1];
     float mx = 0.f;
-    for (int ky = 0; ky < kh; ++ky) {
-        const int iy = oy * stride - pad + ky;
-        if (iy < 0 || iy >= H) continue;
-        for (int kx = 0; kx < kw; ++kx) {
-            const int ix = ox * stride - pad + kx;
-            if (ix < 0 || ix >= W) continue;
-            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, fabsf(cnn_fetch(in, img, iy * W + ix, c)));
+    if (NCACHE > 0) {
+#pragma unroll
+        for (int t = 0; t < NCACHE; ++t) {
+            const int v = lane + 32 * t;
+            cache[t] = v < KV ? fetch(v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(cache[t].x), fabsf(cache[t].y))), fmaxf(fabsf(cache[t].z), fabsf(cache[t].w)));
+        }
+    } else {
+        for (int v = lane; v < KV; v += 32) {
+            const float4 x = fetch(v);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
         }
     }
     mx = warp_max(mx);
@@ -63,40 +92,62 @@ cnn_im2col_planes_kernel(CnnInput in, int C, int n_img, int H, int W, int kh, in
     if (lane == 0) inv[m] = ldexpf(1.f, -e);
     __half* ph = hi + (size_t)m * kpad;
     __half* pl = lo + (size_t)m * kpad;
-    int k0 = 0;
-    for (int ky = 0; ky < kh; ++ky) {
-        const int iy = oy * stride - pad + ky;
-        for (int kx = 0; kx < kw; ++kx, k0 += C) {
-            const int ix = ox * stride - pad + kx;
-            const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
-            for (int c = lane; c < C; c += 32) {
-                const float v = inside ? cnn_fetch(in, img, iy * W + ix, c) * sc : 0.f;
-                const __half h = __float2half_rn(v);
-                ph[k0 + c] = h;
-                pl[k0 + c] = __float2half_rn(v - __half2float(h));
-            }
+    auto put = [&](int v, float4 x) {
+        const float a[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            h[j] = __float2half_rn(a[j]);
+            l[j] = __float2half_rn(a[j] - __half2float(h[j]));
         }
+        if (VEC == 4) {
+            *reinterpret_cast<uint2*>(ph + 4 * v) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(pl + 4 * v) = *reinterpret_cast<uint2*>(l);
+        } else {
+            ph[v] = h[0];
+            pl[v] = l[0];
+        }
+    };
+    if (NCACHE > 0) {
+#pragma unroll
+        for (int t = 0; t < NCACHE; ++t) {
+            const int v = lane + 32 * t;
+            if (v < KV) put(v, cache[t]);
+        }
+    } else {
+        for (int v = lane; v < KV; v += 32) put(v, fetch(v));
     }
-    for (int k = k0 + lane; k < kpad; k += 32) { ph[k] = __float2half_rn(0.f); pl[k] = __float2half_rn(0.f); }
+    for (int k = KV * VEC + lane; k < kpad; k += 32) { ph[k] = __float2half_rn(0.f); pl[k] = __float2half_rn(0.f); }
 }
 
-// MaxPool2d(k, stride, pad, ceil_mode=True): thread per (output pixel, channel), channel fastest; windows are clipped to
-// the image (the padding never wins a maximum)
+// MaxPool2d(k, stride, pad, ceil_mode=True): thread per (output pixel, VEC channels), channel fastest; windows are clipped
+// to the image (the padding never wins a maximum)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 cnn_maxpool_kernel(CnnInput in, int C, int n_img, int H, int W, int k, int stride, int pad, int OH, int OW,
                    float* __restrict__ out) {
-    const long long total = (long long)n_img * OH * OW * C;
+    const int CV = C / VEC;
+    const long long total = (long long)n_img * OH * OW * CV;
     for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-        const int c = (int)(idx % C);
-        const long long m = idx / C;
+        const int c = (int)(idx % CV) * VEC;
+        const long long m = idx / CV;
         const int img = (int)(m / (OH * OW)), r = (int)(m % (OH * OW));
         const int oy = r / OW, ox = r % OW;
         const int y0 = max(0, oy * stride - pad), y1 = min(H, oy * stride - pad + k);
         const int x0 = max(0, ox * stride - pad), x1 = min(W, ox * stride - pad + k);
-        float best = -INFINITY;
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) best = fmaxf(best, cnn_fetch(in, img, y * W + x, c));
-        out[idx] = best;
+            for (int x = x0; x < x1; ++x) {
+                if (VEC == 4) {
+                    const float4 v = cnn_fetch4(in, img, y * W + x, c);
+                    best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+                    best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                } else {
+                    best.x = fmaxf(best.x, cnn_fetch(in, img, y * W + x, c));
+                }
+            }
+        if (VEC == 4) st4(out + m * C + c, best);
+        else out[m * C + c] = best.x;
     }
 }
 

@@ -738,6 +738,16 @@ int cnn_input(const edsnet_cnn_input* in, CnnInput* out, int* channels) {
     *channels = C;
     return EDSNET_OK;
 }
+// 16-byte vector path: channel-contiguous sources whose columns, counts, strides and bases are multiples of four floats
+bool cnn_vec4(const CnnInput& ci, int C) {
+    if (C % 4) return false;
+    for (int i = 0; i < ci.n_src; ++i) {
+        const CnnSrc& q = ci.s[i];
+        if (q.sc != 1 || (q.ch & 3) || (q.col0 & 3) || (q.sp & 3) || (q.sn & 3) || (reinterpret_cast<uintptr_t>(q.p) & 15))
+            return false;
+    }
+    return true;
+}
 int pool_out(int H, int k, int stride, int pad) {           // torch, ceil_mode=True
     int o = (H + 2 * pad - k + stride - 1) / stride + 1;
     if ((o - 1) * stride >= H + pad) --o;                   // the last window must start inside the image or its left padding
@@ -761,8 +771,16 @@ int edsnet_cnn_im2col(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int3
     __half* hi = static_cast<__half*>(planes);
     __half* lo = hi + (size_t)M * kpad;
     float* inv = reinterpret_cast<float*>(lo + (size_t)M * kpad);
-    cnn_im2col_planes_kernel<<<(unsigned)((M + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+    const unsigned blocks = (unsigned)((M + 7) / 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cnn_vec4(ci, C)) {
+        if (kh * kw * C <= 1024)
+            cnn_im2col_planes_kernel<4, 8><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+        else
+            cnn_im2col_planes_kernel<4, 0><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+    } else {
+        cnn_im2col_planes_kernel<1, 0><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+    }
     CU_CHECK(cudaGetLastError(), "cnn_im2col_planes_kernel");
     return EDSNET_OK;
 }
@@ -778,7 +796,10 @@ int edsnet_cnn_maxpool(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int
     const int OH = pool_out(H, k, stride, pad), OW = pool_out(W, k, stride, pad);
     const long long total = (long long)n_img * OH * OW * C;
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
-    cnn_maxpool_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(ci, C, n_img, H, W, k, stride, pad, OH, OW, out);
+    if (cnn_vec4(ci, C) && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        cnn_maxpool_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(ci, C, n_img, H, W, k, stride, pad, OH, OW, out);
+    else
+        cnn_maxpool_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(ci, C, n_img, H, W, k, stride, pad, OH, OW, out);
     CU_CHECK(cudaGetLastError(), "cnn_maxpool_kernel");
     return EDSNET_OK;
 }
