@@ -182,8 +182,9 @@ landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict_
 // TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kA3Stage = 8 * 8192;                                          // k_h0 k_h1 v_h0 v_h1, hi and lo
-constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32;              // key scales [2 stages][4][64] + pair exchange
+constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32 + 128 * 4 + 64;   // key scales [2 stages][4][64] + pair exchange
                                                                             // + largest v scale [2 stages][2 heads][2 warps]
+                                                                            // + landmark-key scales [128] + attn2 reductions
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
 // 352 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
@@ -194,12 +195,19 @@ constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 
 // gridDim.z > 1 (few, long videos: one video would otherwise keep 4 of 148 SMs busy): CTA z streams the z-th contiguous
 // range of key tiles and leaves its un-normalised output rows and (running max, sum) in `part` [V][8][Z][64][66];
 // a3v_merge_kernel combines the ranges (flash-decoding style).  The zero pad keys belong to range 0.
+//
+// attn2 != nullptr: the CTA of range 0 also produces attn2 = softmax(q_land k_land^T) of its two heads
+// (nystroformer.py:117,130) and the two magnitudes the pseudo-inverse start value needs (:16-18) before it starts on the
+// key tiles: the landmark queries are already in place as the A operand, the landmark keys go through the (still unused)
+// P tile as a K-major B operand, one extra product per head into the S accumulators.  The key / value ring fills
+// meanwhile.  This replaces attn2_kernel (a launch of its own with 64^3 FFMA products per head) on the tcgen05 path.
 constexpr int kA3PartLd = 66;
 constexpr int kA3Threads = 352;
 __global__ void __launch_bounds__(kA3Threads, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
-              float* __restrict__ a3v, float* __restrict__ part) {
+              float* __restrict__ a3v, float* __restrict__ part, const float* __restrict__ k_land,
+              float* __restrict__ attn2, float* __restrict__ stats) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
@@ -207,8 +215,10 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
     float* s_pair = sc_vec + 2 * 4 * 64;                                    // [2 halves][128 rows]
     float* s_vmx = s_pair + 2 * 128;                                        // [stage][head][warp 2 | warp 3]
+    float* s_ikl = s_vmx + 8;                                               // [128] inverse plane scales of the landmark keys
+    float* s_a2red = s_ikl + 128;                                           // [2 kinds][2 heads][2 warps] attn2 reductions
     // barriers: K full[2] +0, K empty[2] +16, S done +32, P.V done +40, V full[2] +48, V empty[2] +64, S read out +80,
-    // P in place +88; TMEM slot +96
+    // P in place +88; TMEM slot +96; attn2 product done +104, read out +112
     const uint32_t bars = base + oVec + kA3VecBytes;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kA3VecBytes + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,8 +230,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int tile0 = zi * per;                                             // first key tile of this CTA's range
     const int n_tiles = max(0, min(per, tiles_all - tile0));
     const int h0 = pair * 2;
+    const bool do_attn2 = attn2 != nullptr && zi == 0;
 
     if (tid == 0) {
+        mbar_init(bars + 104, 2);                                           // attn2 products done (one commit per issuer)
+        mbar_init(bars + 112, 256);                                         // attn2 logits read out
         mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
         mbar_init(bars + 16, 2); mbar_init(bars + 24, 2);                   // K empty (one commit per issuer)
         mbar_init(bars + 32, 2);                                            // S products done
@@ -253,6 +266,14 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             const float m0 = warp_max(sc0), m1 = warp_max(sc1);
             if (lane == 0) { s_vmx[0 * 2 + (warp - 2)] = m0; s_vmx[1 * 2 + (warp - 2)] = m1; }
         }
+    } else if (tid < 256 && do_attn2) {
+        // landmark keys of both heads -> K-major B operand planes in the P tile: head hh at hh * 16 KB, hi then lo
+        const int t = tid - 128, hh = t >> 6, j = t & 63;
+        float kl[64];
+        load_row64(kl, k_land + (((size_t)v * kHeads + h0 + hh) * kLandmark + j) * kDimHead);
+        const int e = scale_exp(absmax64(kl));
+        s_ikl[t] = ldexpf(1.f, -e);
+        store_row64(g + oP + hh * 16384, g + oP + hh * 16384 + 8192, j, kl, ldexpf(1.f, e));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -289,6 +310,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             // ---- MMA issuer of head ih: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
             const uint32_t ih = (uint32_t)(warp - 9);
             bool mok = true;
+            if (do_attn2) {
+                tc_fence_after();
+                issue_split_mma64<false>(tmem_base + ih * 128u, tmem_base + ih * 128u + 64u, base + oQl, base + oQl + 16384,
+                                         base + oP + ih * 16384u, base + oP + ih * 16384u + 8192);
+                umma_commit(bars + 104);
+                mok = mbar_wait(bars + 112, 0u);                            // logits read out: the S accumulators are free
+            }
             auto issue_s = [&](int i) {
                 const int s1 = i & 1;
                 mok = mbar_wait(bars + 8 * s1, (uint32_t)(i >> 1) & 1u) && mok;         // K of that tile has landed
@@ -335,6 +363,60 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         float alpha_prev = 1.f, inv_p_prev = 1.f;
         bool ok = true;
         named_bar_sync(1, 256);                                             // everyone has read inv_ql out of s_pair
+        if (do_attn2) {
+            // ---- attn2 rows of this thread's head: softmax over the 64 landmark keys (32 per thread of the row pair) ----
+            bool aok = mbar_wait(bars + 104, 0u);
+            tc_fence_after();
+            float p[32];
+            tmem_read32_sum(tS, tS + 64u, p);
+            tc_fence_before();
+            mbar_arrive(bars + 112);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { p[j] *= inv_ql * s_ikl[hh * 64 + half * 32 + j]; mx = fmaxf(mx, p[j]); }
+            s_pair[half * 128 + row] = mx;
+            named_bar_sync(1, 256);
+            mx = fmaxf(mx, s_pair[(half ^ 1) * 128 + row]);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
+            named_bar_sync(1, 256);                                         // maxima consumed: s_pair carries the sums now
+            s_pair[half * 128 + row] = sum;
+            named_bar_sync(1, 256);
+            sum += s_pair[(half ^ 1) * 128 + row];
+            // the landmark-key planes are dead (the product has completed): the P tile holds the probabilities as fp32
+            // [128 rows][64] for the column sums
+            float* a2s = reinterpret_cast<float*>(g + oP);
+            float rsum = 0.f;
+            float* dst = attn2 + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kLandmark + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 o = make_float4(p[j] / sum, p[j + 1] / sum, p[j + 2] / sum, p[j + 3] / sum);
+                rsum += (o.x + o.y) + (o.z + o.w);
+                st4(dst + j, o);
+                st4(a2s + row * 64 + half * 32 + j, o);
+            }
+            named_bar_sync(1, 256);                                         // (also: everyone is done with the sums in s_pair)
+            s_pair[half * 128 + row] = rsum;
+            // column sums: thread (half 0, row) <-> column (row & 63) of head hh, the 64 rows in order
+            float csum = 0.f;
+            if (half == 0) {
+                const float* col = a2s + hh * 64 * 64 + (row & 63);
+                for (int i = 0; i < 64; ++i) csum += col[i * 64];
+            }
+            named_bar_sync(1, 256);
+            if (half == 0) {
+                const float rmax = warp_max(rsum + s_pair[128 + row]), cmax = warp_max(csum);
+                if (lane == 0) { s_a2red[(0 * 2 + hh) * 2 + (warp & 1)] = rmax; s_a2red[(1 * 2 + hh) * 2 + (warp & 1)] = cmax; }
+            }
+            named_bar_sync(1, 256);
+            if (aok && half == 0 && (row & 63) == 0) {
+                float* sp = stats + ((size_t)v * kHeads + h0 + hh) * 2;
+                sp[0] = fmaxf(s_a2red[(0 * 2 + hh) * 2], s_a2red[(0 * 2 + hh) * 2 + 1]);
+                sp[1] = fmaxf(s_a2red[(1 * 2 + hh) * 2], s_a2red[(1 * 2 + hh) * 2 + 1]);
+            }
+            // (the first P store of the key loop comes after two more barriers of this group: the column sums are done)
+        }
         auto collect_pv = [&]() {
             ok = mbar_wait(bars + 40, pv_phase) && ok;
             pv_phase ^= 1u;

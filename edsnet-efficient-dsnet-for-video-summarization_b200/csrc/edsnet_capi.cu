@@ -235,7 +235,11 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         else landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
         CU_CHECK(cudaGetLastError(), "landmarks_kernel");
     }
-    {
+    // EDSNET_ATTN2_VARIANT=1: the stand-alone CUDA-core kernel also on the tcgen05 path (cross-check); by default the
+    // a3v kernel produces attn2 and its magnitudes itself
+    static const int attn2_variant = [] { const char* e = getenv("EDSNET_ATTN2_VARIANT"); return e ? atoi(e) : 0; }();
+    const bool attn2_fused = tcp && attn2_variant == 0;
+    if (!attn2_fused) {
         StageScope scope(ST_ATTN2, st);
         attn2_kernel<<<dim3(kHeads, V), 256, 0, st>>>(q_land, k_land, attn2, stats);
         CU_CHECK(cudaGetLastError(), "attn2_kernel");
@@ -245,8 +249,8 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (tcp) {
             // a3_part (edsnet_forward / edsnet_train_forward pass it): room for a3v_split_cap(V) key ranges per (video, head)
             const int z = a3_part ? a3v_splits(V, b->max_rows) : 1;
-            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), tc::kA3Threads, tc::kA3SmemBytes, st>>>(map_hi, map_lo, qkv_inv, b->cu_rows,
-                                                                                   q_land, a3v, a3_part);
+            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), tc::kA3Threads, tc::kA3SmemBytes, st>>>(
+                map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v, a3_part, k_land, attn2_fused ? attn2 : nullptr, stats);
             if (z > 1) {
                 CU_CHECK(cudaGetLastError(), "a3v_tc_kernel");
                 tc::a3v_merge_kernel<<<dim3(kHeads, V), 256, 0, st>>>(a3_part, z, a3v);
@@ -817,11 +821,12 @@ int edsnet_cnn_avgpool_l2norm(const edsnet_cnn_input* in, int32_t n_img, int32_t
 
 int edsnet_forward_launches(const edsnet_config* cfg) {
     if (!cfg) return -1;
-    // qkv, 5 x nystrom core, to_out, layernorm, fc1, fc stack, roi+heads; tcgen05 modes add the operand split of x
+    // qkv, 5 x nystrom core (4 on the tcgen05 path: attn2 is produced by the a3v kernel), to_out, layernorm, fc1, fc stack,
+    // roi+heads; tcgen05 modes add the operand split of x
     // (and of merged for the attention base) and run the value convolution as its own kernel; fp16x3 with the Nystrom
     // base has no LayerNorm kernel (folded into to_out's and fc1's epilogues)
     if (cfg->base_model == EDSNET_BASE_ATTENTION) return cfg->precision == EDSNET_PREC_FP32 ? 7 : 10;
-    return cfg->precision == EDSNET_PREC_FP32 ? 11 : (cfg->precision == EDSNET_PREC_FP16 ? 13 : 12);
+    return cfg->precision == EDSNET_PREC_FP32 ? 11 : (cfg->precision == EDSNET_PREC_FP16 ? 12 : 11);
 }
 
 int edsnet_decode_boxes(const edsnet_config* cfg, const edsnet_batch* batch, const float* pred_loc,

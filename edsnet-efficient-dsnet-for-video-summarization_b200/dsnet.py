@@ -403,7 +403,7 @@ class DSNet(nn.Module):
     # ------------------------------------------------------------------ CUDA-graph replay for repeated shapes
     def graphed_forward(self, lengths: Sequence[int], device=None):
         """Capture `forward_packed` for one fixed list of video lengths into a CUDA graph and return
-        `run(x) -> (pred_cls, pred_loc)`.  A single TVSum-sized video is 12 launches of a few microseconds each, so the
+        `run(x) -> (pred_cls, pred_loc)`.  A single TVSum-sized video is 11 launches of a few microseconds each, so the
         eager call is bound by launch latency; a replay submits them with one driver call.  `run` copies x into the
         graph's static input and returns views of its static outputs (overwritten by the next call).  The graph holds
         the weights' operand planes of the moment: capture again after a parameter update.  eval() / no_grad only."""

@@ -19,8 +19,8 @@ _VIDEO_DT = np.dtype([("scratch_off", np.int64), ("row0", np.int32), ("n", np.in
 def gram_tensor_core(xv: torch.Tensor, out: torch.Tensor) -> None:
     """out (n x n float32 view, row-major) <- X X^T of one video's features (video_helper.py:117) on the tcgen05 GEMM:
     the rows go through the operand-plane gather (`edsnet_cnn_im2col` as a 1 x 1 gather: fp16 hi / lo planes, one
-    power-of-two scale per row) and ONE product with A = B = those planes, three split-fp16 passes (fp32-grade: the
-    entries agree with a float32 matmul to ~5e-7, which is also what two BLAS libraries differ by).  Rows are padded to
+    power-of-two scale per row) and ONE product with A = B = those planes, three split-fp16 passes (the entries agree
+    with the float64 product to ~1e-6: the truncating fp32 accumulation of the tensor core).  Rows are padded to
     the GEMM's 128-column granularity; torch only moves data here."""
     import ctypes as C
     from .features import _Act
