@@ -139,6 +139,26 @@ __device__ __forceinline__ void issue_split_mma64(uint32_t acc_main, uint32_t ac
     }
 }
 
+// Both heads of a pair in one instruction: the left operand stacks the two heads along M (rows 0..63 | 64..127), the four
+// right-operand planes (head 0 hi, head 0 lo, head 1 hi, head 1 lo) lie 8 KB apart and form ONE N = 256 operand, and the
+// accumulators (head 0 main | cross | head 1 main | cross) are 256 adjacent TMEM columns.  A_hi B and A_lo B: two
+// instructions per K step, 8 per product pair instead of 16.  Each accumulator half receives the products of both rows
+// blocks (only its own head's block is read), and all four terms hi.hi + hi.lo + lo.hi + lo.lo are summed (the lo.lo term,
+// 2^-22 relative, comes for free).  The tensor core takes an instruction every ~90 cycles from one SM, whatever its size
+// (clock64 probes: two issuing warps did not issue faster than one), so the instruction count is what paces these
+// small-tile kernels.
+template <bool B_MN>
+__device__ __forceinline__ void issue_pair_mma64(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
+    constexpr uint32_t idesc = B_MN ? make_idesc_bmn(128, 256) : make_idesc(128, 256);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ka = (uint32_t)k * 32u, kb = B_MN ? (uint32_t)k * 2048u : (uint32_t)k * 32u;
+        const uint64_t db = B_MN ? make_smem_desc_mn2(b + kb) : make_smem_desc<64>(b + kb);
+        umma_f16(acc, make_smem_desc<64>(a_hi + ka), db, idesc, k != 0 ? 1u : 0u);
+        umma_f16(acc, make_smem_desc<64>(a_lo + ka), db, idesc, 1u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // landmarks from the planes: q_land / k_land [V][8][64][64] fp32 = mean over each block of `seg` padded rows.
 // grid (64 landmarks, V), 256 threads; thread owns 4 consecutive columns of the 1024 q|k columns.
@@ -187,11 +207,10 @@ constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32 + 128 * 4 + 64;   
                                                                             // + landmark-key scales [128] + attn2 reductions
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
-// 352 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
-// 32..63), warp 8 = TMA producer, warps 9 and 10 = MMA issuers, one per head of the pair (told by mbarriers when S has
-// been read out / P is in place, so the row warps never wait for an issue loop).  The two heads' products go to
-// different accumulators, so two threads may issue them concurrently: a thread needs ~90 cycles per tcgen05.mma, and a
-// tile's 32 instructions issued by one thread alone took longer than the tile's softmax.
+// 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
+// 32..63), warp 8 = TMA producer, warp 9 = MMA issuer (told by mbarriers when S has been read out / P is in place, so
+// the row warps never wait for an issue loop).  Both heads' products are one instruction pair per K step
+// (issue_pair_mma64): 16 tcgen05.mma per key tile (48 in round 1).
 // gridDim.z > 1 (few, long videos: one video would otherwise keep 4 of 148 SMs busy): CTA z streams the z-th contiguous
 // range of key tiles and leaves its un-normalised output rows and (running max, sum) in `part` [V][8][Z][64][66];
 // a3v_merge_kernel combines the ranges (flash-decoding style).  The zero pad keys belong to range 0.
@@ -202,7 +221,7 @@ constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 
 // P tile as a K-major B operand, one extra product per head into the S accumulators.  The key / value ring fills
 // meanwhile.  This replaces attn2_kernel (a launch of its own with 64^3 FFMA products per head) on the tcgen05 path.
 constexpr int kA3PartLd = 66;
-constexpr int kA3Threads = 352;
+constexpr int kA3Threads = 320;
 __global__ void __launch_bounds__(kA3Threads, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
@@ -233,14 +252,14 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const bool do_attn2 = attn2 != nullptr && zi == 0;
 
     if (tid == 0) {
-        mbar_init(bars + 104, 2);                                           // attn2 products done (one commit per issuer)
+        mbar_init(bars + 104, 1);                                           // attn2 products done
         mbar_init(bars + 112, 256);                                         // attn2 logits read out
         mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
-        mbar_init(bars + 16, 2); mbar_init(bars + 24, 2);                   // K empty (one commit per issuer)
-        mbar_init(bars + 32, 2);                                            // S products done
-        mbar_init(bars + 40, 2);                                            // P.V products done
+        mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // K empty
+        mbar_init(bars + 32, 1);                                            // S products done
+        mbar_init(bars + 40, 1);                                            // P.V products done
         mbar_init(bars + 48, 1); mbar_init(bars + 56, 1);                   // V full
-        mbar_init(bars + 64, 2); mbar_init(bars + 72, 2);                   // V empty
+        mbar_init(bars + 64, 1); mbar_init(bars + 72, 1);                   // V empty
         mbar_init(bars + 80, 256);                                          // every row thread has read S
         mbar_init(bars + 88, 256);                                          // every row thread has stored P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,15 +324,13 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 9 || warp == 10) {
+    } else if (warp == 9) {
         if (lane == 0) {
-            // ---- MMA issuer of head ih: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
-            const uint32_t ih = (uint32_t)(warp - 9);
+            // ---- MMA issuer: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
             bool mok = true;
             if (do_attn2) {
                 tc_fence_after();
-                issue_split_mma64<false>(tmem_base + ih * 128u, tmem_base + ih * 128u + 64u, base + oQl, base + oQl + 16384,
-                                         base + oP + ih * 16384u, base + oP + ih * 16384u + 8192);
+                issue_pair_mma64<false>(tmem_base, base + oQl, base + oQl + 16384, base + oP);
                 umma_commit(bars + 104);
                 mok = mbar_wait(bars + 112, 0u);                            // logits read out: the S accumulators are free
             }
@@ -321,9 +338,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 const int s1 = i & 1;
                 mok = mbar_wait(bars + 8 * s1, (uint32_t)(i >> 1) & 1u) && mok;         // K of that tile has landed
                 tc_fence_after();
-                const uint32_t st1 = base + oKV + s1 * kA3Stage + ih * 16384u;
-                issue_split_mma64<false>(tmem_base + ih * 128u, tmem_base + ih * 128u + 64u, base + oQl, base + oQl + 16384,
-                                         st1, st1 + 8192);
+                issue_pair_mma64<false>(tmem_base, base + oQl, base + oQl + 16384, base + oKV + s1 * kA3Stage);
                 umma_commit(bars + 32);
                 umma_commit(bars + 16 + 8 * s1);                            // K half of the stage free after the S products
             };
@@ -338,8 +353,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 mok = mbar_wait(bars + 48 + 8 * s, (uint32_t)(i >> 1) & 1u) && mok;     // V of this tile has landed
                 mok = mbar_wait(bars + 88, (uint32_t)i & 1u) && mok;        // P(i) stored, O(i-1) read by everyone
                 tc_fence_after();
-                issue_split_mma64<true>(tmem_base + 256u + ih * 128u, tmem_base + 320u + ih * 128u, base + oP, base + oP + 16384,
-                                        st + 32768 + ih * 16384u, st + 32768 + ih * 16384u + 8192);
+                issue_pair_mma64<true>(tmem_base + 256u, base + oP, base + oP + 16384, st + 32768);
                 umma_commit(bars + 40);
                 umma_commit(bars + 64 + 8 * s);                             // V half of the stage free after P.V
             }
