@@ -744,13 +744,17 @@ def bench_c2(args, D):
     # capture of the three-pass kernel (profiles/r01m_kernels_full.md, 229 489-row launch) scaled to this launch's rows,
     # and only quoted for that mode.
     alg_bytes_row = (4096 if passes == 3 else 2048) + 6144 + 96
-    traffic = (0.967633e9 + 1.392453e9) * rows_per_launch / 229489.0 if passes == 3 else None
+    # per 229 489-row launch: three passes 0.968 GB read + 1.392 GB written (r01m), two passes 0.478 + 1.382 GB (r02s: the
+    # x lo plane is neither written nor read)
+    cap = {3: (0.967633e9 + 1.392453e9, "profiles/r01m_kernels_full.md"),
+           2: (0.478e9 + 1.382e9, "profiles/r02s_kernels_full_fp16x2.md")}.get(passes)
+    traffic = cap[0] * rows_per_launch / 229489.0 if cap else None
     roofline = {"kernel": f"gemm_tc_kernel<BN128,BK64,{passes} passes,QKV_PLANES> (to_qkv, fp16 hi/lo split operands, epilogue "
                           "writes the q|k|v operand planes)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": peak_src, "traffic": traffic,
-                "traffic_source": "static: ncu --set full capture of a 229 489-row launch of the 3-pass kernel "
-                                  "(profiles/r01m_kernels_full.md), bytes per row x rows of this launch; null for other modes",
+                "traffic_source": (f"static: ncu --set full capture of a 229 489-row launch of the {passes}-pass kernel "
+                                   f"({cap[1]}), bytes per row x rows of this launch") if cap else "null: no capture of this mode",
                 "algorithmic_bytes_per_launch": rows_per_launch * alg_bytes_row,
                 "mma_passes": passes, "frac_counting_passes": passes * achieved / peak_tf,
                 "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": avg_ms, "instrumented_steps": inst_steps,
