@@ -101,6 +101,34 @@ __device__ __forceinline__ void tmem_read32_sum(uint32_t t_main, uint32_t t_lo, 
         for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
     }
 }
+// sum of the hi.hi and cross-term accumulators for 16 columns of this thread's row
+__device__ __forceinline__ void tmem_read16_sum(uint32_t t_main, uint32_t t_lo, float (&v)[16]) {
+    uint32_t r0[16], r1[16];
+    tmem_ld16_nowait(t_main, r0);
+    tmem_ld16_nowait(t_lo, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+}
+// a quarter row (16 values, two 16-byte chunks chunk0, chunk0 + 1) -> the hi and lo planes of row r
+__device__ __forceinline__ void store_row16(unsigned char* hi, unsigned char* lo, int r, int chunk0, const float (&v)[16],
+                                            float mul) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        __half2 hh[4], ll[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float v0 = v[c * 8 + 2 * q] * mul, v1 = v[c * 8 + 2 * q + 1] * mul;
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h);
+            hh[q] = h;
+            ll[q] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        }
+        const uint32_t off = sw128_off(r, chunk0 + c);
+        *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(hh);
+        *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(ll);
+    }
+}
 // sum of the hi.hi and cross-term accumulators for 64 columns of this thread's row
 __device__ __forceinline__ void tmem_read64_sum(uint32_t t_main, uint32_t t_lo, float (&v)[64]) {
 #pragma unroll
@@ -202,15 +230,16 @@ landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict_
 // TMEM 512 columns: S0 S1 O0 O1, each main | cross (64 + 64).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kA3Stage = 8 * 8192;                                          // k_h0 k_h1 v_h0 v_h1, hi and lo
-constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 2 * 128 * 4 + 32 + 128 * 4 + 64;   // key scales [2 stages][4][64] + pair exchange
+constexpr int kA3VecBytes = 2 * 4 * 64 * 4 + 4 * 128 * 4 + 32 + 128 * 4 + 64;   // key scales [2 stages][4][64] + row exchange [4][128]
                                                                             // + largest v scale [2 stages][2 heads][2 warps]
                                                                             // + landmark-key scales [128] + attn2 reductions
 constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 1024;
 
-// 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: keys / output columns 0..31 and
-// 32..63), warp 8 = TMA producer, warp 9 = MMA issuer (told by mbarriers when S has been read out / P is in place, so
-// the row warps never wait for an issue loop).  Both heads' products are one instruction pair per K step
-// (issue_pair_mma64): 16 tcgen05.mma per key tile (48 in round 1).
+// 576 threads: warps 0..15 = rows -- FOUR threads per accumulator row (t, t + 128, t + 256, t + 384 share row t & 127 and
+// own 16 keys / output columns each: clock64 probes showed the per-row softmax chain of two threads with 32 columns
+// each, 3 900 cycles per key tile, as what paces this kernel, not the 16 MMA instructions), warp 16 = TMA producer,
+// warp 17 = MMA issuer (told by mbarriers when S has been read out / P is in place, so the row warps never wait for an
+// issue loop).  Both heads' products are one instruction pair per K step (issue_pair_mma64).
 // gridDim.z > 1 (few, long videos: one video would otherwise keep 4 of 148 SMs busy): CTA z streams the z-th contiguous
 // range of key tiles and leaves its un-normalised output rows and (running max, sum) in `part` [V][8][Z][64][66];
 // a3v_merge_kernel combines the ranges (flash-decoding style).  The zero pad keys belong to range 0.
@@ -221,19 +250,19 @@ constexpr int kA3SmemBytes = 32768 + 2 * kA3Stage + 32768 + kA3VecBytes + 128 + 
 // P tile as a K-major B operand, one extra product per head into the S accumulators.  The key / value ring fills
 // meanwhile.  This replaces attn2_kernel (a launch of its own with 64^3 FFMA products per head) on the tcgen05 path.
 constexpr int kA3PartLd = 66;
-constexpr int kA3Threads = 320;
+constexpr int kA3Threads = 576, kA3RowThreads = 512;
 __global__ void __launch_bounds__(kA3Threads, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
-              float* __restrict__ a3v, float* __restrict__ part, const float* __restrict__ k_land,
+              float* __restrict__ a3v, float* __restrict__ part_out, const float* __restrict__ k_land,
               float* __restrict__ attn2, float* __restrict__ stats) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
     constexpr int oQl = 0, oKV = 32768, oP = 32768 + 2 * kA3Stage, oVec = oP + 32768;
     float* sc_vec = reinterpret_cast<float*>(g + oVec);                     // [stage][k_h0 k_h1 v_h0 v_h1][64]
-    float* s_pair = sc_vec + 2 * 4 * 64;                                    // [2 halves][128 rows]
-    float* s_vmx = s_pair + 2 * 128;                                        // [stage][head][warp 2 | warp 3]
+    float* s_pair = sc_vec + 2 * 4 * 64;                                    // [4 parts][128 rows]
+    float* s_vmx = s_pair + 4 * 128;                                        // [stage][head][warp 2 | warp 3]
     float* s_ikl = s_vmx + 8;                                               // [128] inverse plane scales of the landmark keys
     float* s_a2red = s_ikl + 128;                                           // [2 kinds][2 heads][2 warps] attn2 reductions
     // barriers: K full[2] +0, K empty[2] +16, S done +32, P.V done +40, V full[2] +48, V empty[2] +64, S read out +80,
@@ -253,46 +282,69 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 
     if (tid == 0) {
         mbar_init(bars + 104, 1);                                           // attn2 products done
-        mbar_init(bars + 112, 256);                                         // attn2 logits read out
+        mbar_init(bars + 112, kA3RowThreads);                               // attn2 logits read out
         mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
         mbar_init(bars + 16, 1); mbar_init(bars + 24, 1);                   // K empty
         mbar_init(bars + 32, 1);                                            // S products done
         mbar_init(bars + 40, 1);                                            // P.V products done
         mbar_init(bars + 48, 1); mbar_init(bars + 56, 1);                   // V full
         mbar_init(bars + 64, 1); mbar_init(bars + 72, 1);                   // V empty
-        mbar_init(bars + 80, 256);                                          // every row thread has read S
-        mbar_init(bars + 88, 256);                                          // every row thread has stored P
+        mbar_init(bars + 80, kA3RowThreads);                                // every row thread has read S
+        mbar_init(bars + 88, kA3RowThreads);                                // every row thread has stored P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(bars + 96, 512);
+    if (warp == 16) tmem_alloc(bars + 96, 512);
     float inv_ql = 1.f;
-    if (tid < 128) {
-        // landmark queries of both heads -> A operand planes (row t), per-row scale
-        float q[64];
-        load_row64(q, q_land + (((size_t)v * kHeads + h0 + (tid >> 6)) * kLandmark + (tid & 63)) * kDimHead);
-        const int e = scale_exp(absmax64(q));
-        inv_ql = ldexpf(1.f, -e);
-        s_pair[tid] = inv_ql;
-        store_row64(g + oQl, g + oQl + 16384, tid, q, ldexpf(1.f, e));
-        // scales of the first tile: thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
-        const int key = tile0 * 64 + (tid & 63), qkv_part = 1 + (tid >> 6);
-        const bool in = key < vi.T;
-        const float* ip = inv + (size_t)(vi.row0 + (in ? key : 0)) * 24 + qkv_part * 8 + h0;
-        const float sc0 = in ? __ldg(ip) : 0.f, sc1 = in ? __ldg(ip + 1) : 0.f;
-        sc_vec[((tid >> 6) * 2 + 0) * 64 + (tid & 63)] = sc0;
-        sc_vec[((tid >> 6) * 2 + 1) * 64 + (tid & 63)] = sc1;
-        if (tid >= 64) {                                   // warps 2, 3 hold the v scales: their maxima per head
-            const float m0 = warp_max(sc0), m1 = warp_max(sc1);
-            if (lane == 0) { s_vmx[0 * 2 + (warp - 2)] = m0; s_vmx[1 * 2 + (warp - 2)] = m1; }
+    // Prologue (a clock64 probe put it at 8 000 cycles with one thread per 64-value row, a third of an average CTA's
+    // life, and nothing overlaps it at one CTA per SM): two threads per row, lanes 2r and 2r + 1 of the same warp, the row
+    // maximum through one shuffle; all global loads issued before the first dependent use.
+    if (tid < 256) {
+        // landmark queries of both heads -> A operand planes (row r), per-row scale
+        const int r = tid >> 1, hf = tid & 1;
+        float q[32];
+        const float* src = q_land + (((size_t)v * kHeads + h0 + (r >> 6)) * kLandmark + (r & 63)) * kDimHead + hf * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 x = ldg4(src + j);
+            q[j] = x.x; q[j + 1] = x.y; q[j + 2] = x.z; q[j + 3] = x.w;
         }
-    } else if (tid < 256 && do_attn2) {
+        // scales of the first tile (threads 0..127): thread t < 64 -> key t: k scales of both heads; 64 <= t < 128 -> v scales
+        float sc0 = 0.f, sc1 = 0.f;
+        if (tid < 128) {
+            const int key = tile0 * 64 + (tid & 63), qkv_part = 1 + (tid >> 6);
+            if (key < vi.T) {
+                const float* ip = inv + (size_t)(vi.row0 + key) * 24 + qkv_part * 8 + h0;
+                sc0 = __ldg(ip); sc1 = __ldg(ip + 1);
+            }
+        }
+        float mx = absmax32(q);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        const int e = scale_exp(mx);
+        if (hf == 0) s_pair[r] = ldexpf(1.f, -e);
+        store_row32(g + oQl, g + oQl + 16384, r, hf * 4, q, ldexpf(1.f, e));
+        if (tid < 128) {
+            sc_vec[((tid >> 6) * 2 + 0) * 64 + (tid & 63)] = sc0;
+            sc_vec[((tid >> 6) * 2 + 1) * 64 + (tid & 63)] = sc1;
+            if (tid >= 64) {                               // warps 2, 3 hold the v scales: their maxima per head
+                const float m0 = warp_max(sc0), m1 = warp_max(sc1);
+                if (lane == 0) { s_vmx[0 * 2 + (warp - 2)] = m0; s_vmx[1 * 2 + (warp - 2)] = m1; }
+            }
+        }
+    } else if (tid < kA3RowThreads && do_attn2) {
         // landmark keys of both heads -> K-major B operand planes in the P tile: head hh at hh * 16 KB, hi then lo
-        const int t = tid - 128, hh = t >> 6, j = t & 63;
-        float kl[64];
-        load_row64(kl, k_land + (((size_t)v * kHeads + h0 + hh) * kLandmark + j) * kDimHead);
-        const int e = scale_exp(absmax64(kl));
-        s_ikl[t] = ldexpf(1.f, -e);
-        store_row64(g + oP + hh * 16384, g + oP + hh * 16384 + 8192, j, kl, ldexpf(1.f, e));
+        const int t = tid - 256, r = t >> 1, hf = t & 1, hh = r >> 6, j = r & 63;
+        float kl[32];
+        const float* src = k_land + (((size_t)v * kHeads + h0 + hh) * kLandmark + j) * kDimHead + hf * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            const float4 x = ldg4(src + c);
+            kl[c] = x.x; kl[c + 1] = x.y; kl[c + 2] = x.z; kl[c + 3] = x.w;
+        }
+        float mx = absmax32(kl);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        const int e = scale_exp(mx);
+        if (hf == 0) s_ikl[r] = ldexpf(1.f, -e);
+        store_row32(g + oP + hh * 16384, g + oP + hh * 16384 + 8192, j, hf * 4, kl, ldexpf(1.f, e));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -300,7 +352,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 8) {
+    if (warp == 16) {
         if (lane == 0) {
             // ---- TMA producer: 8 boxes of 64 rows x 64 columns per tile.  The K half of a stage is released by the
             // S products, the V half by the P.V products, so the K tiles run one tile further ahead than the V tiles ----
@@ -324,7 +376,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         if (lane == 0) {
             // ---- MMA issuer: S(i+1) as soon as S(i) has been read out, P.V(i) as soon as P(i) is in place ----
             bool mok = true;
@@ -359,72 +411,82 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             }
         }
     } else {
-        const int row = tid & 127, half = tid >> 7;
+        constexpr int NR = kA3RowThreads;
+        const int row = tid & 127, part = tid >> 7;                         // part p owns keys / columns 16 p .. 16 p + 15
         const int hh = row >> 6;                                            // which head of the pair this row belongs to
         inv_ql = s_pair[row];
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(hh * 128 + half * 32), tO = tS + 256u;
-        float o[32];
+        const uint32_t tS = tmem_base + lane_addr + (uint32_t)(hh * 128 + part * 16), tO = tS + 256u;
+        float o[16];
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o[d] = 0.f;
-        // running max is shared by the two threads of a row; the running sum is per thread (its keys) and merged at the end
+        for (int d = 0; d < 16; ++d) o[d] = 0.f;
+        // the maximum of a value over the four threads of a row (exchange through s_pair; ends with everyone past the reads)
+        auto row_max4 = [&](float x) -> float {
+            s_pair[part * 128 + row] = x;
+            named_bar_sync(1, NR);
+            return fmaxf(fmaxf(s_pair[row], s_pair[128 + row]), fmaxf(s_pair[256 + row], s_pair[384 + row]));
+        };
+        auto row_sum4 = [&](float x) -> float {
+            s_pair[part * 128 + row] = x;
+            named_bar_sync(1, NR);
+            return (s_pair[row] + s_pair[128 + row]) + (s_pair[256 + row] + s_pair[384 + row]);
+        };
+        // running max is shared by the four threads of a row; the running sum is per thread (its keys) and merged at the end
         const bool pads_here = vi.pad > 0 && zi == 0;                       // the zero pad keys: logit 0, value 0
-        float run_max = pads_here ? 0.f : -INFINITY, run_sum = (half == 0 && pads_here) ? (float)vi.pad : 0.f;
+        float run_max = pads_here ? 0.f : -INFINITY, run_sum = (part == 0 && pads_here) ? (float)vi.pad : 0.f;
         // Software pipeline over the key tiles: S(i+1) is issued as soon as every thread has pulled S(i) out of TMEM,
         // so it runs under the softmax of tile i; the P.V product of tile i is only collected in iteration i+1, after
         // that tile's softmax arithmetic, so it runs under the S read-out and the exponentials of tile i+1.
         uint32_t s_phase = 0, pv_phase = 0;
         float alpha_prev = 1.f, inv_p_prev = 1.f;
         bool ok = true;
-        named_bar_sync(1, 256);                                             // everyone has read inv_ql out of s_pair
+        named_bar_sync(1, NR);                                              // everyone has read inv_ql out of s_pair
         if (do_attn2) {
-            // ---- attn2 rows of this thread's head: softmax over the 64 landmark keys (32 per thread of the row pair) ----
+            // ---- attn2 rows of this thread's head: softmax over the 64 landmark keys (16 per thread of the row) ----
             bool aok = mbar_wait(bars + 104, 0u);
             tc_fence_after();
-            float p[32];
-            tmem_read32_sum(tS, tS + 64u, p);
+            float p[16];
+            tmem_read16_sum(tS, tS + 64u, p);
             tc_fence_before();
             mbar_arrive(bars + 112);
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { p[j] *= inv_ql * s_ikl[hh * 64 + half * 32 + j]; mx = fmaxf(mx, p[j]); }
-            s_pair[half * 128 + row] = mx;
-            named_bar_sync(1, 256);
-            mx = fmaxf(mx, s_pair[(half ^ 1) * 128 + row]);
+            for (int j = 0; j < 16; ++j) { p[j] *= inv_ql * s_ikl[hh * 64 + part * 16 + j]; mx = fmaxf(mx, p[j]); }
+            mx = row_max4(mx);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
-            named_bar_sync(1, 256);                                         // maxima consumed: s_pair carries the sums now
-            s_pair[half * 128 + row] = sum;
-            named_bar_sync(1, 256);
-            sum += s_pair[(half ^ 1) * 128 + row];
+            for (int j = 0; j < 16; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
+            named_bar_sync(1, NR);                                          // maxima consumed: s_pair carries the sums now
+            sum = row_sum4(sum);
             // the landmark-key planes are dead (the product has completed): the P tile holds the probabilities as fp32
             // [128 rows][64] for the column sums
             float* a2s = reinterpret_cast<float*>(g + oP);
             float rsum = 0.f;
-            float* dst = attn2 + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kLandmark + half * 32;
+            float* dst = attn2 + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kLandmark + part * 16;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 o = make_float4(p[j] / sum, p[j + 1] / sum, p[j + 2] / sum, p[j + 3] / sum);
-                rsum += (o.x + o.y) + (o.z + o.w);
-                st4(dst + j, o);
-                st4(a2s + row * 64 + half * 32 + j, o);
+            for (int j = 0; j < 16; j += 4) {
+                const float4 q4 = make_float4(p[j] / sum, p[j + 1] / sum, p[j + 2] / sum, p[j + 3] / sum);   // (exact divisions: attn2 feeds the ill-conditioned chain)
+                rsum += (q4.x + q4.y) + (q4.z + q4.w);
+                st4(dst + j, q4);
+                st4(a2s + row * 64 + part * 16 + j, q4);
             }
-            named_bar_sync(1, 256);                                         // (also: everyone is done with the sums in s_pair)
-            s_pair[half * 128 + row] = rsum;
-            // column sums: thread (half 0, row) <-> column (row & 63) of head hh, the 64 rows in order
+            named_bar_sync(1, NR);                                          // (also: everyone is done with the sums in s_pair)
+            rsum = row_sum4(rsum);
+            // column sums: thread (part 0, row) <-> column (row & 63) of head hh, the 64 rows in order
             float csum = 0.f;
-            if (half == 0) {
+            if (part == 0) {
                 const float* col = a2s + hh * 64 * 64 + (row & 63);
-                for (int i = 0; i < 64; ++i) csum += col[i * 64];
-            }
-            named_bar_sync(1, 256);
-            if (half == 0) {
-                const float rmax = warp_max(rsum + s_pair[128 + row]), cmax = warp_max(csum);
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;                // four chains, combined in a fixed order
+#pragma unroll 4
+                for (int i = 0; i < 64; i += 4) {
+                    c0 += col[i * 64]; c1 += col[(i + 1) * 64]; c2 += col[(i + 2) * 64]; c3 += col[(i + 3) * 64];
+                }
+                csum = (c0 + c1) + (c2 + c3);
+                const float rmax = warp_max(rsum), cmax = warp_max(csum);
                 if (lane == 0) { s_a2red[(0 * 2 + hh) * 2 + (warp & 1)] = rmax; s_a2red[(1 * 2 + hh) * 2 + (warp & 1)] = cmax; }
             }
-            named_bar_sync(1, 256);
-            if (aok && half == 0 && (row & 63) == 0) {
+            named_bar_sync(1, NR);
+            if (aok && part == 0 && (row & 63) == 0) {
                 float* sp = stats + ((size_t)v * kHeads + h0 + hh) * 2;
                 sp[0] = fmaxf(s_a2red[(0 * 2 + hh) * 2], s_a2red[(0 * 2 + hh) * 2 + 1]);
                 sp[1] = fmaxf(s_a2red[(1 * 2 + hh) * 2], s_a2red[(1 * 2 + hh) * 2 + 1]);
@@ -435,10 +497,10 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             ok = mbar_wait(bars + 40, pv_phase) && ok;
             pv_phase ^= 1u;
             tc_fence_after();
-            float pv[32];
-            tmem_read32_sum(tO, tO + 64u, pv);
+            float pv[16];
+            tmem_read16_sum(tO, tO + 64u, pv);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha_prev, pv[d] * inv_p_prev);
+            for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], alpha_prev, pv[d] * inv_p_prev);
         };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
@@ -451,27 +513,25 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                     nsc0 = __ldg(ip); nsc1 = __ldg(ip + 1);
                 }
             }
-            const uint32_t st = base + oKV + s * kA3Stage;
             ok = mbar_wait(bars + 32, s_phase) && ok;
             s_phase ^= 1u;
             tc_fence_after();
-            // ---- this thread's 32 logits of its row ----
-            float p[32];
-            tmem_read32_sum(tS, tS + 64u, p);
-            const float* isk = sc_vec + (s * 4 + hh) * 64 + half * 32;
-            const float* isv = sc_vec + (s * 4 + 2 + hh) * 64 + half * 32;
-            const int kvalid = vi.T - (tile0 + i) * 64 - half * 32;
+            // ---- this thread's 16 logits of its row ----
+            float p[16];
+            tmem_read16_sum(tS, tS + 64u, p);
+            const float* isk = sc_vec + (s * 4 + hh) * 64 + part * 16;
+            const float* isv = sc_vec + (s * 4 + 2 + hh) * 64 + part * 16;
+            const int kvalid = vi.T - (tile0 + i) * 64 - part * 16;
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 p[j] = j < kvalid ? p[j] * (inv_ql * isk[j]) : -INFINITY;
                 mx = fmaxf(mx, p[j]);
             }
             const float vmx = fmaxf(s_vmx[(s * 2 + hh) * 2], s_vmx[(s * 2 + hh) * 2 + 1]);   // largest v scale of the tile
-            s_pair[half * 128 + row] = mx;
             tc_fence_before();
             mbar_arrive(bars + 80);                                         // this thread holds its S(i) values
-            named_bar_sync(1, 256);
+            mx = row_max4(mx);
             // next tile's scales into the other stage's slot: its previous readers (tile i-1) are past their last barrier
             if (tid < 128) {
                 sc_vec[(((i + 1) & 1) * 4 + (tid >> 6) * 2 + 0) * 64 + (tid & 63)] = nsc0;
@@ -484,11 +544,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                     }
                 }
             }
-            const float new_max = fmaxf(run_max, fmaxf(mx, s_pair[(half ^ 1) * 128 + row]));
+            const float new_max = fmaxf(run_max, mx);
             const float alpha = expf(run_max - new_max);                    // exp(-inf) = 0 on a fresh start
             float ps = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float e = expf(p[j] - new_max);                       // 0 for masked keys
                 ps += e;
                 p[j] = e * isv[j];                                          // fold v's per-key scale into P
@@ -497,36 +557,34 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             run_max = new_max;
             // the previous tile's P.V product: its P tile and O accumulator are about to be reused
             if (i > 0) collect_pv();
-            // P' <= max_j isv[j]: one row scale for both halves without another exchange
+            // P' <= max_j isv[j]: one row scale for all four parts without another exchange
             const int ep = scale_exp(vmx);
-            store_row32(g + oP, g + oP + 16384, row, half * 4, p, ldexpf(1.f, ep));
+            store_row16(g + oP, g + oP + 16384, row, part * 2, p, ldexpf(1.f, ep));
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bars + 88);                                         // P(i) stored, O(i-1) read
-            named_bar_sync(1, 256);                                         // scale slots / s_pair reusable
+            named_bar_sync(1, NR);                                          // scale slots / s_pair reusable
             alpha_prev = alpha;
             inv_p_prev = ldexpf(1.f, -ep);
         }
         if (n_tiles > 0 && ok) collect_pv();
-        // merge the two partial sums of the row
-        s_pair[half * 128 + row] = run_sum;
-        named_bar_sync(1, 256);
-        const float tot = run_sum + s_pair[(half ^ 1) * 128 + row];
+        // merge the four partial sums of the row
+        const float tot = row_sum4(run_sum);
         if (ok && zsplit == 1) {
             const float rs = 1.f / tot;
-            float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kDimHead + half * 32;
+            float* dst = a3v + (((size_t)v * kHeads + h0 + hh) * kLandmark + (row & 63)) * kDimHead + part * 16;
 #pragma unroll
-            for (int d = 0; d < 32; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
+            for (int d = 0; d < 16; d += 4) st4(dst + d, make_float4(o[d] * rs, o[d + 1] * rs, o[d + 2] * rs, o[d + 3] * rs));
         } else if (ok) {
-            float* dst = part + ((((size_t)v * kHeads + h0 + hh) * zsplit + zi) * kLandmark + (row & 63)) * kA3PartLd;
+            float* dst = part_out + ((((size_t)v * kHeads + h0 + hh) * zsplit + zi) * kLandmark + (row & 63)) * kA3PartLd;
 #pragma unroll
-            for (int d = 0; d < 32; d += 2) *reinterpret_cast<float2*>(dst + half * 32 + d) = make_float2(o[d], o[d + 1]);
-            if (half == 0) *reinterpret_cast<float2*>(dst + 64) = make_float2(run_max, tot);
+            for (int d = 0; d < 16; d += 2) *reinterpret_cast<float2*>(dst + part * 16 + d) = make_float2(o[d], o[d + 1]);
+            if (part == 0) *reinterpret_cast<float2*>(dst + 64) = make_float2(run_max, tot);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // Combine the key ranges of a3v_tc_kernel: a3v[j][d] = sum_z o_z[j][d] e^(m_z - m) / sum_z l_z e^(m_z - m), m = max_z m_z
