@@ -1117,8 +1117,14 @@ __global__ void __launch_bounds__(320, 1)
 value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                      const float* __restrict__ inv, const int* __restrict__ cu_rows, const int2* __restrict__ tiles,
                      const float* __restrict__ conv_w, const float* __restrict__ attn, const float* __restrict__ w_max,
-                     __half* __restrict__ m_hi, __half* __restrict__ m_lo, float* __restrict__ m_inv, int write_lo) {
+                     __half* __restrict__ m_hi, __half* __restrict__ m_lo, float* __restrict__ m_inv, int write_lo,
+                     int n_tiles) {
     // write_lo == 0: the to_out product that follows runs two passes (A_hi only): the lo plane is not written
+    // Persistent: one CTA per SM walks the 128-row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (a tile is the same work
+    // whatever its video).  A CTA of this size costs 3-4 us to launch on an SM that has just been vacated (globaltimer
+    // probe on the a3v kernel), and the band zeroing, tap staging, barrier set-up and TMEM allocation are per CTA: all of it
+    // is paid once per SM instead of once per tile.  Every barrier completes an even number of phases per tile, so the
+    // parities below repeat from tile to tile.
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
@@ -1133,10 +1139,6 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     const uint32_t bars = base + oVec + kCvVecFloats * 4;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kCvVecFloats * 4 + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int2 tile = tiles[blockIdx.x];
-    const VidInfo vi = vid_info(cu_rows, tile.x);
-    const int r0 = tile.y;
-    const int win0 = vi.row0 + r0 - 16;                                     // packed row of window row 0 (may be < 0)
 
     if (tid == 0) {
         for (int q = 0; q < kCvStages; ++q) { mbar_init(bars + 8 * q, 1); mbar_init(bars + 24 + 8 * q, 1); }
@@ -1144,12 +1146,23 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         mbar_init(bars + 56, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < kHeads) s_vmax[tid] = 0u;
     if (warp == 8) tmem_alloc(bars + 64, 256);
-    // zero the band once (only its 33 diagonals are ever rewritten), stage the taps
+    // zero the band once (only its 33 diagonals are ever rewritten, by every tile in full), stage the taps
     for (int i = tid; i < kCvBandBytes / 16; i += 320) reinterpret_cast<uint4*>(g + oBand)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < kHeads * kTaps; i += 320) s_w[i] = __ldg(conv_w + i);
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    uint32_t phase = 0;                                                     // row threads: parity of the MMA-done barrier
+
+    for (int ti = blockIdx.x; ti < n_tiles; ti += (int)gridDim.x) {
+    const int2 tile = tiles[ti];
+    const VidInfo vi = vid_info(cu_rows, tile.x);
+    const int r0 = tile.y;
+    const int win0 = vi.row0 + r0 - 16;                                     // packed row of window row 0 (may be < 0)
+    if (tid < kHeads) s_vmax[tid] = 0u;
+    __syncthreads();                                                        // (everyone has left the previous tile)
     // inverse v plane scales of the window rows, all heads (0 outside the video: masks the band column)
     for (int i = tid; i < kHeads * 192; i += 320) {
         const int hd = i / 192, j = i - hd * 192;
@@ -1182,10 +1195,7 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     }
     __syncthreads();
     for (int i = tid; i < kHeads * 192; i += 320) s_inv[i] *= s_fc[i / 192];        // band column factors 2^(e_c - sv[j])
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
     const float sc = *s_scale;
 
     if (warp == 8) {
@@ -1261,7 +1271,6 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         };
         if (live && half == 0) m_inv[vi.row0 + row] = 1.f / sc;
         build_band(0);
-        uint32_t phase = 0;
         bool ok = true;
         // Epilogue layout: in TMEM a thread owns one row (32 of its columns), and stored that way a warp instruction
         // would touch 32 rows x 16 bytes.  Every 16-column slab goes through a warp-private 32 x 16 smem tile and comes
@@ -1325,6 +1334,7 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
             }
         }
     }
+    }   // tiles of this CTA
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, 256);

@@ -290,9 +290,9 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
                 if (!tc::make_map(&map32_hi, p_hi, (uint64_t)b->total_rows, kQkvCols, 64, 32, &msg) ||
                     !tc::make_map(&map32_lo, p_lo, (uint64_t)b->total_rows, kQkvCols, 64, 32, &msg))
                     return fail(EDSNET_E_CUDA, "nystrom_core: " + msg);
-                tc::value_conv_tc_kernel<<<b->n_tiles128, 320, tc::kCvSmemBytes, st>>>(
+                tc::value_conv_tc_kernel<<<std::min(b->n_tiles128, tc::num_sms()), 320, tc::kCvSmemBytes, st>>>(
                     map32_hi, map32_lo, qkv_inv, b->cu_rows, reinterpret_cast<const int2*>(b->tiles128), conv_w, merged,
-                    stats, m_hi, m_lo, m_inv, merged_lo ? 1 : 0);
+                    stats, m_hi, m_lo, m_inv, merged_lo ? 1 : 0, b->n_tiles128);
             }
         } else {
             tc::value_conv_kernel<<<dim3(b->n_tiles128, 4), 256, tc::kConvSmemBytes, st>>>(
