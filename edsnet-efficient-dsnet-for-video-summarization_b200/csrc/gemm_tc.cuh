@@ -111,6 +111,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync_gemm(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -381,7 +384,10 @@ struct SlabFromTmem2 {
 template <typename Slab>
 __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre& pre, int row0, int lane,
                                                    int nc0, int M, int N, float* C, const GemmEpiArgs& ep,
-                                                   float* scratch) {
+                                                   float* scratch, const float* col_scale, const float* col_bias) {
+    // col_scale / col_bias: ep.b_scale / ep.bias of all N columns, staged in shared memory once per (persistent) CTA: a
+    // thread needs the constants of all its 64 columns for every tile, 32 16-byte loads that used to go to global memory
+    // through an L1 this kernel's streams keep evicting (10 % of the epilogue's stall samples)
     const int rr = lane >> 1, c8 = (lane & 1) * 8;
     const float ra = pre.ra;
     float4 resv[2][4];
@@ -415,7 +421,7 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
             const int c = nc0 + q * 16 + j;
-            const float4 rb = ldg4(ep.b_scale + c), b = ldg4(ep.bias + c);
+            const float4 rb = lds4(col_scale + c), b = lds4(col_bias + c);
             st4(scratch + lane * kEpiScratchLd + j,
                 make_float4(v[j] * (ra * rb.x) + b.x, v[j + 1] * (ra * rb.y) + b.y,
                             v[j + 2] * (ra * rb.z) + b.z, v[j + 3] * (ra * rb.w) + b.w));
@@ -479,7 +485,9 @@ struct TcCfg {
     static constexpr int kStageBytes = kAPlanes * kATile + kBPlanes * kBTile;
     static constexpr int kEpiWarps = BN / 16;              // 8 (two per TMEM lane quarter) or 4
     static constexpr int kScratchOff = STAGES * kStageBytes + 256;    // after the barriers
-    static constexpr int kSmemBytes = kScratchOff + kEpiWarps * kEpiScratchWarp + 1024 /*alignment slack*/;
+    static constexpr int kColConstOff = kScratchOff + kEpiWarps * kEpiScratchWarp;   // EPI_RES_LNPLANES: b_scale | bias, N = 1024
+    static constexpr int kColConstBytes = 2 * 1024 * 4;
+    static constexpr int kSmemBytes = kColConstOff + kColConstBytes + 1024 /*alignment slack*/;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
 };
 
@@ -610,6 +618,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int quarter = warp & 3;
         const int chalf = (warp - 2) >> 2;                       // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127 (BN 128)
         const int n_pairs = ACCS == 4 ? (nk < 2 ? nk : 2) : 1;      // (main | cross) accumulator pairs in use
+        float* col_const = reinterpret_cast<float*>(gen_base + Cfg::kColConstOff);
+        if (EPI == EPI_RES_LNPLANES) {
+            // (N == 1024 for this epilogue, checked by the host)
+            const int et = threadIdx.x - 64;
+            for (int i = et; i < 256; i += 32 * Cfg::kEpiWarps) {
+                st4(col_const + 4 * i, ldg4(ep.b_scale + 4 * i));
+                st4(col_const + 1024 + 4 * i, ldg4(ep.bias + 4 * i));
+            }
+            named_bar_sync_gemm(1, 32 * Cfg::kEpiWarps);
+        }
         bool ok = true;
         int t = 0;
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
@@ -634,7 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 SlabFromTmem2 slab;
                 slab.t0 = t0;
                 slab.bn = (uint32_t)BN;
-                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch, col_const, col_const + 1024);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -713,7 +731,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else if (EPI == EPI_RES_LNPLANES) {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 SlabFromRegs slab{v};
-                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+                epi_store_lnplanes(slab, ln_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch, col_const, col_const + 1024);
             } else {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 epi_store_f32<EPI>(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
