@@ -193,8 +193,11 @@ __device__ __forceinline__ void issue_pair_mma64(uint32_t acc, uint32_t a_hi, ui
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 landmarks_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const float* __restrict__ inv,
-                        const int* __restrict__ cu_rows, float* __restrict__ q_land, float* __restrict__ k_land) {
+                        const int* __restrict__ cu_rows, float* __restrict__ q_land, float* __restrict__ k_land,
+                        unsigned* __restrict__ ticket) {
     const int v = blockIdx.y, j = blockIdx.x;
+    // the work-item counter of the (persistent) a3v kernel that follows on the same stream starts at zero
+    if (ticket != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;
     const VidInfo vi = vid_info(cu_rows, v);
     const int c4 = threadIdx.x * 4;
     const int slot = c4 >> 6;                                   // part * 8 + head, part in {q, k}
@@ -255,7 +258,13 @@ __global__ void __launch_bounds__(kA3Threads, 1)
 a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ inv, const int* __restrict__ cu_rows, const float* __restrict__ q_land,
               float* __restrict__ a3v, float* __restrict__ part_out, const float* __restrict__ k_land,
-              float* __restrict__ attn2, float* __restrict__ stats) {
+              float* __restrict__ attn2, float* __restrict__ stats, unsigned* __restrict__ ticket, int n_videos,
+              int zsplit) {
+    // ticket != nullptr: PERSISTENT -- one CTA per SM draws work items (head pair, video, key range) from a device-side
+    // counter (zeroed by the landmarks kernel in front of this launch) until they run out.  A CTA of this size costs
+    // 3-4.7 us to launch on an SM that has just been vacated (globaltimer stamps) and one item is only ~27 us of work;
+    // every item starts from freshly initialised barriers, so nothing else about an item changes.  ticket == nullptr:
+    // one item per CTA, item = blockIdx.x.
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* g = smem_raw + (base - smem_u32(smem_raw));
@@ -270,10 +279,19 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const uint32_t bars = base + oVec + kA3VecBytes;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kA3VecBytes + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pair = blockIdx.x, v = blockIdx.y;
+    const int n_items = 4 * n_videos * zsplit;
+    __shared__ int s_item;
+    if (warp == 16) tmem_alloc(bars + 96, 512);
+    bool first_item = true;
+    uint32_t tmem_base = 0;
+    for (;;) {
+    if (tid == 0) s_item = ticket != nullptr ? (int)atomicAdd(ticket, 1u) : (first_item ? (int)blockIdx.x : n_items);
+    __syncthreads();                                                        // (also: everyone has left the previous item)
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int pair = item & 3, v = (item >> 2) % n_videos, zi = (item >> 2) / n_videos;
     const VidInfo vi = vid_info(cu_rows, v);
     const int tiles_all = (vi.T + 63) / 64;
-    const int zsplit = (int)gridDim.z, zi = (int)blockIdx.z;
     const int per = (tiles_all + zsplit - 1) / zsplit;
     const int tile0 = zi * per;                                             // first key tile of this CTA's range
     const int n_tiles = max(0, min(per, tiles_all - tile0));
@@ -281,6 +299,11 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const bool do_attn2 = attn2 != nullptr && zi == 0;
 
     if (tid == 0) {
+        if (!first_item) {
+            for (int q = 0; q < 12; ++q) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * q) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 104) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 112) : "memory");
+        }
         mbar_init(bars + 104, 1);                                           // attn2 products done
         mbar_init(bars + 112, kA3RowThreads);                               // attn2 logits read out
         mbar_init(bars, 1); mbar_init(bars + 8, 1);                         // K full
@@ -293,7 +316,6 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         mbar_init(bars + 88, kA3RowThreads);                                // every row thread has stored P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) tmem_alloc(bars + 96, 512);
     float inv_ql = 1.f;
     // Prologue (a clock64 probe put it at 8 000 cycles with one thread per 64-value row, a third of an average CTA's
     // life, and nothing overlaps it at one CTA per SM): two threads per row, lanes 2r and 2r + 1 of the same warp, the row
@@ -350,7 +372,7 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    tmem_base = *tmem_slot_ptr;
 
     if (warp == 16) {
         if (lane == 0) {
@@ -583,8 +605,15 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         }
     }
     tc_fence_before();
+    first_item = false;
+    }   // work items
+    tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc(tmem_base, 512);
+    if (warp == 16 && !first_item) tmem_dealloc(tmem_base, 512);
+    if (warp == 16 && first_item) {                                        // no item at all: the allocation is still ours
+        tc_fence_after();
+        tmem_dealloc(*tmem_slot_ptr, 512);
+    }
 }
 
 // Combine the key ranges of a3v_tc_kernel: a3v[j][d] = sum_z o_z[j][d] e^(m_z - m) / sum_z l_z e^(m_z - m), m = max_z m_z

@@ -231,7 +231,9 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
     const int V = b->n_videos;
     {
         StageScope scope(ST_LANDMARKS, st);
-        if (tcp) tc::landmarks_planes_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(p_hi, p_lo, qkv_inv, b->cu_rows, q_land, k_land);
+        // zmat is not touched before the pinv kernel writes Z: its first word is the a3v kernel's work-item counter
+        if (tcp) tc::landmarks_planes_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(p_hi, p_lo, qkv_inv, b->cu_rows, q_land, k_land,
+                                                                              reinterpret_cast<unsigned*>(zmat));
         else landmarks_kernel<<<dim3(kLandmark, V), 256, 0, st>>>(qkv, b->cu_rows, q_land, k_land);
         CU_CHECK(cudaGetLastError(), "landmarks_kernel");
     }
@@ -249,8 +251,13 @@ int nystrom_core_impl(int precision, const edsnet_batch* b, const float* qkv, co
         if (tcp) {
             // a3_part (edsnet_forward / edsnet_train_forward pass it): room for a3v_split_cap(V) key ranges per (video, head)
             const int z = a3_part ? a3v_splits(V, b->max_rows) : 1;
-            tc::a3v_tc_kernel<<<dim3(kHeads / 2, V, z), tc::kA3Threads, tc::kA3SmemBytes, st>>>(
-                map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v, a3_part, k_land, attn2_fused ? attn2 : nullptr, stats);
+            // EDSNET_A3V_VARIANT=1: one CTA per work item instead of the persistent kernel (cross-check)
+            static const int a3v_variant = [] { const char* e = getenv("EDSNET_A3V_VARIANT"); return e ? atoi(e) : 0; }();
+            const int n_items = (kHeads / 2) * V * z;
+            unsigned* ticket = (zmat != nullptr && a3v_variant == 0) ? reinterpret_cast<unsigned*>(zmat) : nullptr;
+            tc::a3v_tc_kernel<<<ticket ? std::min(n_items, tc::num_sms()) : n_items, tc::kA3Threads, tc::kA3SmemBytes, st>>>(
+                map_hi, map_lo, qkv_inv, b->cu_rows, q_land, a3v, a3_part, k_land, attn2_fused ? attn2 : nullptr, stats,
+                ticket, V, z);
             if (z > 1) {
                 CU_CHECK(cudaGetLastError(), "a3v_tc_kernel");
                 tc::a3v_merge_kernel<<<dim3(kHeads, V), 256, 0, st>>>(a3_part, z, a3v);
