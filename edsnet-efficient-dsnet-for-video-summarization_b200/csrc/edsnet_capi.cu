@@ -1064,7 +1064,7 @@ size_t edsnet_train_workspace_bytes(const edsnet_config* cfg, int32_t total_rows
 
 int edsnet_train_launches(const edsnet_config* cfg, int32_t* forward, int32_t* backward) {
     if (!cfg) return fail(EDSNET_E_ARG, "config is NULL");
-    if (forward) *forward = 4 + 1 + 1 + 6 + 1 + 1 + 1 + 1 + 1 + 1 + 1;       // weight planes, split, qkv, core, ..., roi
+    if (forward) *forward = 4 + 1 + 1 + 5 + 1 + 1 + 1 + 1 + 1 + 1 + 1;       // weight planes, split, qkv, core (attn2 inside a3v), ..., roi
     if (backward) *backward = 37;
     return EDSNET_OK;
 }
