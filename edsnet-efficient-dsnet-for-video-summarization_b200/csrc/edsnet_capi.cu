@@ -789,6 +789,10 @@ int edsnet_cnn_im2col(const edsnet_cnn_input* in, int32_t n_img, int32_t H, int3
             cnn_im2col_planes_kernel<4, 8><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
         else
             cnn_im2col_planes_kernel<4, 0><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
+    } else if (kh * kw * C <= 256) {
+        // few channels (the network input): eight pixels per warp, the row in registers
+        const unsigned blocks8 = (unsigned)((M + 63) / 64);
+        cnn_im2col_smallc_kernel<8, 8><<<blocks8, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
     } else {
         cnn_im2col_planes_kernel<1, 0><<<blocks, 256, 0, st>>>(ci, C, n_img, H, W, kh, kw, stride, pad, OH, OW, kpad, hi, lo, inv);
     }
