@@ -465,10 +465,123 @@ __device__ __forceinline__ void epi_store_lnplanes(Slab& slab, const LnPlanesPre
     }
 }
 
+// EPI_RES_LNPLANES, wide read-out (two-pass mode).  ncu of the slab version above: the L1 data pipe is 83 % busy (9 200
+// wavefronts per tile against 10 750 cycles) -- 3 070 of them the TMA fill of the operand ring, the rest this epilogue:
+// its 16-column slabs make every global instruction touch 16 lines (512 B in 16 wavefronts) and its transposition tile
+// is read with a two-way bank conflict.  Here a warp owns 32 rows x 64 columns of shared memory instead: phase A, thread
+// <-> accumulator row, leaves o = acc a_scale b_scale + bias there (16-byte slots XOR-swizzled by row & 7: conflict-free
+// both ways) and hands the TMEM buffer back BEFORE any global access; phase B, eight lanes per row, reads 8 columns per
+// lane, fetches the residual as ONE 32-byte load per lane (4 rows x 256 contiguous bytes per instruction), and stores
+// 4 rows x 128 contiguous bytes per plane and instruction.  Row sums: 8 values per lane, then a fixed xor tree.
+constexpr int kWideScratchWarp = 32 * 256 + 256;      // o tile + (shift, plane scale) per row
+struct LnWidePre {
+    float x[4][8];          // residual of read-out iterations 0..3; 4..7 are fetched as these are used up
+    float2 xs;              // (mean, max|.|) of the residual row of this thread's accumulator row
+    float ra;               // A row scale of that row
+};
+__device__ __forceinline__ void ldg8(float (&v)[8], const float* p) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void lnwide_load_res(float (&dst)[8], int i, int row0, int lane, int nc0, int M,
+                                                const GemmEpiArgs& ep) {
+    const int grow = row0 + 4 * i + (lane >> 3);
+    if (grow < M) {
+        ldg8(dst, ep.res + (size_t)grow * ep.ldr + nc0 + (lane & 7) * 8);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = 0.f;
+    }
+}
+__device__ __forceinline__ void lnwide_prefetch(LnWidePre& pre, int row0, int lane, int nc0, int M, const GemmEpiArgs& ep) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lnwide_load_res(pre.x[i], i, row0, lane, nc0, M, ep);
+    const int row = row0 + lane;
+    pre.ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
+    pre.xs = row < M ? __ldg(reinterpret_cast<const float2*>(ep.aux2) + row) : make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ int wide_slot(int s, int r) { return (s & 8) | ((s ^ r) & 7); }
+// returns after phase A with the accumulators consumed (the caller releases the TMEM buffer), continues with `finish`
+template <typename Slab>
+__device__ __forceinline__ void epi_lnwide_stage(Slab& slab, const LnWidePre& pre, int row0, int lane, int nc0, int M, int N,
+                                                 float* C, const GemmEpiArgs& ep, float* scratch, const float* col_scale,
+                                                 const float* col_bias) {
+    slab.prefetch(0);
+    const float ra = pre.ra;
+    const float bound = 2.f * pre.xs.y + __ldg(ep.aux3 + 1) + 32768.f * ra * __ldg(ep.aux3);
+    int e = 0;
+    if (bound > 0.f && bound < INFINITY) e = 14 - ilogbf(bound);
+    e = max(-100, min(100, e));
+    float2* rowc = reinterpret_cast<float2*>(scratch + 32 * 64);
+    rowc[lane] = make_float2(pre.xs.x, ldexpf(1.f, e));
+    if (nc0 == 0 && row0 + lane < M) {
+        float* z_inv = reinterpret_cast<float*>(reinterpret_cast<__half*>(C) + 2 * (size_t)M * N);
+        z_inv[row0 + lane] = ldexpf(1.f, -e);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[16];
+        slab.get(q, v);
+        if (q < 3) slab.prefetch(q + 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int s = q * 4 + j, c = nc0 + s * 4;
+            const float4 rb = lds4(col_scale + c), b = lds4(col_bias + c);
+            st4(scratch + lane * 64 + wide_slot(s, lane) * 4,
+                make_float4(v[4 * j] * (ra * rb.x) + b.x, v[4 * j + 1] * (ra * rb.y) + b.y,
+                            v[4 * j + 2] * (ra * rb.z) + b.z, v[4 * j + 3] * (ra * rb.w) + b.w));
+        }
+    }
+}
+__device__ __forceinline__ void epi_lnwide_finish(LnWidePre& pre, int row0, int lane, int nc0, int M, int N, float* C,
+                                                  const GemmEpiArgs& ep, const float* scratch) {
+    const int c = lane & 7, rsub = lane >> 3;
+    const bool even_first = c < 4;
+    const int sA = 2 * c + (even_first ? 0 : 1), sB = 2 * c + (even_first ? 1 : 0);
+    __half* hi_base = reinterpret_cast<__half*>(C);
+    __half* lo_base = hi_base + (size_t)M * N;
+    const float2* rowc = reinterpret_cast<const float2*>(scratch + 32 * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rsub, grow = row0 + r;
+        const float4 oA = lds4(scratch + r * 64 + wide_slot(sA, r) * 4), oB = lds4(scratch + r * 64 + wide_slot(sB, r) * 4);
+        const float4 o0 = even_first ? oA : oB, o1 = even_first ? oB : oA;
+        const float2 rc = rowc[r];
+        const float(&x)[8] = pre.x[i & 3];
+        const float z[8] = {o0.x + (x[0] - rc.x), o0.y + (x[1] - rc.x), o0.z + (x[2] - rc.x), o0.w + (x[3] - rc.x),
+                            o1.x + (x[4] - rc.x), o1.y + (x[5] - rc.x), o1.z + (x[6] - rc.x), o1.w + (x[7] - rc.x)};
+        float s1 = 0.f, s2 = 0.f;
+        __half2 hh[4], ll[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            s1 += z[2 * t] + z[2 * t + 1];
+            s2 += z[2 * t] * z[2 * t] + z[2 * t + 1] * z[2 * t + 1];
+            const float v0 = z[2 * t] * rc.y, v1 = z[2 * t + 1] * rc.y;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            hh[t] = __halves2half2(h0, h1);
+            ll[t] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+        }
+        if (grow < M) {
+            const size_t o = (size_t)grow * N + nc0 + c * 8;
+            *reinterpret_cast<uint4*>(hi_base + o) = *reinterpret_cast<uint4*>(hh);
+            *reinterpret_cast<uint4*>(lo_base + o) = *reinterpret_cast<uint4*>(ll);
+        }
+        if (i < 4) lnwide_load_res(pre.x[i], i + 4, row0, lane, nc0, M, ep);
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        }
+        if (c == 0 && grow < M)
+            *reinterpret_cast<float2*>(ep.aux + ((size_t)grow * 16 + (nc0 >> 6)) * 2) = make_float2(s1, s2);
+    }
+}
+
 // ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (two main | cross pairs, K blocks alternate) or 2 (one pair);
 // PASSES == 1: 1.  Whatever fits twice into the 512 TMEM columns is double-buffered (MMAs of tile t+1 overlap the
 // drain of tile t).
-template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES >= 2 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int ACCS = (PASSES >= 2 ? 4 : 1), int WIDE = 0>
 struct TcCfg {
     static constexpr int BM = 128;
     static constexpr int kATile = BM * BK * 2;             // bytes of one fp16 plane tile
@@ -485,7 +598,8 @@ struct TcCfg {
     static constexpr int kStageBytes = kAPlanes * kATile + kBPlanes * kBTile;
     static constexpr int kEpiWarps = BN / 16;              // 8 (two per TMEM lane quarter) or 4
     static constexpr int kScratchOff = STAGES * kStageBytes + 256;    // after the barriers
-    static constexpr int kColConstOff = kScratchOff + kEpiWarps * kEpiScratchWarp;   // EPI_RES_LNPLANES: b_scale | bias, N = 1024
+    static constexpr int kScratchWarp = WIDE ? kWideScratchWarp : kEpiScratchWarp;   // WIDE: epi_lnwide_* (EPI_RES_LNPLANES)
+    static constexpr int kColConstOff = kScratchOff + kEpiWarps * kScratchWarp;   // EPI_RES_LNPLANES: b_scale | bias, N = 1024
     static constexpr int kColConstBytes = 2 * 1024 * 4;
     static constexpr int kSmemBytes = kColConstOff + kColConstBytes + 1024 /*alignment slack*/;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
@@ -496,11 +610,13 @@ struct TcCfg {
 // boundaries, so the smem ring is full again by the time the epilogue has drained TMEM.  The epilogue pulls the
 // whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
 // residual and stores -- the next tile's MMAs overlap those global accesses.
-template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1), int WIDE = 0>
 __global__ void __launch_bounds__(64 + 2 * BN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
-    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS>;
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS, WIDE>;
+    static_assert(!WIDE || (EPI == EPI_RES_LNPLANES && ACCS == 2 && Cfg::kBufs == 2 && BN == 128),
+                  "the wide read-out belongs to the double-buffered to_out tile");
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
@@ -636,8 +752,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
             const int nc0 = n0 + chalf * 64;                         // first global column of this thread
             LnPlanesPre ln_pre;
+            LnWidePre wide_pre;
             if (EPI == EPI_RES_LNPLANES) {
-                lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, ep);
+                if constexpr (WIDE != 0) lnwide_prefetch(wide_pre, m0 + quarter * 32, lane, nc0, M, ep);
+                else lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, ep);
                 const int nxt = tile + gridDim.x;
                 if (nxt < n_tiles)
                     lnplanes_prefetch_l2((nxt / tiles_n) * Cfg::BM + quarter * 32, lane, (nxt % tiles_n) * BN + chalf * 64,
@@ -647,6 +765,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) +
                                 (uint32_t)(chalf * 64);
+            if constexpr (WIDE != 0) {
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * Cfg::kScratchWarp);
+                SlabFromTmem2 slab;
+                slab.t0 = t0;
+                slab.bn = (uint32_t)BN;
+                epi_lnwide_stage(slab, wide_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch, col_const, col_const + 1024);
+                tc_fence_before();
+                __syncwarp();                                        // the o tile is complete, TMEM is drained
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                epi_lnwide_finish(wide_pre, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+                __syncwarp();                                        // before the next tile overwrites the o tile
+                continue;
+            }
             if (EPI == EPI_RES_LNPLANES && ACCS == 2 && Cfg::kBufs == 2) {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
                 SlabFromTmem2 slab;
@@ -840,14 +971,15 @@ inline int num_sms() {
     return n;
 }
 
-template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1)>
+template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1), int WIDE = 0>
 cudaError_t launch_variant(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                            cudaStream_t st, std::string* msg) {
-    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS>;
+    using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS, WIDE>;
+    static_assert(Cfg::kSmemBytes <= 232448, "227 KB of shared memory per CTA");
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, A16, 2ull * M, K, BK, Cfg::BM, msg)) return cudaErrorUnknown;
     if (!make_map(&mapB, B16, 2ull * N, K, BK, BN, msg)) return cudaErrorUnknown;
-    auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI, ACCS>;
+    auto kern = gemm_tc_kernel<BN, BK, STAGES, PASSES, EPI, ACCS, WIDE>;
     static const char tag = 0;                      // one per template instantiation
     if (DeviceOnce once_{&tag}) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -883,6 +1015,9 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
             // double-buffered in TMEM (the next tile's MMAs run under the drain of this one): the second pair of the
             // three-pass scheme only exists to keep the truncating accumulation under 32 steps per accumulator
             // (1e-6-grade error), which is irrelevant at this mode's 5e-4 bar; variant 6 = the two-pair scheme.
+            // to_out: three stages make room for the wide read-out's 64 KB of o tiles (variant 7 = the slab epilogue)
+            if constexpr (EPI == EPI_RES_LNPLANES)
+                if (variant != 7) return launch_variant<128, 64, 3, 2, EPI, 2, 1>(A16, B16, C, M, N, K, ep, st, msg);
             if (K <= 512 || variant != 6) return launch_variant<128, 64, 4, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 4, 2, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         } else if (PASSES == 3) {
