@@ -578,6 +578,29 @@ __device__ __forceinline__ void epi_lnwide_finish(LnWidePre& pre, int row0, int 
     }
 }
 
+// WIDE == 2: the same read-out with SIXTEEN epilogue warps (the eight-warp version above runs at 0.44 instructions per
+// cycle and scheduler: two warps per scheduler cannot hide the latencies of their dependent chains).  A TMEM lane
+// quarter is served by four warps of 32 columns each; two of them share one 32 x 64 region: phase A, each dumps the raw
+// sums of its 32 columns (no constants: a thread per row would need all of them, 1 000 of the 2 700 shared-memory
+// wavefronts per tile); a 64-thread named barrier; phase B, each reads 16 of the 32 rows, eight lanes per row, applies
+// a_scale b_scale / bias / residual for ITS 8 columns (constants in registers), stores 4 rows x 128 bytes per plane and
+// instruction.  Row sums: one value per (lane, iteration), combined by recursive halving (4 instead of 12 shuffles).
+constexpr int kWide2Region = 32 * 256 + 32 * 16;      // raw tile + (shift, plane scale, a_scale, -) per row
+__device__ __forceinline__ int wide2_slot(int s, int r) { return (s & 8) | (((s & 7) ^ (r & 7) ^ (s >> 3)) & 7); }
+struct LnWide2Pre {
+    float x[2][8];          // residual of read-out iterations 0 and 1 (2 and 3 follow after phase A)
+    float cs[8], cb[8];     // b_scale / bias of this lane's 8 columns
+    float2 xs;              // row thread (first warp of a pair): (mean, max|.|) of the residual row
+    float ra;               // ... and its A row scale
+};
+__device__ __forceinline__ void lnwide2_load_res(float (&dst)[8], int grow, int gcol, int M, const GemmEpiArgs& ep) {
+    if (grow < M) {
+        ldg8(dst, ep.res + (size_t)grow * ep.ldr + gcol);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = 0.f;
+    }
+}
 // ACCS: TMEM accumulators per tile.  PASSES == 3: 4 (two main | cross pairs, K blocks alternate) or 2 (one pair);
 // PASSES == 1: 1.  Whatever fits twice into the 512 TMEM columns is double-buffered (MMAs of tile t+1 overlap the
 // drain of tile t).
@@ -596,10 +619,10 @@ struct TcCfg {
     static_assert(PASSES >= 2 ? (ACCS == 4 || ACCS == 2) : ACCS == 1, "accumulator scheme");
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     static constexpr int kStageBytes = kAPlanes * kATile + kBPlanes * kBTile;
-    static constexpr int kEpiWarps = BN / 16;              // 8 (two per TMEM lane quarter) or 4
+    static constexpr int kEpiWarps = WIDE == 2 ? 16 : BN / 16;   // 8 (two per TMEM lane quarter) or 4; 16: wide read-out in warp pairs
     static constexpr int kScratchOff = STAGES * kStageBytes + 256;    // after the barriers
     static constexpr int kScratchWarp = WIDE ? kWideScratchWarp : kEpiScratchWarp;   // WIDE: epi_lnwide_* (EPI_RES_LNPLANES)
-    static constexpr int kColConstOff = kScratchOff + kEpiWarps * kScratchWarp;   // EPI_RES_LNPLANES: b_scale | bias, N = 1024
+    static constexpr int kColConstOff = kScratchOff + (WIDE == 2 ? 8 * kWide2Region : kEpiWarps * kScratchWarp);   // EPI_RES_LNPLANES: b_scale | bias, N = 1024
     static constexpr int kColConstBytes = 2 * 1024 * 4;
     static constexpr int kSmemBytes = kColConstOff + kColConstBytes + 1024 /*alignment slack*/;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
@@ -611,7 +634,7 @@ struct TcCfg {
 // whole 128 x 128 tile (all accumulators summed) into registers, releases TMEM, and only then applies scale / bias /
 // residual and stores -- the next tile's MMAs overlap those global accesses.
 template <int BN, int BK, int STAGES, int PASSES, int EPI, int ACCS = (PASSES >= 2 ? 4 : 1), int WIDE = 0>
-__global__ void __launch_bounds__(64 + 2 * BN, 1)
+__global__ void __launch_bounds__(WIDE == 2 ? 576 : 64 + 2 * BN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
     using Cfg = TcCfg<BN, BK, STAGES, PASSES, ACCS, WIDE>;
@@ -751,10 +774,129 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int buf = t % Cfg::kBufs;
             const uint32_t tph = (uint32_t)(t / Cfg::kBufs) & 1u;
             const int nc0 = n0 + chalf * 64;                         // first global column of this thread
+            if constexpr (WIDE == 2) {
+                const int cg = (warp - 2) >> 2;                          // 32-column group of this warp
+                const int region = quarter + 4 * (cg >> 1);
+                float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + region * kWide2Region);
+                float4* rowc = reinterpret_cast<float4*>(scratch + 32 * 64);
+                const int row0 = m0 + quarter * 32;
+                const int c = lane & 7, rsub = lane >> 3;
+                const int rbase = (cg & 1) * 16;                         // rows of the region this warp reads out
+                const int gcol = n0 + (cg >> 1) * 64 + c * 8;            // first of this lane's 8 read-out columns
+                LnWide2Pre pre;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) lnwide2_load_res(pre.x[i], row0 + rbase + 4 * i + rsub, gcol, M, ep);
+                {
+                    const float4 s0 = lds4(col_const + gcol), s1 = lds4(col_const + gcol + 4);
+                    const float4 b0 = lds4(col_const + 1024 + gcol), b1 = lds4(col_const + 1024 + gcol + 4);
+                    pre.cs[0] = s0.x; pre.cs[1] = s0.y; pre.cs[2] = s0.z; pre.cs[3] = s0.w;
+                    pre.cs[4] = s1.x; pre.cs[5] = s1.y; pre.cs[6] = s1.z; pre.cs[7] = s1.w;
+                    pre.cb[0] = b0.x; pre.cb[1] = b0.y; pre.cb[2] = b0.z; pre.cb[3] = b0.w;
+                    pre.cb[4] = b1.x; pre.cb[5] = b1.y; pre.cb[6] = b1.z; pre.cb[7] = b1.w;
+                }
+                if ((cg & 1) == 0) {
+                    const int row = row0 + lane;
+                    pre.ra = row < M ? __ldg(ep.a_scale + row) : 0.f;
+                    pre.xs = row < M ? __ldg(reinterpret_cast<const float2*>(ep.aux2) + row) : make_float2(0.f, 0.f);
+                }
+                {   // the next tile's residual lines into L2 a tile ahead: this warp's 32 rows x 32 columns
+                    const int nxt = tile + gridDim.x;
+                    const int prow = (nxt / tiles_n) * Cfg::BM + quarter * 32 + lane;
+                    if (nxt < n_tiles && prow < M)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.res + (size_t)prow * ep.ldr + (nxt % tiles_n) * BN + cg * 32));
+                }
+                ok = mbar_wait(tfull_bar(buf), tph);
+                tc_fence_after();
+                SlabFromTmem2 slab;
+                slab.t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * 32);
+                slab.bn = (uint32_t)BN;
+                slab.prefetch(0);
+                if ((cg & 1) == 0) {
+                    const float bound = 2.f * pre.xs.y + __ldg(ep.aux3 + 1) + 32768.f * pre.ra * __ldg(ep.aux3);
+                    int e = 0;
+                    if (bound > 0.f && bound < INFINITY) e = 14 - ilogbf(bound);
+                    e = max(-100, min(100, e));
+                    rowc[lane] = make_float4(pre.xs.x, ldexpf(1.f, e), pre.ra, 0.f);
+                    if (n0 == 0 && cg == 0 && row0 + lane < M) {
+                        float* z_inv = reinterpret_cast<float*>(reinterpret_cast<__half*>(C) + 2 * (size_t)M * N);
+                        z_inv[row0 + lane] = ldexpf(1.f, -e);
+                    }
+                }
+                // ---- phase A: raw accumulator sums of this warp's 32 columns, thread <-> row ----
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float v[16];
+                    slab.get(q, v);
+                    if (q < 1) slab.prefetch(q + 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        st4(scratch + lane * 64 + wide2_slot((cg & 1) * 8 + q * 4 + j, lane) * 4,
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                }
+                tc_fence_before();
+                named_bar_sync_gemm(2 + region, 64);                     // both halves of the region are written
+                if (lane == 0) mbar_arrive(tempty_bar(buf));             // TMEM drained before any global access
+                // ---- phase B: 16 rows x 64 columns, eight lanes per row ----
+                __half* hi_base = reinterpret_cast<__half*>(C);
+                __half* lo_base = hi_base + (size_t)M * N;
+                float s1[4], s2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rbase + 4 * i + rsub, grow = row0 + r;
+                    const float4 o0 = lds4(scratch + r * 64 + wide2_slot(2 * c, r) * 4);
+                    const float4 o1 = lds4(scratch + r * 64 + wide2_slot(2 * c + 1, r) * 4);
+                    const float4 rc = rowc[r];
+                    const float(&x)[8] = pre.x[i & 1];
+                    const float a[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                    float z[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = (a[j] * (rc.z * pre.cs[j]) + pre.cb[j]) + (x[j] - rc.x);
+                    float t1 = 0.f, t2 = 0.f;
+                    __half2 hh[4], ll[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        t1 += z[2 * t] + z[2 * t + 1];
+                        t2 += z[2 * t] * z[2 * t] + z[2 * t + 1] * z[2 * t + 1];
+                        const float v0 = z[2 * t] * rc.y, v1 = z[2 * t + 1] * rc.y;
+                        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                        hh[t] = __halves2half2(h0, h1);
+                        ll[t] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+                    }
+                    s1[i] = t1;
+                    s2[i] = t2;
+                    if (grow < M) {
+                        const size_t o = (size_t)grow * N + gcol;
+                        *reinterpret_cast<uint4*>(hi_base + o) = *reinterpret_cast<uint4*>(hh);
+                        *reinterpret_cast<uint4*>(lo_base + o) = *reinterpret_cast<uint4*>(ll);
+                    }
+                    if (i < 2) lnwide2_load_res(pre.x[i], row0 + rbase + 4 * (i + 2) + rsub, gcol, M, ep);
+                }
+                named_bar_sync_gemm(2 + region, 64);                     // region free for the next tile's phase A
+                // row sums over the eight lanes of a row by recursive halving: lane c ends with iteration (c & 1) * 2 + ((c >> 1) & 1)
+                {
+                    const bool b0 = (c & 1) != 0, b1 = (c & 2) != 0;
+                    float k10 = b0 ? s1[2] : s1[0], k11 = b0 ? s1[3] : s1[1];
+                    float k20 = b0 ? s2[2] : s2[0], k21 = b0 ? s2[3] : s2[1];
+                    k10 += __shfl_xor_sync(0xffffffffu, b0 ? s1[0] : s1[2], 1);
+                    k11 += __shfl_xor_sync(0xffffffffu, b0 ? s1[1] : s1[3], 1);
+                    k20 += __shfl_xor_sync(0xffffffffu, b0 ? s2[0] : s2[2], 1);
+                    k21 += __shfl_xor_sync(0xffffffffu, b0 ? s2[1] : s2[3], 1);
+                    float u1 = b1 ? k11 : k10, u2 = b1 ? k21 : k20;
+                    u1 += __shfl_xor_sync(0xffffffffu, b1 ? k10 : k11, 2);
+                    u2 += __shfl_xor_sync(0xffffffffu, b1 ? k20 : k21, 2);
+                    u1 += __shfl_xor_sync(0xffffffffu, u1, 4);
+                    u2 += __shfl_xor_sync(0xffffffffu, u2, 4);
+                    const int it = (b0 ? 2 : 0) + (b1 ? 1 : 0);
+                    const int grow = row0 + rbase + 4 * it + rsub;
+                    if (c < 4 && grow < M)
+                        *reinterpret_cast<float2*>(ep.aux + ((size_t)grow * 16 + (n0 >> 6) + (cg >> 1)) * 2) = make_float2(u1, u2);
+                }
+                continue;
+            }
             LnPlanesPre ln_pre;
             LnWidePre wide_pre;
             if (EPI == EPI_RES_LNPLANES) {
-                if constexpr (WIDE != 0) lnwide_prefetch(wide_pre, m0 + quarter * 32, lane, nc0, M, ep);
+                if constexpr (WIDE == 1) lnwide_prefetch(wide_pre, m0 + quarter * 32, lane, nc0, M, ep);
                 else lnplanes_prefetch(ln_pre, m0 + quarter * 32, lane, nc0, M, ep);
                 const int nxt = tile + gridDim.x;
                 if (nxt < n_tiles)
@@ -765,7 +907,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             const uint32_t t0 = tmem_base + (uint32_t)(buf * Cfg::kAccs * BN) + ((uint32_t)(quarter * 32) << 16) +
                                 (uint32_t)(chalf * 64);
-            if constexpr (WIDE != 0) {
+            if constexpr (WIDE == 1) {
                 float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * Cfg::kScratchWarp);
                 SlabFromTmem2 slab;
                 slab.t0 = t0;
@@ -998,7 +1140,9 @@ cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, i
 
 // variant (profiling knob, edsnet_debug_set_tc_variant / EDSNET_TC_VARIANT): 0 = default (128 x 128 tiles, BK 64, four
 // accumulators; two double-buffered accumulators when K <= 512), 3 = two double-buffered accumulators for every K,
-// 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh).  A BK 32 / 64-byte-swizzle variant and a 128 x 64
+// 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh); two-pass mode: 6 = two accumulator pairs, 7 = to_out with
+// the 16-column slab epilogue and a four-deep ring, 8 = to_out with the eight-warp wide read-out, 9 = to_qkv with a three-deep
+// ring (costs 4 %).  A BK 32 / 64-byte-swizzle variant and a 128 x 64
 // tile variant were measured slower (profiles/r01e_gemm_variants.log) and removed.
 inline int& variant_ref() {
     static int v = [] { const char* e = getenv("EDSNET_TC_VARIANT"); return e ? atoi(e) : 0; }();   // profiling knob
@@ -1017,7 +1161,11 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
             // (1e-6-grade error), which is irrelevant at this mode's 5e-4 bar; variant 6 = the two-pair scheme.
             // to_out: three stages make room for the wide read-out's 64 KB of o tiles (variant 7 = the slab epilogue)
             if constexpr (EPI == EPI_RES_LNPLANES)
-                if (variant != 7) return launch_variant<128, 64, 3, 2, EPI, 2, 1>(A16, B16, C, M, N, K, ep, st, msg);
+                if (variant != 7)
+                    return variant == 8 ? launch_variant<128, 64, 3, 2, EPI, 2, 1>(A16, B16, C, M, N, K, ep, st, msg)
+                                        : launch_variant<128, 64, 3, 2, EPI, 2, 2>(A16, B16, C, M, N, K, ep, st, msg);
+            if constexpr (EPI == EPI_QKV_PLANES)      // probe: the same kernel with a three-deep ring
+                if (variant == 9) return launch_variant<128, 64, 3, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             if (K <= 512 || variant != 6) return launch_variant<128, 64, 4, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             return launch_variant<128, 64, 4, 2, EPI>(A16, B16, C, M, N, K, ep, st, msg);
         } else if (PASSES == 3) {
