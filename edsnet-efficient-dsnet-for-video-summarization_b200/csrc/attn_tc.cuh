@@ -1138,7 +1138,7 @@ constexpr int kCvBandBytes = 3 * 32768;                                    // [k
 constexpr int kCvVPlane = kConvRowsIn * 128;                                // 160 window rows x 128 B = 20 KB
 constexpr int kCvVStage = 2 * kCvVPlane;                                   // hi | lo
 constexpr int kCvStages = 2;
-constexpr int kCvScratch = 8 * 32 * 20 * 4;                                // per row warp: 32 rows x 16 columns (+4 pad) fp32
+constexpr int kCvScratch = 4 * 32 * 256;                                   // per TMEM lane quarter (a warp pair): 32 rows x 64 columns fp32
 constexpr int kCvVecFloats = kHeads * 192 + kHeads * kTaps + 3 * kHeads + 4;   // inv window, taps, e_c / f-scale, scale
 constexpr int kCvSmemBytes = kCvBandBytes + kCvStages * kCvVStage + kCvScratch + kCvVecFloats * 4 + 128 + 1024;
 
@@ -1302,30 +1302,32 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         build_band(0);
         bool ok = true;
         // Epilogue layout: in TMEM a thread owns one row (32 of its columns), and stored that way a warp instruction
-        // would touch 32 rows x 16 bytes.  Every 16-column slab goes through a warp-private 32 x 16 smem tile and comes
-        // back as (row rr + 8 i, columns 4 cc .. 4 cc + 3): 8 rows x 64 B (attention part in) / 8 rows x 32 B (a plane
-        // out) per instruction.
-        float* scr = reinterpret_cast<float*>(g + oScr) + warp * (32 * 20);
-        const int wrow0 = r0 + (warp & 3) * 32;                             // first tile row of this warp's TMEM lanes
-        const int rr = lane >> 2, cc = lane & 3;
-        auto attn_off = [&](int hd, int q, int i) -> size_t {
-            const int rw = min(wrow0 + rr + 8 * i, vi.T - 1);
-            return (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + half * 32 + q * 16 + cc * 4;
+        // would touch 32 rows x 16 bytes.  The two warps of a TMEM lane quarter (column halves 0 and 1) therefore share a
+        // 32 x 64 fp32 region (16-byte slots swizzled as in the to_out epilogue, gemm_tc.cuh wide2_slot): each dumps its
+        // 32 columns, a 64-thread named barrier, then each reads 16 of the 32 rows with eight lanes per row: the
+        // attention part arrives as ONE 32-byte load per lane (4 rows x 256 contiguous bytes per instruction) and a
+        // plane leaves as 4 rows x 128 contiguous bytes per instruction (was 8 rows x 64 B in, 8 rows x 32 B out: the
+        // L1 data pipe was 53 % busy, ncu r02v).
+        float* reg = reinterpret_cast<float*>(g + oScr) + (warp & 3) * (32 * 64);
+        const int bar_id = 2 + (warp & 3);
+        const int wrow0 = r0 + (warp & 3) * 32 + half * 16;                 // first tile row this warp reads out
+        const int rsub = lane >> 3, c8 = lane & 7;
+        auto attn_ptr = [&](int hd, int i) -> const float* {
+            const int rw = min(wrow0 + 4 * i + rsub, vi.T - 1);
+            return attn + (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + c8 * 8;
         };
-        float4 an[8];                                                       // attention part, one head ahead
+        float an[4][8];                                                     // attention part, one head ahead
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) an[q * 4 + i] = ldg4(attn + attn_off(0, q, i));
+        for (int i = 0; i < 4; ++i) ldg8(an[i], attn_ptr(0, i));
         for (int hd = 0; hd < kHeads && ok; ++hd) {
-            float4 a[8];
+            float a[4][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = an[j];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = an[i][j];
             if (hd + 1 < kHeads) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) an[q * 4 + i] = ldg4(attn + attn_off(hd + 1, q, i));
+                for (int i = 0; i < 4; ++i) ldg8(an[i], attn_ptr(hd + 1, i));
             }
             ok = mbar_wait(bars + 56, phase) && ok;
             phase ^= 1u;
@@ -1337,30 +1339,31 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
             tc_fence_before();
             const float ic = s_ic[hd];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int j = 0; j < 8; ++j)
+                st4(reg + lane * 64 + wide2_slot(half * 8 + j, lane) * 4,
+                    make_float4(cv[4 * j], cv[4 * j + 1], cv[4 * j + 2], cv[4 * j + 3]));
+            named_bar_sync(bar_id, 64);                                     // both column halves of the region are in place
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    st4(scr + lane * 20 + j, make_float4(cv[q * 16 + j], cv[q * 16 + j + 1], cv[q * 16 + j + 2], cv[q * 16 + j + 3]));
-                __syncwarp();
+            for (int i = 0; i < 4; ++i) {
+                const int rl = half * 16 + 4 * i + rsub, rw = wrow0 + 4 * i + rsub;
+                const float4 c0 = lds4(reg + rl * 64 + wide2_slot(2 * c8, rl) * 4);
+                const float4 c1 = lds4(reg + rl * 64 + wide2_slot(2 * c8 + 1, rl) * 4);
+                const float cvv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                __half2 hh[4], ll[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rw = wrow0 + rr + 8 * i;
-                    const float4 c4 = lds4(scr + (rr + 8 * i) * 20 + cc * 4);
-                    const float4 at = a[q * 4 + i];
-                    const float v0 = fmaf(c4.x, ic, at.x) * sc, v1 = fmaf(c4.y, ic, at.y) * sc;
-                    const float v2 = fmaf(c4.z, ic, at.z) * sc, v3 = fmaf(c4.w, ic, at.w) * sc;
-                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1), h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
-                    __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
-                    __half2 ll[2] = {__halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
-                                     __halves2half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3)))};
-                    if (rw < vi.T) {
-                        const size_t oo = (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + half * 32 + q * 16 + cc * 4;
-                        *reinterpret_cast<uint2*>(m_hi + oo) = *reinterpret_cast<uint2*>(hh);
-                        if (write_lo) *reinterpret_cast<uint2*>(m_lo + oo) = *reinterpret_cast<uint2*>(ll);
-                    }
+                for (int t = 0; t < 4; ++t) {
+                    const float v0 = fmaf(cvv[2 * t], ic, a[i][2 * t]) * sc, v1 = fmaf(cvv[2 * t + 1], ic, a[i][2 * t + 1]) * sc;
+                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                    hh[t] = __halves2half2(h0, h1);
+                    ll[t] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
                 }
-                __syncwarp();
+                if (rw < vi.T) {
+                    const size_t oo = (size_t)(vi.row0 + rw) * kInner + hd * kDimHead + c8 * 8;
+                    *reinterpret_cast<uint4*>(m_hi + oo) = *reinterpret_cast<uint4*>(hh);
+                    if (write_lo) *reinterpret_cast<uint4*>(m_lo + oo) = *reinterpret_cast<uint4*>(ll);
+                }
             }
+            named_bar_sync(bar_id, 64);                                     // region free for the next head
         }
     }
     }   // tiles of this CTA
