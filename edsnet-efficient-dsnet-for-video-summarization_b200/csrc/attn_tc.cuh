@@ -653,7 +653,7 @@ a3v_merge_kernel(const float* __restrict__ part, int zsplit, float* __restrict__
 // TMEM 256 columns: S main | S cross | O main | O cross.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAoVecBytes = 64 * 4 + 4 * 128 * 4;                            // inv_kl [64] + pair exchange max / sum [2][128] each
-constexpr int kAoScratch = 8 * 32 * 12 * 4;                                 // per row warp: 32 rows x 8 columns (+4 pad) fp32
+constexpr int kAoScratch = 0;                                               // the read-out borrows the dead q stage (collect)
 constexpr int kAoSmemBytes = 2 * 8192 + 2 * 8192 + 2 * 32768 + kAoVecBytes + 128 + kAoScratch + 1024;
 
 // 320 threads: warps 0..7 = rows (thread t and t + 128 share accumulator row t & 127: landmarks / output columns
@@ -779,29 +779,41 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         float rs_prev = 0.f;
         // P.V product of tile j: read out, scale by the row's 1 / sum, store
         // Stored straight from the accumulator layout a warp instruction would touch 32 rows x 16 bytes (32 L1 tag
-        // look-ups); every 8-column slab goes through a warp-private 32 x 8 smem tile and leaves as 16 rows x 32 B.
-        float* scr = reinterpret_cast<float*>(g + oVec + kAoVecBytes + 128) + warp * (32 * 12);
-        const int wrow0 = (warp & 3) * 32, rr = lane >> 1, cc = lane & 1;
-        auto collect = [&](int j, float rs) {
+        // look-ups).  The two warps of a TMEM lane quarter share a 32 x 64 fp32 region instead (as the value convolution
+        // does): each dumps its 32 columns, a 64-thread named barrier, each reads 16 rows back with eight lanes per row
+        // and stores 4 rows x 256 contiguous bytes per instruction.  The region needs no memory of its own: when
+        // collect(i - 1) runs, S(i) has been read out, so the q tile of stage i & 1 is dead, and the bytes a pair
+        // borrows (rows 32 quarter .. + 31 of both planes, 2 x 4 KB) are exactly the rows the SAME two warps fill with
+        // P(i) right afterwards.
+        const int quarter = warp & 3, bar_id = 2 + quarter;
+        const int rsub = lane >> 3, c8 = lane & 7;
+        auto reg_ptr = [&](unsigned char* stage, int r, int slot) -> float* {      // 16-byte slot `slot` of region row r
+            return reinterpret_cast<float*>(stage + (slot >> 3) * 16384 + (quarter * 32 + r) * 128 +
+                                            (((slot & 7) ^ (r & 7) ^ (slot >> 3)) & 7) * 16);
+        };
+        auto collect = [&](int j, float rs, unsigned char* stage) {
             ok = mbar_wait(bars + 40, pv_phase) && ok;
             pv_phase ^= 1u;
             tc_fence_after();
             float ov[32];
             tmem_read32_sum(tO, tO + 64u, ov);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                st4(scr + lane * 12, make_float4(ov[q * 8] * rs, ov[q * 8 + 1] * rs, ov[q * 8 + 2] * rs, ov[q * 8 + 3] * rs));
-                st4(scr + lane * 12 + 4, make_float4(ov[q * 8 + 4] * rs, ov[q * 8 + 5] * rs, ov[q * 8 + 6] * rs, ov[q * 8 + 7] * rs));
-                __syncwarp();
+            for (int q = 0; q < 8; ++q)
+                st4(reg_ptr(stage, lane, half * 8 + q),
+                    make_float4(ov[4 * q] * rs, ov[4 * q + 1] * rs, ov[4 * q + 2] * rs, ov[4 * q + 3] * rs));
+            named_bar_sync(bar_id, 64);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int row = rbase + j * 128 + wrow0 + rr + 16 * i;
-                    const float4 o4 = lds4(scr + (rr + 16 * i) * 12 + cc * 4);
-                    if (row < vi.T)
-                        st4(attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + half * 32 + q * 8 + cc * 4, o4);
+            for (int i = 0; i < 4; ++i) {
+                const int rl = half * 16 + 4 * i + rsub;
+                const int row = rbase + j * 128 + quarter * 32 + rl;
+                const float4 o0 = lds4(reg_ptr(stage, rl, 2 * c8)), o1 = lds4(reg_ptr(stage, rl, 2 * c8 + 1));
+                if (row < vi.T) {
+                    float* dst = attn + (size_t)(vi.row0 + row) * kInner + h * kDimHead + c8 * 8;
+                    st4(dst, o0);
+                    st4(dst + 4, o1);
                 }
-                __syncwarp();
             }
+            named_bar_sync(bar_id, 64);                                     // the rows are free for P again
         };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
@@ -826,7 +838,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             for (int j = 0; j < 32; ++j) { p[j] = expf(p[j] - mx); sum += p[j]; }
             s_psum[half * 128 + trow] = sum;
             // the previous tile's output: its accumulator is about to be overwritten by P.V(i)
-            if (i > 0) collect(i - 1, rs_prev);
+            if (i > 0) collect(i - 1, rs_prev, stp);
             // un-normalised probabilities (<= 1, fixed scale 2^14); the row sum divides the output instead
             store_row32(stp, stp + 16384, trow, half * 4, p, 16384.f);
             fence_proxy_async();
@@ -836,7 +848,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             rs_prev = o_scale / (sum + s_psum[(half ^ 1) * 128 + trow]);
             inv_q = inv_q_next;
         }
-        if (n_tiles > 0 && ok) collect(n_tiles - 1, rs_prev);
+        if (n_tiles > 0 && ok) collect(n_tiles - 1, rs_prev, g + oQ + (n_tiles & 1) * 32768);
     }
     tc_fence_before();
     __syncthreads();
