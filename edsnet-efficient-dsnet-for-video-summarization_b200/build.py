@@ -14,8 +14,10 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 ROOT = os.path.dirname(PKG_DIR)
 LIB = os.path.join(CSRC, "libedsnet_b200.so")
 
+# cudart is linked dynamically (the static runtime would embed its whole symbol table, including entry points this
+# library never calls); torch has libcudart.so.12 loaded already, the rpath serves a caller that binds the C ABI alone
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def sources():
