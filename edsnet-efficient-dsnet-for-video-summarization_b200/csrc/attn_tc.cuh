@@ -1174,8 +1174,7 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     float* s_w = s_inv + kHeads * 192;                                      // [8][33]
     float* s_fc = s_w + kHeads * kTaps;                                     // [8] 2^e_c per head
     float* s_ic = s_fc + kHeads;                                            // [8] 2^-e_c
-    unsigned* s_vmax = reinterpret_cast<unsigned*>(s_ic + kHeads);         // [8] max inverse v scale over the window
-    float* s_scale = reinterpret_cast<float*>(s_vmax + kHeads);            // output plane scale
+    unsigned* s_vmax = reinterpret_cast<unsigned*>(s_ic + kHeads);         // [8] bound on |merged| per head (float bits)
     // barriers: V full[kCvStages] +0, V empty[kCvStages] +24, band ready +48, MMA done +56; TMEM slot +64
     const uint32_t bars = base + oVec + kCvVecFloats * 4;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(g + oVec + kCvVecFloats * 4 + 64);
@@ -1202,42 +1201,40 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     const VidInfo vi = vid_info(cu_rows, tile.x);
     const int r0 = tile.y;
     const int win0 = vi.row0 + r0 - 16;                                     // packed row of window row 0 (may be < 0)
-    if (tid < kHeads) s_vmax[tid] = 0u;
     __syncthreads();                                                        // (everyone has left the previous tile)
-    // inverse v plane scales of the window rows, all heads (0 outside the video: masks the band column)
-    for (int i = tid; i < kHeads * 192; i += 320) {
-        const int hd = i / 192, j = i - hd * 192;
-        const int r = r0 - 16 + j;
-        float f = 0.f;
-        if (r >= 0 && r < vi.T && j < kConvRowsIn) {
-            f = __ldg(inv + (size_t)(vi.row0 + r) * 24 + 16 + hd);
-            atomicMax(&s_vmax[hd], __float_as_uint(f));
+    // Per head (a warp each): inverse v plane scales of the window rows (0 outside the video: masks the band column),
+    // their maximum, the band exponent e_c that puts the largest band entry into [2^14, 2^15), the band column factors
+    // 2^(e_c - sv[j]), and the head's bound on |merged|; one barrier instead of four and no shared-memory atomics
+    // (the four-phase version was 17 % of this kernel's stall samples, ncu r02w)
+    if (warp < kHeads) {
+        const int hd = warp;
+        float f[6], vmi = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int j = lane + 32 * k, r = r0 - 16 + j;
+            f[k] = (r >= 0 && r < vi.T && j < kConvRowsIn) ? __ldg(inv + (size_t)(vi.row0 + r) * 24 + 16 + hd) : 0.f;
+            vmi = fmaxf(vmi, f[k]);
         }
-        s_inv[i] = f;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        const int hd = tid >> 2, q = tid & 3;
+        vmi = warp_max(vmi);
         float l1 = 0.f, wm = 0.f;
-        for (int t = q; t < kTaps; t += 4) { const float a = fabsf(s_w[hd * kTaps + t]); l1 += a; wm = fmaxf(wm, a); }
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, 1));
-        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, 2));
-        const float vmi = __uint_as_float(s_vmax[hd]);
-        if (q == 0) {
-            const int ec = scale_exp(wm * vmi);                             // largest band entry into [2^14, 2^15)
-            s_fc[hd] = ldexpf(1.f, ec);
+        for (int t = lane; t < kTaps; t += 32) { const float a = fabsf(s_w[hd * kTaps + t]); l1 += a; wm = fmaxf(wm, a); }
+        l1 = warp_sum(l1);
+        wm = warp_max(wm);
+        const int ec = scale_exp(wm * vmi);
+        const float fc = ldexpf(1.f, ec);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_inv[hd * 192 + lane + 32 * k] = f[k] * fc;
+        if (lane == 0) {
+            s_fc[hd] = fc;
             s_ic[hd] = ldexpf(1.f, -ec);
+            s_vmax[hd] = __float_as_uint(__ldg(w_max + ((size_t)tile.x * kHeads + hd) * 2) + l1 * (32768.f * vmi));
         }
-        float bound = __ldg(w_max + ((size_t)tile.x * kHeads + hd) * 2) + l1 * (32768.f * vmi);
-        bound = warp_max(bound);
-        if (tid == 0) *s_scale = ldexpf(1.f, scale_exp(bound));
     }
     __syncthreads();
-    for (int i = tid; i < kHeads * 192; i += 320) s_inv[i] *= s_fc[i / 192];        // band column factors 2^(e_c - sv[j])
-    __syncthreads();
-    const float sc = *s_scale;
+    float bound = 0.f;
+#pragma unroll
+    for (int hd = 0; hd < kHeads; ++hd) bound = fmaxf(bound, __uint_as_float(s_vmax[hd]));
+    const float sc = ldexpf(1.f, scale_exp(bound));
 
     if (warp == 8) {
         if (lane == 0) {
