@@ -283,12 +283,17 @@ a3v_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     __shared__ int s_item;
     if (warp == 16) tmem_alloc(bars + 96, 512);
     bool first_item = true;
+    int next_item = 0;                                                      // thread 0: ticket drawn one item ahead
     uint32_t tmem_base = 0;
     for (;;) {
-    if (tid == 0) s_item = ticket != nullptr ? (int)atomicAdd(ticket, 1u) : (first_item ? (int)blockIdx.x : n_items);
+    // the ticket of the NEXT item is drawn while this one streams (the atomic's round trip was 7 % of this kernel's stall
+    // samples when every item began with it, ncu r02w); tickets past the end are harmless
+    if (tid == 0) s_item = ticket != nullptr ? (first_item ? (int)atomicAdd(ticket, 1u) : next_item)
+                                             : (first_item ? (int)blockIdx.x : n_items);
     __syncthreads();                                                        // (also: everyone has left the previous item)
     const int item = s_item;
     if (item >= n_items) break;
+    if (tid == 0 && ticket != nullptr) next_item = (int)atomicAdd(ticket, 1u);
     const int pair = item & 3, v = (item >> 2) % n_videos, zi = (item >> 2) / n_videos;
     const VidInfo vi = vid_info(cu_rows, v);
     const int tiles_all = (vi.T + 63) / 64;
@@ -813,7 +818,7 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                     st4(dst + 4, o1);
                 }
             }
-            named_bar_sync(bar_id, 64);                                     // the rows are free for P again
+            ok = named_bar_and(bar_id, 64, ok);                             // the rows are free for P again
         };
         for (int i = 0; i < n_tiles && ok; ++i) {
             const int s = i & 1;
@@ -1372,7 +1377,7 @@ value_conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
                     if (write_lo) *reinterpret_cast<uint4*>(m_lo + oo) = *reinterpret_cast<uint4*>(ll);
                 }
             }
-            named_bar_sync(bar_id, 64);                                     // region free for the next head
+            ok = named_bar_and(bar_id, 64, ok);                             // region free for the next head
         }
     }
     }   // tiles of this CTA

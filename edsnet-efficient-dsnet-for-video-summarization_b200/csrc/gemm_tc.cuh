@@ -114,6 +114,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void named_bar_sync_gemm(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// barrier over `threads` threads that also ANDs a predicate: the warps that share a read-out region leave their tile loop
+// together when one of them has seen a pipeline wait time out (a lone leaver would hang its partner at the next barrier)
+__device__ __forceinline__ bool named_bar_and(int id, int threads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %3, 0;\n\t"
+        "bar.red.and.pred p, %1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(id), "r"(threads), "r"((uint32_t)pred)
+        : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -871,7 +885,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                     if (i < 2) lnwide2_load_res(pre.x[i], row0 + rbase + 4 * (i + 2) + rsub, gcol, M, ep);
                 }
-                named_bar_sync_gemm(2 + region, 64);                     // region free for the next tile's phase A
+                ok = named_bar_and(2 + region, 64, ok);                  // region free for the next tile's phase A
                 // row sums over the eight lanes of a row by recursive halving: lane c ends with iteration (c & 1) * 2 + ((c >> 1) & 1)
                 {
                     const bool b0 = (c & 1) != 0, b1 = (c & 2) != 0;
