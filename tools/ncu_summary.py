@@ -17,6 +17,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum", "smsp__cycles_active.avg",
         "sm__cycles_elapsed.avg.per_second", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg",
+        "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
