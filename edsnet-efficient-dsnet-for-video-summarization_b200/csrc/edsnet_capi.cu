@@ -144,6 +144,8 @@ int gemm_dispatch(int precision, int epilogue, const float* A, const void* A16, 
     if (epilogue == EPI_RES_LNPLANES &&
         (precision == EDSNET_PREC_FP32 || N != kFeat || !bias || !res || !aux || !aux2 || !aux3))
         return fail(EDSNET_E_ARG, "gemm: the LayerNorm-plane epilogue needs a tcgen05 precision, N = 1024 and its operands");
+    if (epilogue == EPI_RES_LNPLANES && ((reinterpret_cast<uintptr_t>(res) & 31u) || (reinterpret_cast<uintptr_t>(C) & 31u)))
+        return fail(EDSNET_E_ARG, "gemm: the LayerNorm-plane epilogue reads the residual with 32-byte loads: res and C must be 32-byte aligned");
     if (epilogue == EPI_LN_FOLD && (precision == EDSNET_PREC_FP32 || K != kFeat || !bias || !aux || !aux2))
         return fail(EDSNET_E_ARG, "gemm: the LayerNorm-fold epilogue needs a tcgen05 precision, K = 1024 and its operands");
     if (epilogue == 4 && (precision == EDSNET_PREC_FP32 || !aux || N != kQkvCols))
@@ -510,6 +512,9 @@ int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsn
     rc = check_batch(batch);
     if (rc) return rc;
     if (!w || !x || !pred_cls || !pred_loc || !workspace) return fail(EDSNET_E_ARG, "forward: NULL operand");
+    // the kernels read x and the workspace with 32-byte vector loads (rows are 4 KB, so any row of an aligned buffer is fine)
+    if ((reinterpret_cast<uintptr_t>(x) & 31u) || (reinterpret_cast<uintptr_t>(workspace) & 31u))
+        return fail(EDSNET_E_ARG, "forward: x and workspace must be 32-byte aligned");
     edsnet_workspace_layout L;
     const size_t need = edsnet_workspace_bytes(cfg, batch->total_rows, batch->n_videos, &L);
     if (workspace_bytes < need) return fail(EDSNET_E_WORKSPACE, "forward: workspace too small");

@@ -158,7 +158,8 @@ size_t edsnet_workspace_bytes(const edsnet_config* cfg, int32_t total_rows, int3
                               edsnet_workspace_layout* layout);
 
 /* DSNet.forward (dsnet.py:100-115) over a packed batch: x [dev][total_rows][1024] fp32 ->
- * pred_cls [dev][total_rows][S] (sigmoid scores), pred_loc [dev][total_rows][S][2] (centre, log-width offsets). */
+ * pred_cls [dev][total_rows][S] (sigmoid scores), pred_loc [dev][total_rows][S][2] (centre, log-width offsets).
+ * x and workspace must be 32-byte aligned (EDSNET_E_ARG otherwise). */
 int edsnet_forward(const edsnet_config* cfg, const edsnet_weights* w, const edsnet_batch* batch,
                    const float* x, float* pred_cls, float* pred_loc,
                    void* workspace, size_t workspace_bytes, void* stream);

@@ -466,6 +466,10 @@ def test_error_surface():
     lib = _capi.lib()
     assert lib.edsnet_forward(None, None, None, None, None, None, None, 0, None) == _capi.E_ARG
     assert "config" in _capi.last_error()
+    # the kernels read x with 32-byte vector loads: a misaligned view is refused, not faulted on
+    buf = torch.zeros(8 * 1024 + 1, device=DEV)
+    with pytest.raises(RuntimeError, match="aligned"):
+        make_model(p, [4], 2, "fp16x2", DEV)(buf[1:].view(1, 8, 1024))
 
 
 def test_pipeline_from_host_buffers():
