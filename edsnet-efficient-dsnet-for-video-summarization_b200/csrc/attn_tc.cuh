@@ -701,20 +701,48 @@ attn_out_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     }
     if (warp == 8) tmem_alloc(bars + 64, 256);
     __syncthreads();
-    float wrow[64];
-    if (tid < 64) {
-        float kl[64];
-        load_row64(kl, k_land + hoff + tid * 64);
-        const int e = scale_exp(absmax64(kl));
-        inv_kl[tid] = ldexpf(1.f, -e);
-        store_row64(g + oK, g + oK + 8192, tid, kl, ldexpf(1.f, e));
-    } else if (tid < 128) {
-        load_row64(wrow, w_mat + hoff + (tid - 64) * 64);
-        atomicMax(s_wmax, __float_as_uint(absmax64(wrow)));
+    // Prologue: k_land and W (64 x 64 fp32 each, L2 resident) -> operand planes.  All 256 row threads take part and the
+    // loads are coalesced (float4 number tid + 256 k: a matrix row = 16 consecutive lanes, its maximum one half-warp
+    // reduction); one thread per row with 16 strided float4 loads each kept 192 threads idle behind 128 and was 9 % of
+    // this kernel's stall samples (ncu r02w).
+    float4 kv[4], wv[4];
+    auto put4 = [&](unsigned char* hi, unsigned char* lo, int idx, const float4& x, float mul) {
+        const int row = idx >> 4, c4 = idx & 15;
+        const float v0 = x.x * mul, v1 = x.y * mul, v2 = x.z * mul, v3 = x.w * mul;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1), h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+        __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+        __half2 ll[2] = {__halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1))),
+                         __halves2half2(__float2half_rn(v2 - __half2float(h2)), __float2half_rn(v3 - __half2float(h3)))};
+        const uint32_t off = sw128_off(row, c4 >> 1) + (uint32_t)((c4 & 1) * 8);
+        *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(ll);
+    };
+    if (tid < 256) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            kv[k] = ldg4(k_land + hoff + (size_t)(tid + 256 * k) * 4);
+            wv[k] = ldg4(w_mat + hoff + (size_t)(tid + 256 * k) * 4);
+        }
+        float wm = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + 256 * k;
+            const float mx = half_warp_max(fmaxf(fmaxf(fabsf(kv[k].x), fabsf(kv[k].y)), fmaxf(fabsf(kv[k].z), fabsf(kv[k].w))));
+            const int e = scale_exp(mx);
+            if ((tid & 15) == 0) inv_kl[idx >> 4] = ldexpf(1.f, -e);
+            put4(g + oK, g + oK + 8192, idx, kv[k], ldexpf(1.f, e));
+            wm = fmaxf(wm, fmaxf(fmaxf(fabsf(wv[k].x), fabsf(wv[k].y)), fmaxf(fabsf(wv[k].z), fabsf(wv[k].w))));
+        }
+        wm = warp_max(wm);
+        if (lane == 0) atomicMax(s_wmax, __float_as_uint(wm));
     }
     __syncthreads();
     const int ew = scale_exp(__uint_as_float(*s_wmax));
-    if (tid >= 64 && tid < 128) store_row64(g + oW, g + oW + 8192, tid - 64, wrow, ldexpf(1.f, ew));
+    if (tid < 256) {
+        const float wmul = ldexpf(1.f, ew);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) put4(g + oW, g + oW + 8192, tid + 256 * k, wv[k], wmul);
+    }
     // max|W| of this (video, head): every output row is a convex combination of W's rows, so this bounds the
     // attention part of `merged` (value_conv_kernel derives the operand-plane scale from it)
     if (tid == 0 && w_max_out != nullptr && blockIdx.z == 0) w_max_out[((size_t)v * kHeads + h) * 2] = __uint_as_float(*s_wmax);
