@@ -461,7 +461,7 @@ int edsnet_debug_stage_times(double* ms_sum, int32_t* launches, int32_t n) {
 }
 
 int edsnet_debug_set_tc_variant(int32_t variant) {
-    if (variant != 0 && variant != 3 && variant != 4 && variant != 6) return fail(EDSNET_E_ARG, "tc variant must be 0, 3, 4 or 6");
+    if (variant < 0 || variant > 9 || variant == 1 || variant == 2) return fail(EDSNET_E_ARG, "tc variant must be 0 or 3..9");
     tc::variant_ref() = variant;
     return EDSNET_OK;
 }

@@ -1152,9 +1152,13 @@ template <int STAGES, int EPI>
 cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
                         cudaStream_t st, std::string* msg);
 
+template <int STAGES, int EPI>
+cudaError_t launch_pair2(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
+                         cudaStream_t st, std::string* msg);
+
 // variant (profiling knob, edsnet_debug_set_tc_variant / EDSNET_TC_VARIANT): 0 = default (128 x 128 tiles, BK 64, four
 // accumulators; two double-buffered accumulators when K <= 512), 3 = two double-buffered accumulators for every K,
-// 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh); two-pass mode: 6 = two accumulator pairs, 7 = to_out with
+// 4 = CTA pairs (cta_group::2, 256 x 128 pair tiles, gemm_tc2.cuh); two-pass mode: 5 = CTA pairs (gemm_tc2p_kernel), 6 = two accumulator pairs, 7 = to_out with
 // the 16-column slab epilogue and a four-deep ring, 8 = to_out with the eight-warp wide read-out, 9 = to_qkv with a three-deep
 // ring (costs 4 %).  A BK 32 / 64-byte-swizzle variant and a 128 x 64
 // tile variant were measured slower (profiles/r01e_gemm_variants.log) and removed.
@@ -1178,6 +1182,8 @@ cudaError_t launch_shape(const __half* A16, const __half* B16, float* C, int M, 
                 if (variant != 7)
                     return variant == 8 ? launch_variant<128, 64, 3, 2, EPI, 2, 1>(A16, B16, C, M, N, K, ep, st, msg)
                                         : launch_variant<128, 64, 3, 2, EPI, 2, 2>(A16, B16, C, M, N, K, ep, st, msg);
+            if constexpr (EPI <= EPI_QKV_PLANES)      // two-pass CTA pairs (gemm_tc2.cuh)
+                if (variant == 5) return launch_pair2<6, EPI>(A16, B16, C, M, N, K, ep, st, msg);
             if constexpr (EPI == EPI_QKV_PLANES)      // probe: the same kernel with a three-deep ring
                 if (variant == 9) return launch_variant<128, 64, 3, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);
             if (K <= 512 || variant != 6) return launch_variant<128, 64, 4, 2, EPI, 2>(A16, B16, C, M, N, K, ep, st, msg);

@@ -245,4 +245,176 @@ cudaError_t launch_pair(const __half* A16, const __half* B16, float* C, int M, i
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-pass CTA-pair kernel (round 2).  The one-CTA two-pass kernel moves 96 KB through an SM's shared memory per 64-wide K
+// block (48 KB of TMA fill + 48 KB of operand reads) for 4 x 128 tensor cycles: at 128 B per cycle that is 768 cycles, and
+// 715-760 is what to_qkv measures.  In a pair the N = 256 right operand [B_hi | B_lo] splits exactly along its planes:
+// the leader holds the 128 rows of B_hi, its peer the 128 rows of B_lo, each CTA its own 128 rows of A_hi; ONE
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16: 128 cycles per SM, so the ~90-cycle issue interval that capped the
+// three-instruction kernel above stays hidden) leaves every CTA with the same (main | cross) accumulator pair as the
+// one-CTA kernel, so the epilogues are shared.  32 KB per CTA and K block (64 KB through shared memory), six stages,
+// accumulator pair double-buffered in TMEM.
+// ---------------------------------------------------------------------------------------------------------------
+template <int STAGES>
+struct Tc2pCfg {
+    static constexpr int BM = 128, BN = 128, BK = 64;      // per-CTA output tile; the pair covers 256 x 128
+    static constexpr int kATile = BM * BK * 2;             // 16 KB: A_hi rows of this CTA
+    static constexpr int kBTile = BN * BK * 2;             // 16 KB: B_hi (leader) or B_lo (peer) rows of the n tile
+    static constexpr int kStageBytes = kATile + kBTile;    // 32 KB per CTA
+    static constexpr int kTmemCols = 512;                  // two (main | cross) pairs
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kThreads = 320;
+    static constexpr int kScratchOff = STAGES * kStageBytes + 256;
+    static constexpr int kSmemBytes = kScratchOff + kEpiWarps * kEpiScratchWarp + 1024;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gemm_tc2p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 float* __restrict__ C, int M, int N, int K, GemmEpiArgs ep) {
+    using Cfg = Tc2pCfg<STAGES>;
+    constexpr int BN = Cfg::BN, BK = Cfg::BK;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // same offset in both CTAs of the pair
+    const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // used in the leader only
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };   // used in the leader only
+    constexpr int kSlotOff = 8 * (2 * STAGES + 4);
+    const uint32_t tmem_slot = bar_base + kSlotOff;
+    unsigned char* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * Cfg::kStageBytes + kSlotOff);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int nk = K / BK;
+    const int tiles_n = N / BN;
+    const int n_tiles = tiles_n * ((M + 2 * Cfg::BM - 1) / (2 * Cfg::BM));    // 256 x 128 pair tiles
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * Cfg::kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                    // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer (both CTAs): own A_hi rows; the leader B_hi, the peer B_lo ----
+            int it = 0;
+            bool ok = true;
+            for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+                const int m0 = (tile / tiles_n) * (2 * Cfg::BM) + (int)rank * Cfg::BM;
+                const int nb0 = (tile % tiles_n) * BN + (int)rank * N;        // plane p of B starts at row p * N
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+                    const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                    const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);     // both CTAs' bytes
+                    tma_load_2d_pair(st, &mapA, lead_full, kb * BK, m0);
+                    tma_load_2d_pair(st + Cfg::kATile, &mapB, lead_full, kb * BK, nb0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ---- MMA issuer (leader CTA): D[256 x 256] = A_hi [B_hi | B_lo]^T over both CTAs' TMEM ----
+            constexpr uint32_t idesc = make_idesc(2 * Cfg::BM, 2 * BN);
+            bool ok = true;
+            int it = 0, t = 0;
+            for (int tile = pair; tile < n_tiles && ok; tile += n_pairs, ++t) {
+                const int buf = t & 1;
+                ok = mbar_wait(tempty_bar(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u);      // both epilogues have drained it
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * BN);
+                for (int kb = 0; kb < nk && ok; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    ok = mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * Cfg::kStageBytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t koff = k * 32;
+                        umma_f16_pair(acc, make_smem_desc<BK>(st + koff), make_smem_desc<BK>(st + Cfg::kATile + koff), idesc,
+                                      (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_pair(empty_bar(s));
+                }
+                umma_commit_pair(tfull_bar(buf));
+            }
+        }
+    } else {
+        // ---- epilogue (both CTAs): this CTA's 128 rows of the pair tile ----
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        float* scratch = reinterpret_cast<float*>(gen_base + Cfg::kScratchOff + (warp - 2) * kEpiScratchWarp);
+        bool ok = true;
+        int t = 0;
+        for (int tile = pair; tile < n_tiles && ok; tile += n_pairs, ++t) {
+            const int buf = t & 1;
+            const int m0 = (tile / tiles_n) * (2 * Cfg::BM) + (int)rank * Cfg::BM;
+            const int n0 = (tile % tiles_n) * BN;
+            ok = mbar_wait(tfull_bar(buf), (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + (uint32_t)(buf * 2 * BN) + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64);
+            const int nc0 = n0 + chalf * 64;
+            float v[64];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(t0 + (uint32_t)c0, r0);
+                tmem_ld16_nowait(t0 + (uint32_t)BN + (uint32_t)c0, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c0 + j] = __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar(buf), 0));
+            if (EPI == EPI_QKV_PLANES) epi_store_planes(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+            else epi_store_f32<EPI>(v, m0 + quarter * 32, lane, nc0, M, N, C, ep, scratch);
+        }
+    }
+    // neither CTA may leave (or free TMEM) while the other still reads its shared memory / signals its barriers
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+template <int STAGES, int EPI>
+cudaError_t launch_pair2(const __half* A16, const __half* B16, float* C, int M, int N, int K, GemmEpiArgs ep,
+                         cudaStream_t st, std::string* msg) {
+    using Cfg = Tc2pCfg<STAGES>;
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, A16, 2ull * M, K, Cfg::BK, Cfg::BM, msg)) return cudaErrorUnknown;
+    if (!make_map(&mapB, B16, 2ull * N, K, Cfg::BK, Cfg::BN, msg)) return cudaErrorUnknown;
+    auto kern = gemm_tc2p_kernel<STAGES, EPI>;
+    static const char tag = 0;                      // one per template instantiation
+    if (DeviceOnce once_{&tag}) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+    }
+    const int n_tiles = (N / Cfg::BN) * ((M + 2 * Cfg::BM - 1) / (2 * Cfg::BM));
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(mapA, mapB, C, M, N, K, ep);
+    return cudaGetLastError();
+}
+
 }  // namespace tc
