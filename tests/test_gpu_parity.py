@@ -116,6 +116,41 @@ def test_gemm_kernel_variants(variant):
         capi.check(lib.edsnet_debug_set_tc_variant(0))
 
 
+def test_two_pass_pair_kernel():
+    """The two-pass CTA-pair kernel (cta_group::2: B_hi in the leader, B_lo in its peer; EDSNET_TC_VARIANT=5) computes the
+    same products as the one-CTA two-pass kernel (ragged M, odd numbers of pair tiles, all fp32 epilogues)."""
+    capi, lib = _lib()
+    capi.check(lib.edsnet_debug_set_tc_variant(5))
+    try:
+        for M, N, K, epi in [(1000, 1536, 1024, 1), (333, 1024, 512, 3), (4096, 128, 1024, 2), (77, 1536, 1024, 0),
+                             (257, 128, 128, 0)]:
+            _gemm_check("fp16x2", M, N, K, epi)
+    finally:
+        capi.check(lib.edsnet_debug_set_tc_variant(0))
+
+
+@pytest.mark.parametrize("variant", [7, 8])
+def test_to_out_read_out_variants_agree(variant):
+    """to_out in the two-pass mode: the 16-column slab epilogue (7) and the eight-warp wide read-out (8) behind the
+    profiling knob give the default (sixteen warps in pairs) kernel's scores up to the order of the LayerNorm row sums."""
+    capi, lib = _lib()
+    g, x, p = golden_case(FWD, CASES[0])
+    scales = [int(s) for s in g["scales"]]
+    model = make_model(p, scales, int(g["fc_depth"]), "fp16x2", DEV)
+    xd = x[None].to(DEV)
+    with torch.no_grad():
+        cls0, loc0 = model(xd)
+        capi.check(lib.edsnet_debug_set_tc_variant(variant))
+        try:
+            cls1, loc1 = model(xd)
+        finally:
+            capi.check(lib.edsnet_debug_set_tc_variant(0))
+    assert lib.edsnet_debug_tc_status(1) == 0
+    assert orc.rel_l2(cls1.cpu().numpy(), cls0.cpu().numpy()) < 2e-6
+    assert orc.rel_l2(loc1.cpu().numpy(), loc0.cpu().numpy()) < 2e-6
+    assert orc.rel_l2(loc1.cpu().numpy(), g["pred_loc"]) < TOL["fp16x2"]
+
+
 # ------------------------------------------------------------------------------------------------ forward
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16x2"])
 @pytest.mark.parametrize("name", CASES)
