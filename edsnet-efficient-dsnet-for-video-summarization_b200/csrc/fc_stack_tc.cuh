@@ -16,7 +16,7 @@ namespace tc {
 
 constexpr int kFcTile = 128;                                  // rows per warpgroup tile
 constexpr int kFcPlane = 128 * 128 * 2;                       // bytes of one fp16 128x128 plane
-// W hi | W lo | A hi (wg0) | A lo (wg0) | A hi (wg1) | A lo (wg1) | vectors | barriers
+// W (K half 0: hi | lo, K half 1: hi | lo) | A hi (wg0) | A lo (wg0) | A hi (wg1) | A lo (wg1) | vectors | barriers
 constexpr int kFcSlots = 5;                                   // LayerNorm sums (2, by layer parity), row max, head dots (2)
 constexpr int kFcXchBytes = 2 * kFcSlots * 2 * 128 * 2 * 4;    // [group][slot][half][row][2] floats
 constexpr int kFcVecFloats = 7 * 128;                         // wscale bias gamma beta | w_cls w_loc0 w_loc1
@@ -58,7 +58,7 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t w_hi = base, w_lo = base + kFcPlane;
+    const uint32_t w_hi = base;                                             // K half h at h * 32 KB: hi rows, then lo rows
     float* vec = reinterpret_cast<float*>(gbase + 6 * kFcPlane);          // wscale[128] bias[128] gamma[128] beta[128]
     float* xch = vec + kFcVecFloats;                                        // [group][slot][half][row][2]
     const uint32_t bar0 = base + 6 * kFcPlane + kFcVecFloats * 4 + kFcXchBytes;   // mbarrier per group, then the TMEM slot
@@ -73,7 +73,8 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     for (int idx = tid; idx < 2 * 128 * 16; idx += 512) {
         const int plane = idx >> 11, r = (idx >> 4) & 127, c16 = idx & 15;
         const uint4 val = __ldg(reinterpret_cast<const uint4*>(w_planes + (size_t)plane * 128 * 128 + r * 128 + c16 * 8));
-        *reinterpret_cast<uint4*>(gbase + plane * kFcPlane + fc_plane_off(r, c16)) = val;
+        // per K half: [W_hi rows | W_lo rows], 16 KB each, so that [W_hi | W_lo] is ONE 256-row right operand
+        *reinterpret_cast<uint4*>(gbase + (c16 >> 3) * 32768 + plane * 16384 + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = val;
     }
     if (tid < 128) {
         vec[tid] = __ldg(w_inv_scale + tid);
@@ -103,7 +104,7 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
     unsigned char* a_lo_ptr = a_hi_ptr + kFcPlane;
     const uint32_t my_bar = bar0 + 8u * grp;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    constexpr uint32_t idesc = make_idesc(128, 128);
+    constexpr uint32_t idesc = make_idesc(128, 128), idesc2 = make_idesc(128, 256);
     const int n_tiles = (rows + kFcTile - 1) / kFcTile;
     // plane scale of every LayerNorm output: |LN(x)| <= sqrt(127) max|gamma| + max|beta|
     float gmax = 0.f, bmax = 0.f;
@@ -166,13 +167,16 @@ fc_stack_tc_kernel(const float* __restrict__ u_in, const __half* __restrict__ w_
             if (gt == 0) {
                 tc_fence_after();
 #pragma unroll
+                // A_hi [W_hi | W_lo]^T as ONE N = 256 instruction into the adjacent (main | cross) accumulators, then
+                // A_lo W_hi^T into the cross half: 16 instead of 24 instructions per layer (the tensor core takes one
+                // instruction per ~90 cycles from an SM, DESIGN 5b, and an N = 128 instruction is only 64 cycles of work)
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t koff = (uint32_t)((k >> 2) * 16384 + (k & 3) * 32);
+                    const uint32_t woff = (uint32_t)((k >> 2) * 32768 + (k & 3) * 32);
                     const uint64_t dah = make_smem_desc<64>(a_hi + koff), dal = make_smem_desc<64>(a_lo + koff);
-                    const uint64_t dbh = make_smem_desc<64>(w_hi + koff), dbl = make_smem_desc<64>(w_lo + koff);
-                    umma_f16(acc_main, dah, dbh, idesc, k != 0 ? 1u : 0u);
-                    umma_f16(acc_lo, dah, dbl, idesc, k != 0 ? 1u : 0u);
-                    umma_f16(acc_lo, dal, dbh, idesc, 1u);
+                    const uint64_t dbw = make_smem_desc<64>(w_hi + woff);
+                    umma_f16(acc_main, dah, dbw, idesc2, k != 0 ? 1u : 0u);
+                    umma_f16(acc_lo, dal, dbw, idesc, 1u);
                 }
                 umma_commit(my_bar);
             }
